@@ -1,0 +1,359 @@
+"""ctypes binding of include/hpp_b200.h (plumbing for tests and bench.py; not a compute path)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VARIANT_RS, VARIANT_DUBINS = 0, 1
+# GL/config/reeds_config.yaml:1-9 -- maxSteerAngle, wheelBase, axleToFront, axleToBack, width, pathLength, step_car
+DEFAULT_PARAMS = (0.6, 2.75, 1.1, 1.2, 1.9, 4.0, 1.0)
+MAX_COMMANDS, MAX_SIM = 26, 8
+
+
+class HppError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("max_steer", "wheel_base", "axle_to_front", "axle_to_back", "width",
+                                          "path_length", "step_car")]
+
+
+class QuirkReport(C.Structure):
+    _fields_ = [("reachable", C.c_uint64), ("max_cost", C.c_double), ("h1_progress_break", C.c_int32),
+                ("h2_bucket_clamp", C.c_int32), ("rounds", C.c_uint32), ("tile_visits", C.c_uint32)]
+
+
+class Node(C.Structure):
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("heading", C.c_double), ("cost", C.c_double),
+                ("steer", C.c_double), ("direction", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Child(C.Structure):
+    _fields_ = [("traj", (C.c_double * 5) * MAX_SIM), ("cost", C.c_double), ("steer", C.c_double),
+                ("direction", C.c_int32), ("valid", C.c_int32)]
+
+
+class Shot(C.Structure):
+    _fields_ = [("found", C.c_int32), ("n_paths", C.c_int32), ("chosen", C.c_int32), ("n_samples", C.c_int32),
+                ("cost", C.c_double), ("sample_offset", C.c_uint64)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("iterations", C.c_int32), ("via_shot", C.c_int32), ("status", C.c_int32),
+                ("cost", C.c_double), ("traj_offset", C.c_uint64)]
+
+
+NODE_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("heading", "f8"), ("cost", "f8"), ("steer", "f8"),
+                       ("direction", "i4"), ("pad_", "i4")])
+CHILD_DTYPE = np.dtype([("traj", "f8", (MAX_SIM, 5)), ("cost", "f8"), ("steer", "f8"), ("direction", "i4"),
+                        ("valid", "i4")])
+SHOT_DTYPE = np.dtype([("found", "i4"), ("n_paths", "i4"), ("chosen", "i4"), ("n_samples", "i4"), ("cost", "f8"),
+                       ("sample_offset", "u8")])
+PLAN_DTYPE = np.dtype([("n_states", "i4"), ("iterations", "i4"), ("via_shot", "i4"), ("status", "i4"),
+                       ("cost", "f8"), ("traj_offset", "u8")])
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(HERE, "libhpp_b200.so")
+
+
+def lib():
+    """Load libhpp_b200.so.  Fails loudly when it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise HppError(f"{p} is missing: run hybrid_path_planning_b200/csrc/build.sh (or __graft_entry__.build())")
+        L = C.CDLL(p)
+        vp, i32, u32, u64, dbl, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_double, C.c_size_t
+        sigs = {
+            "hpp_ctx_create": [C.c_int, C.POINTER(vp)],
+            "hpp_ctx_destroy": [vp],
+            "hpp_ctx_sync": [vp],
+            "hpp_map_create": [vp, vp, u32, u32, C.c_float, dbl, dbl, C.POINTER(Params), C.POINTER(vp)],
+            "hpp_map_create_dev": [vp, vp, u32, u32, C.c_float, dbl, dbl, C.POINTER(Params), C.POINTER(vp)],
+            "hpp_map_destroy": [vp],
+            "hpp_map_update": [vp, vp],
+            "hpp_map_update_dev": [vp, vp],
+            "hpp_map_layers": [vp, vp, vp],
+            "hpp_map_layers_dev": [vp, C.POINTER(vp), C.POINTER(vp)],
+            "hpp_map_cells": [vp, vp, sz, vp, vp],
+            "hpp_inflate": [vp, vp, u32, u32, dbl, dbl, vp],
+            "hpp_inflate_dev": [vp, vp, u32, u32, dbl, dbl, vp],
+            "hpp_collide_circles": [vp, vp, sz, vp],
+            "hpp_collide_circles_dev": [vp, vp, sz, vp],
+            "hpp_collide_sat": [vp, vp, sz, vp],
+            "hpp_collide_sat_dev": [vp, vp, sz, vp],
+            "hpp_heuristic_rs": [vp, i32, i32, i32, i32, vp, C.POINTER(QuirkReport)],
+            "hpp_heuristic_dubins": [vp, i32, i32, vp, C.POINTER(QuirkReport)],
+            "hpp_heuristic_batch_dev": [vp, C.c_int, vp, sz, vp, vp],
+            "hpp_expand": [vp, C.c_int, vp, sz, vp],
+            "hpp_expand_dev": [vp, C.c_int, vp, sz, vp],
+            "hpp_rs_shot": [vp, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)],
+            "hpp_dubins_shot": [vp, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)],
+            "hpp_rs_all_paths": [vp, vp, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, sz],
+            "hpp_dubins_path": [vp, vp, vp, dbl, dbl, vp, vp, vp, vp, sz],
+            "hpp_plan_batch": [vp, C.c_int, vp, vp, sz, vp, vp, sz, C.POINTER(sz)],
+        }
+        for name, args in sigs.items():
+            if hasattr(L, name):
+                f = getattr(L, name)
+                f.argtypes = args
+                f.restype = C.c_int
+        L.hpp_last_error.argtypes = [vp]
+        L.hpp_last_error.restype = C.c_char_p
+        L.hpp_ctx_stream.argtypes = [vp]
+        L.hpp_ctx_stream.restype = vp
+        L.hpp_ctx_launch_count.argtypes = [vp]
+        L.hpp_ctx_launch_count.restype = u64
+        L.hpp_version.restype = C.c_char_p
+        L.hpp_num_commands.argtypes = [C.POINTER(Params), C.c_int]
+        L.hpp_num_commands.restype = i32
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    """host numpy array or raw device address -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (device memory owned by torch: plumbing)
+        return a.data_ptr()
+    return int(a)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        st = self.L.hpp_ctx_create(device, C.byref(h))
+        if st != 0:
+            raise HppError(f"hpp_ctx_create(device={device}) failed with status {st}: no usable sm_100 GPU "
+                           "(there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def check(self, st):
+        if st != 0:
+            raise HppError(f"status {st}: {self.L.hpp_last_error(self.h).decode()}")
+
+    def sync(self):
+        self.check(self.L.hpp_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.hpp_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.L.hpp_ctx_launch_count(self.h))
+
+    def inflate(self, occ, resolution, radius):
+        occ = np.ascontiguousarray(occ, np.int8)
+        H, W = occ.shape
+        out = np.empty_like(occ)
+        self.check(self.L.hpp_inflate(self.h, occ.ctypes.data, W, H, float(resolution), float(radius), out.ctypes.data))
+        return out
+
+    def inflate_dev(self, occ_dev, W, H, resolution, radius, out_dev):
+        self.check(self.L.hpp_inflate_dev(self.h, _ptr(occ_dev), W, H, float(resolution), float(radius), _ptr(out_dev)))
+
+    def rs_all_paths(self, s, g, maxc, step=1.0, max_paths=48, samples_cap=400000):
+        s3 = (C.c_double * 3)(*s)
+        g3 = (C.c_double * 3)(*g)
+        n_paths = C.c_int32(0)
+        n_seg = np.zeros(max_paths, np.int32)
+        lengths = np.zeros((max_paths, 5))
+        types = np.zeros((max_paths, 5), np.uint8)
+        tl = np.zeros(max_paths)
+        ns = np.zeros(max_paths, np.int32)
+        samples = np.zeros((samples_cap, 3))
+        self.check(self.L.hpp_rs_all_paths(self.h, s3, g3, maxc, step, max_paths, C.byref(n_paths), n_seg.ctypes.data,
+                                           lengths.ctypes.data, types.ctypes.data, tl.ctypes.data, ns.ctypes.data,
+                                           samples.ctypes.data, samples_cap))
+        out, off = [], 0
+        for k in range(n_paths.value):
+            m = int(ns[k])
+            out.append(dict(lengths=lengths[k, :n_seg[k]].copy(), types=bytes(types[k, :n_seg[k]]).decode(), L=tl[k],
+                            x=samples[off:off + m, 0].copy(), y=samples[off:off + m, 1].copy(),
+                            yaw=samples[off:off + m, 2].copy()))
+            off += m
+        return out
+
+    def dubins_path(self, s, g, curv, step=0.1, samples_cap=100000):
+        s3 = (C.c_double * 3)(*s)
+        g3 = (C.c_double * 3)(*g)
+        length = C.c_double(0)
+        mode = C.create_string_buffer(4)
+        ns = C.c_int32(0)
+        samples = np.zeros((samples_cap, 3))
+        self.check(self.L.hpp_dubins_path(self.h, s3, g3, curv, step, C.byref(length), mode, C.byref(ns),
+                                          samples.ctypes.data, samples_cap))
+        m = ns.value
+        return dict(length=length.value, mode=mode.raw[:3].decode().rstrip("\0"), x=samples[:m, 0].copy(),
+                    y=samples[:m, 1].copy(), yaw=samples[:m, 2].copy())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hpp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Map:
+    """Device-resident Grid_map (occupancy + obstacle/distance layers + per-cell tables)."""
+
+    def __init__(self, ctx, occ, resolution=0.2, origin=None, params=DEFAULT_PARAMS, device_occ=None):
+        self.ctx, self.L = ctx, ctx.L
+        self.params = Params(*params)
+        res_f = np.float32(resolution)
+        if device_occ is None:
+            occ = np.ascontiguousarray(occ, np.int8)
+            self.H, self.W = occ.shape
+        else:
+            self.W, self.H = occ  # (W, H) when the occupancy lives on the device
+        if origin is None:
+            origin = (-self.W * float(res_f) / 2.0, -self.H * float(res_f) / 2.0)
+        self.res = float(res_f)
+        self.ox, self.oy = float(origin[0]), float(origin[1])
+        h = C.c_void_p()
+        if device_occ is None:
+            st = self.L.hpp_map_create(ctx.h, occ.ctypes.data, self.W, self.H, C.c_float(float(res_f)), self.ox, self.oy,
+                                       C.byref(self.params), C.byref(h))
+        else:
+            st = self.L.hpp_map_create_dev(ctx.h, _ptr(device_occ), self.W, self.H, C.c_float(float(res_f)), self.ox,
+                                           self.oy, C.byref(self.params), C.byref(h))
+        ctx.check(st)
+        self.h = h
+        self.n = self.W * self.H
+
+    def update(self, occ):
+        occ = np.ascontiguousarray(occ, np.int8)
+        self.ctx.check(self.L.hpp_map_update(self.h, occ.ctypes.data))
+
+    def update_dev(self, occ_dev):
+        self.ctx.check(self.L.hpp_map_update_dev(self.h, _ptr(occ_dev)))
+
+    def layers(self):
+        obstacle = np.empty(self.n, np.float32)
+        distance = np.empty(self.n, np.float32)
+        self.ctx.check(self.L.hpp_map_layers(self.h, obstacle.ctypes.data, distance.ctypes.data))
+        return obstacle, distance
+
+    def layers_dev(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self.ctx.check(self.L.hpp_map_layers_dev(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def cells(self, xy):
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        cell = np.empty((len(xy), 2), np.int32)
+        flags = np.empty(len(xy), np.uint8)
+        self.ctx.check(self.L.hpp_map_cells(self.h, xy.ctypes.data, len(xy), cell.ctypes.data, flags.ctypes.data))
+        return cell, flags
+
+    def collide_circles(self, xyh):
+        xyh = np.ascontiguousarray(xyh, np.float64).reshape(-1, 3)
+        v = np.empty(len(xyh), np.uint8)
+        self.ctx.check(self.L.hpp_collide_circles(self.h, xyh.ctypes.data, len(xyh), v.ctypes.data))
+        return v
+
+    def collide_sat(self, xyh):
+        xyh = np.ascontiguousarray(xyh, np.float64).reshape(-1, 3)
+        v = np.empty(len(xyh), np.uint8)
+        self.ctx.check(self.L.hpp_collide_sat(self.h, xyh.ctypes.data, len(xyh), v.ctypes.data))
+        return v
+
+    def collide_circles_dev(self, xyh_dev, n, verdict_dev):
+        self.ctx.check(self.L.hpp_collide_circles_dev(self.h, _ptr(xyh_dev), n, _ptr(verdict_dev)))
+
+    def collide_sat_dev(self, xyh_dev, n, verdict_dev):
+        self.ctx.check(self.L.hpp_collide_sat_dev(self.h, _ptr(xyh_dev), n, _ptr(verdict_dev)))
+
+    def heuristic_rs(self, goal, start=(0, 0)):
+        cost = np.empty((self.H, self.W), np.float64)
+        rep = QuirkReport()
+        self.ctx.check(self.L.hpp_heuristic_rs(self.h, goal[0], goal[1], start[0], start[1], cost.ctypes.data,
+                                               C.byref(rep)))
+        return cost, rep
+
+    def heuristic_dubins(self, goal):
+        cost = np.empty((self.H, self.W), np.float64)
+        rep = QuirkReport()
+        self.ctx.check(self.L.hpp_heuristic_dubins(self.h, goal[0], goal[1], cost.ctypes.data, C.byref(rep)))
+        return cost, rep
+
+    def heuristic_batch_dev(self, variant, goals, cost_dev, want_reports=False):
+        goals = np.ascontiguousarray(goals, np.int32).reshape(-1, 2)
+        reps = (QuirkReport * len(goals))() if want_reports else None
+        self.ctx.check(self.L.hpp_heuristic_batch_dev(self.h, variant, goals.ctypes.data, len(goals), _ptr(cost_dev),
+                                                      C.cast(reps, C.c_void_p) if reps is not None else None))
+        return reps
+
+    def num_commands(self, variant):
+        return int(self.L.hpp_num_commands(C.byref(self.params), variant))
+
+    def expand(self, variant, parents):
+        """parents: structured array NODE_DTYPE -> children [n, n_cmd] CHILD_DTYPE"""
+        parents = np.ascontiguousarray(parents, NODE_DTYPE)
+        nc = self.num_commands(variant)
+        kids = np.zeros((len(parents), nc), CHILD_DTYPE)
+        self.ctx.check(self.L.hpp_expand(self.h, variant, parents.ctypes.data, len(parents), kids.ctypes.data))
+        return kids
+
+    def _shot(self, fn, starts, goals, samples_cap):
+        starts = np.ascontiguousarray(starts, NODE_DTYPE)
+        goals = np.ascontiguousarray(goals, np.float64).reshape(-1, 3)
+        stride = 0 if len(goals) == 1 else 3
+        shots = np.zeros(len(starts), SHOT_DTYPE)
+        samples = np.zeros((samples_cap, 5))
+        used = C.c_size_t(0)
+        self.ctx.check(fn(self.h, starts.ctypes.data, len(starts), goals.ctypes.data, stride, shots.ctypes.data,
+                          samples.ctypes.data, samples_cap, C.byref(used)))
+        return shots, samples[:used.value]
+
+    def rs_shot(self, starts, goals, samples_cap=1 << 20):
+        return self._shot(self.L.hpp_rs_shot, starts, goals, samples_cap)
+
+    def dubins_shot(self, starts, goals, samples_cap=1 << 20):
+        return self._shot(self.L.hpp_dubins_shot, starts, goals, samples_cap)
+
+    def plan_batch(self, variant, starts, goals, traj_cap=1 << 22):
+        starts = np.ascontiguousarray(starts, np.float64).reshape(-1, 3)
+        goals = np.ascontiguousarray(goals, np.float64).reshape(-1, 3)
+        plans = np.zeros(len(starts), PLAN_DTYPE)
+        traj = np.zeros((traj_cap, 5))
+        used = C.c_size_t(0)
+        self.ctx.check(self.L.hpp_plan_batch(self.h, variant, starts.ctypes.data, goals.ctypes.data, len(starts),
+                                             plans.ctypes.data, traj.ctypes.data, traj_cap, C.byref(used)))
+        return plans, traj[:used.value]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hpp_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_nodes(xyh, cost=0.0, steer=0.0, direction=1):
+    xyh = np.asarray(xyh, np.float64).reshape(-1, 3)
+    a = np.zeros(len(xyh), NODE_DTYPE)
+    a["x"], a["y"], a["heading"] = xyh[:, 0], xyh[:, 1], xyh[:, 2]
+    a["cost"], a["steer"], a["direction"] = cost, steer, direction
+    return a

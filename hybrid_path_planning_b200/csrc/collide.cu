@@ -1,0 +1,113 @@
+// collide.cu -- K4 (circle footprint over the distance layer) and K5 (SAT footprint over the occupancy)
+// batch kernels.  See collide.cuh for the reference citations.
+//
+// K4: one thread per pose, the 4 circles in the reference's order with its early exit.  Poses stream in as
+//     3 doubles (24 B), the verdict streams out as 1 byte; the up-to-16 float taps are gathers into the
+//     distance layer served by L2/HBM.  Algorithmic bytes: 24 + 1 + 4*4*4 = 89 B per pose.
+// K5: one warp per pose (window rows across lanes, bit-packed occupancy), 8 poses per CTA.
+#include "collide.cuh"
+
+__global__ void __launch_bounds__(256) collide_circles_kernel(hpp_geom g, circ_consts cc,
+                                                              const float *__restrict__ dist,
+                                                              const double *__restrict__ xyh, size_t n,
+                                                              uint8_t *__restrict__ verdict) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double x = xyh[3 * i], y = xyh[3 * i + 1], h = xyh[3 * i + 2];
+    verdict[i] = (uint8_t)circles_collide(g, cc, dist, x, y, h);
+  }
+}
+
+struct rect_consts {
+  float rx[5], ry[5];
+};
+
+__global__ void __launch_bounds__(256) collide_sat_kernel(hpp_geom g, rect_consts rc,
+                                                          const uint32_t *__restrict__ bits, int pitch,
+                                                          const double *__restrict__ xyh, size_t n,
+                                                          uint8_t *__restrict__ verdict) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const double x = xyh[3 * i], y = xyh[3 * i + 1], h = xyh[3 * i + 2];
+    int v = sat_collide_warp(g, rc.rx, rc.ry, bits, pitch, x, y, h);
+    if (lane == 0) verdict[i] = (uint8_t)v;
+  }
+}
+
+static circ_consts make_cc(const hpp_map *m) {
+  circ_consts cc;
+  for (int k = 0; k < 4; k++) {
+    cc.cx[k] = m->car.cx[k];
+    cc.cy[k] = m->car.cy[k];
+  }
+  cc.cr = m->car.cr;
+  return cc;
+}
+static rect_consts make_rc(const hpp_map *m) {
+  rect_consts rc;
+  for (int k = 0; k < 5; k++) {
+    rc.rx[k] = m->car.rx[k];
+    rc.ry[k] = m->car.ry[k];
+  }
+  return rc;
+}
+
+extern "C" hpp_status hpp_collide_circles_dev(hpp_map *m, const double *xyh_dev, size_t n, uint8_t *verdict_dev) {
+  if (!m || (n && (!xyh_dev || !verdict_dev))) return HPP_ERR_ARG;
+  if (n == 0) return HPP_OK;
+  hpp_ctx *c = m->ctx;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  // grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
+  long long want = hpp_div_up((long long)n, 256);
+  int grid = (int)(want < (long long)c->sm_count * 8 ? want : (long long)c->sm_count * 8);
+  collide_circles_kernel<<<grid, 256, 0, c->stream>>>(m->g, make_cc(m), m->d_distance, xyh_dev, n, verdict_dev);
+  HPP_LAUNCHED(c);
+  return HPP_OK;
+}
+
+extern "C" hpp_status hpp_collide_sat_dev(hpp_map *m, const double *xyh_dev, size_t n, uint8_t *verdict_dev) {
+  if (!m || (n && (!xyh_dev || !verdict_dev))) return HPP_ERR_ARG;
+  if (n == 0) return HPP_OK;
+  hpp_ctx *c = m->ctx;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  long long want = hpp_div_up((long long)n, 8);
+  int grid = (int)(want < (long long)c->sm_count * 8 ? want : (long long)c->sm_count * 8);
+  collide_sat_kernel<<<grid, 256, 0, c->stream>>>(m->g, make_rc(m), m->d_occ_bits, m->bits_pitch, xyh_dev, n,
+                                                   verdict_dev);
+  HPP_LAUNCHED(c);
+  return HPP_OK;
+}
+
+typedef hpp_status (*collide_dev_fn)(hpp_map *, const double *, size_t, uint8_t *);
+
+// host-pointer path: chunked H2D -> kernel -> D2H so that arbitrarily large pose batches stream through
+// a bounded device scratch.
+static hpp_status collide_host(hpp_map *m, const double *xyh, size_t n, uint8_t *verdict, collide_dev_fn fn) {
+  if (!m || (n && (!xyh || !verdict))) return HPP_ERR_ARG;
+  if (n == 0) return HPP_OK;
+  hpp_ctx *c = m->ctx;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  const size_t chunk = n < ((size_t)1 << 24) ? n : ((size_t)1 << 24);
+  void *d_in, *d_out;
+  hpp_status s = hpp_scratch(c, 0, chunk * 24, &d_in);
+  if (s != HPP_OK) return s;
+  s = hpp_scratch(c, 1, chunk, &d_out);
+  if (s != HPP_OK) return s;
+  for (size_t off = 0; off < n; off += chunk) {
+    size_t k = n - off < chunk ? n - off : chunk;
+    HPP_CUDA(c, cudaMemcpyAsync(d_in, xyh + 3 * off, k * 24, cudaMemcpyHostToDevice, c->stream));
+    s = fn(m, (const double *)d_in, k, (uint8_t *)d_out);
+    if (s != HPP_OK) return s;
+    HPP_CUDA(c, cudaMemcpyAsync(verdict + off, d_out, k, cudaMemcpyDeviceToHost, c->stream));
+  }
+  HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HPP_OK;
+}
+
+extern "C" hpp_status hpp_collide_circles(hpp_map *m, const double *xyh, size_t n, uint8_t *verdict) {
+  return collide_host(m, xyh, n, verdict, hpp_collide_circles_dev);
+}
+extern "C" hpp_status hpp_collide_sat(hpp_map *m, const double *xyh, size_t n, uint8_t *verdict) {
+  return collide_host(m, xyh, n, verdict, hpp_collide_sat_dev);
+}

@@ -1,0 +1,200 @@
+// collide.cuh -- device functions for the two vehicle-footprint collision checks.
+//   circles_collide : Grid_map::isSingleStateCollisionFree (RS/src/Grid_map.cpp:239-284) over the "distance"
+//                     layer with grid_map::GridMap::{isInside, atPosition(INTER_LINEAR)} semantics
+//                     (grid_map_core GridMapMath.cpp / GridMap.cpp, un-vendored dependency) and
+//                     CarData::getCircles/local2Global (RS/src/CarData.cpp:100-124).
+//   sat_collide_warp: Grid_map::checkCollision + createObstaclePolygon (DB/src/Grid_map.cpp:50-123),
+//                     fop::SATCollisionChecker::check_collision (DB/src/sat_collision_checker.cc:131-161),
+//                     CarData::getVehicleGeometry_state (DB/src/CarData.cpp:40-59) and the planner's
+//                     "|| !isPointInBounds(gridx, gridy)" (DB/src/HybridAstar.cpp:52).
+// All arithmetic is fp64 in the reference's operation order; the library is compiled with -fmad=false so
+// nothing is contracted into FMAs (the reference build targets baseline x86-64: no FMA).
+#pragma once
+#include "hpp_internal.cuh"
+
+struct circ_consts {
+  double cx[4], cy[4], cr;
+};
+
+// grid_map::getIndexFromPosition: ((p - 0.5*len) - pos) / res, truncated after negation
+__device__ __forceinline__ void gm_index(const hpp_geom &g, double px, double py, int &i, int &j) {
+  double vx = ((px - 0.5 * g.lenx) - g.posx) / g.res;
+  double vy = ((py - 0.5 * g.leny) - g.posy) / g.res;
+  i = (int)(-vx);
+  j = (int)(-vy);
+}
+
+// grid_map::getPositionFromIndex (cell centre); leaves x,y untouched when the index is out of range
+__device__ __forceinline__ void gm_position(const hpp_geom &g, int i, int j, double &x, double &y) {
+  if (i < 0 || j < 0 || i >= g.W || j >= g.H) return;
+  x = (g.posx + (0.5 * g.lenx - 0.5 * g.res)) + g.res * (double)(-i);
+  y = (g.posy + (0.5 * g.leny - 0.5 * g.res)) + g.res * (double)(-j);
+}
+
+// one footprint circle at world position (px,py): 1 = outside the map or clearance < r
+__device__ __forceinline__ int circle_hits(const hpp_geom &g, const float *__restrict__ dist, double px, double py,
+                                           double r) {
+  // isInside -> checkIfPositionWithinMap
+  double tx = -((px - g.posx) - 0.5 * g.lenx);
+  double ty = -((py - g.posy) - 0.5 * g.leny);
+  if (!(tx >= 0.0 && ty >= 0.0 && tx < g.lenx && ty < g.leny)) return 1;
+  // atPositionLinearInterpolated
+  int i0, j0;
+  gm_index(g, px, py, i0, j0);
+  double cx = 0.0, cy = 0.0;
+  gm_position(g, i0, j0, cx, cy);
+  const bool dirx = px >= cx, diry = py >= cy;
+  const int i1 = dirx ? i0 - 1 : i0 + 1;  // second index along x
+  const int j2 = diry ? j0 - 1 : j0 + 1;  // third index along y
+  // f[0] is the tap with the smallest x,y (largest i,j) of the four
+  const int ia = dirx ? i0 : i1, ib = dirx ? i1 : i0;  // ia: larger index (smaller x)
+  const int ja = diry ? j0 : j2, jb = diry ? j2 : j0;
+  const long W = g.W, nn = (long)g.W * g.H;
+  const long l0 = ja * W + ia, l1 = ja * W + ib, l2 = jb * W + ia, l3 = jb * W + ib;
+  float value;
+  if (l0 < 0 || l0 >= nn || l1 < 0 || l1 >= nn || l2 < 0 || l2 >= nn || l3 < 0 || l3 >= nn) {
+    value = __ldg(dist + (size_t)j0 * W + i0);  // INTER_NEAREST fallback
+  } else {
+    const float f0 = __ldg(dist + l0), f1 = __ldg(dist + l1), f2 = __ldg(dist + l2), f3 = __ldg(dist + l3);
+    double bx = cx, by = cy;
+    gm_position(g, ia, ja, bx, by);
+    const double rx = (px - bx) / g.res, ry = (py - by) / g.res;
+    const double fx = 1.0 - rx, fy = 1.0 - ry;
+    value = (float)((double)f0 * fx * fy + (double)f1 * rx * fy + (double)f2 * fx * ry + (double)f3 * rx * ry);
+  }
+  return (double)value < r;
+}
+
+__device__ __forceinline__ int circles_collide(const hpp_geom &g, const circ_consts &cc,
+                                               const float *__restrict__ dist, double x, double y, double h) {
+  double s, c;
+  sincos(h, &s, &c);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    double px = cc.cx[k] * c - cc.cy[k] * s + x;
+    double py = cc.cx[k] * s + cc.cy[k] * c + y;
+    if (circle_hits(g, dist, px, py, cc.cr)) return 1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- SAT
+struct sat_rect {
+  float x[5], y[5];      // Point32 vertices of the vehicle rectangle (closed)
+  double ax[3], ay[3];   // its three axes (orthogonals of the first three edges, float32 edge vectors)
+  double mn[3], mx[3];   // its own projections on those axes
+};
+
+__device__ __forceinline__ void sat_make_rect(const float *rx, const float *ry, double x, double y, double h,
+                                              sat_rect &R) {
+  double s, c;
+  sincos(h, &s, &c);
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    double px = x + (double)rx[k] * c - (double)ry[k] * s;
+    double py = y + (double)rx[k] * s + (double)ry[k] * c;
+    R.x[k] = (float)px;
+    R.y[k] = (float)py;
+  }
+#pragma unroll
+  for (int e = 0; e < 3; e++) {
+    float ex = __fsub_rn(R.x[e + 1], R.x[e]), ey = __fsub_rn(R.y[e + 1], R.y[e]);
+    R.ax[e] = (double)ey;
+    R.ay[e] = -(double)ex;
+    double mn = 0, mx = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      double d = (double)R.x[k] * R.ax[e] + (double)R.y[k] * R.ay[e];
+      if (k == 0 || d < mn) mn = d;
+      if (k == 0 || d > mx) mx = d;
+    }
+    R.mn[e] = mn;
+    R.mx[e] = mx;
+  }
+}
+
+__device__ __forceinline__ bool sat_overlap(double min1, double max1, double min2, double max2) {
+  return (min1 < min2) ? ((min2 - max1) < 0) : ((min1 - max2) < 0);
+}
+
+// SAT test of the vehicle rectangle against the square of occupancy cell (j = column/x, i = row/y)
+__device__ __forceinline__ bool sat_cell_hit(const hpp_geom &g, const sat_rect &R, int i, int j) {
+  double px = g.ox + j * g.res, py = g.oy + i * g.res;
+  const double half = g.res / 2.0;
+  px += g.res / 2;
+  py += g.res / 2;
+  float qx[5], qy[5];
+  qx[0] = (float)(px - half); qy[0] = (float)(py - half);
+  qx[1] = (float)(px + half); qy[1] = (float)(py - half);
+  qx[2] = (float)(px + half); qy[2] = (float)(py + half);
+  qx[3] = (float)(px - half); qy[3] = (float)(py + half);
+  qx[4] = qx[0];              qy[4] = qy[0];
+  // rectangle axes first (same order as the reference: edges1 then edges2)
+#pragma unroll
+  for (int e = 0; e < 3; e++) {
+    double mn = 0, mx = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      double d = (double)qx[k] * R.ax[e] + (double)qy[k] * R.ay[e];
+      if (k == 0 || d < mn) mn = d;
+      if (k == 0 || d > mx) mx = d;
+    }
+    if (!sat_overlap(R.mn[e], R.mx[e], mn, mx)) return false;
+  }
+#pragma unroll
+  for (int e = 0; e < 3; e++) {
+    float ex = __fsub_rn(qx[e + 1], qx[e]), ey = __fsub_rn(qy[e + 1], qy[e]);
+    double ax = (double)ey, ay = -(double)ex;
+    double mn1 = 0, mx1 = 0, mn2 = 0, mx2 = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      double d1 = (double)R.x[k] * ax + (double)R.y[k] * ay;
+      double d2 = (double)qx[k] * ax + (double)qy[k] * ay;
+      if (k == 0 || d1 < mn1) mn1 = d1;
+      if (k == 0 || d1 > mx1) mx1 = d1;
+      if (k == 0 || d2 < mn2) mn2 = d2;
+      if (k == 0 || d2 > mx2) mx2 = d2;
+    }
+    if (!sat_overlap(mn1, mx1, mn2, mx2)) return false;
+  }
+  return true;
+}
+
+// Whole-warp SAT check of one pose (all 32 lanes call with the same pose).  The +-5 m window is scanned
+// through the bit-packed occupancy: lane = window row (strided), two or three 32-bit words per row.
+// Result is a boolean OR over cells, so the scan order does not matter.  Returns the planner predicate.
+__device__ __forceinline__ int sat_collide_warp(const hpp_geom &g, const float *rx, const float *ry,
+                                                const uint32_t *__restrict__ bits, int pitch, double x, double y,
+                                                double h) {
+  const int lane = threadIdx.x & 31;
+  sat_rect R;
+  sat_make_rect(rx, ry, x, y, h, R);
+  const double offset = 5.0;
+  const double min_x = fmax(g.ox, x - offset), max_x = fmin(g.ox + g.W * g.res, x + offset);
+  const double min_y = fmax(g.oy, y - offset), max_y = fmin(g.oy + g.H * g.res, y + offset);
+  const int min_i = max(0, (int)((min_y - g.oy) / g.res)), max_i = min(g.H - 1, (int)((max_y - g.oy) / g.res));
+  const int min_j = max(0, (int)((min_x - g.ox) / g.res)), max_j = min(g.W - 1, (int)((max_x - g.ox) / g.res));
+  int hit = 0;
+  if (max_j >= min_j) {
+    const int w0 = min_j >> 5, w1 = max_j >> 5;
+    for (int i = min_i + lane; i <= max_i && !hit; i += 32) {
+      for (int w = w0; w <= w1 && !hit; w++) {
+        uint32_t word = __ldg(bits + (size_t)i * pitch + w);
+        if (w == w0) word &= 0xFFFFFFFFu << (min_j & 31);
+        if (w == w1) word &= 0xFFFFFFFFu >> (31 - (max_j & 31));
+        while (word) {
+          int b = __ffs(word) - 1;
+          word &= word - 1;
+          if (sat_cell_hit(g, R, i, (w << 5) + b)) {
+            hit = 1;
+            break;
+          }
+        }
+      }
+    }
+  }
+  hit = __any_sync(0xffffffffu, hit);
+  const int gx = (int)((x - g.ox) / g.res), gy = (int)((y - g.oy) / g.res);
+  const int inb = gx >= 0 && gx < g.W && gy >= 0 && gy < g.H;
+  return hit || !inb;
+}

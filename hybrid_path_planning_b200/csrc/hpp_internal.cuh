@@ -1,0 +1,107 @@
+// hpp_internal.cuh -- shared declarations of libhpp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hpp_b200.h"
+
+#define HPP_SM_COUNT_B200 148
+
+struct hpp_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  uint64_t launches;
+  char err[512];
+  // pinned staging for small control words (convergence flags, counters)
+  uint32_t *h_flags;   // pinned host, 64 words
+  uint32_t *d_flags;   // device, 64 words
+  // grow-only scratch (device) + pinned host staging for the host-pointer entry points
+  void *d_scratch[4];
+  size_t d_scratch_bytes[4];
+  void *h_pinned[2];
+  size_t h_pinned_bytes[2];
+};
+
+// per-cell class byte (see map.cu: build_cls_kernel)
+#define CLS_BLOCKED 0x80  // data > 0  (Grid_map::isInCollision, RS/src/Grid_map.cpp:212)
+#define CLS_NEAR4 0x40    // some in-bounds 4-neighbour is blocked (RS/src/HybridAstar.cpp:507-519)
+#define CLS_CNT_MASK 0x0F // number of isInCollision cells in the 3x3 block, out of bounds included
+                          // (DB/src/HybridAstar.cpp:204-218)
+
+struct hpp_geom {
+  int W, H;
+  float res_f;          // info.resolution as sent (float32)
+  double res;           // (double)res_f, what the planners compute with (hazard H6)
+  double ox, oy;        // origin
+  // grid_map::GridMap geometry (RS/src/Grid_map.cpp:15-25, grid_map_core setGeometry)
+  double lenx, leny, posx, posy;
+};
+
+struct hpp_car_dev {
+  hpp_params p;
+  // RS circles (RS/src/CarData.cpp:76-98)
+  double cx[4], cy[4], cr;
+  // Dubins rectangle corners as float32 (DB/src/CarData.cpp:15-37), closed polygon of 5
+  float rx[5], ry[5];
+  // motion commands (RS/src/HybridAstar.cpp:14-23, DB/src/HybridAstar.cpp:14-21)
+  int n_cmd[2];
+  double cmd_steer[2][HPP_MAX_COMMANDS];
+  double cmd_dir[2][HPP_MAX_COMMANDS];
+  double maxc;          // tan(maxSteerAngle) / wheelBase  (RS/src/HybridAstar.cpp:121)
+};
+
+struct hpp_map {
+  hpp_ctx *ctx;
+  hpp_geom g;
+  hpp_car_dev car;
+  size_t n;
+  int8_t *d_occ;        // [y*W + x]
+  uint8_t *d_cls;       // [y*W + x]
+  uint32_t *d_occ_bits; // bit-packed "data > 0", pitch words per row
+  int bits_pitch;
+  uint16_t *d_g;        // pass-1 row distances of the EDT (scratch, kept for reuse)
+  float *d_obstacle;    // [x + y*W]
+  float *d_distance;    // [x + y*W] (already flipped: distance[k] = edt[n-1-k]*res)
+};
+
+#define HPP_CUDA(ctx, call)                                                                       \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,      \
+               cudaGetErrorString(e_));                                                           \
+      return HPP_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define HPP_FAIL(ctx, code, ...)                                  \
+  do {                                                            \
+    snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);        \
+    return (code);                                                \
+  } while (0)
+
+#define HPP_LAUNCHED(ctx)                                                                         \
+  do {                                                                                            \
+    (ctx)->launches++;                                                                            \
+    cudaError_t e_ = cudaGetLastError();                                                          \
+    if (e_ != cudaSuccess) {                                                                      \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: kernel launch -> %s", __FILE__, __LINE__,  \
+               cudaGetErrorString(e_));                                                           \
+      return HPP_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+// grow-only device scratch slot / pinned host slot
+hpp_status hpp_scratch(hpp_ctx *ctx, int slot, size_t bytes, void **out);
+hpp_status hpp_pinned(hpp_ctx *ctx, int slot, size_t bytes, void **out);
+
+// internal launchers (device pointers, enqueue only)
+hpp_status hpp_edt_build(hpp_map *m);                                   // edt.cu
+hpp_status hpp_build_cls(hpp_map *m);                                   // map.cu
+hpp_status hpp_inflate_launch(hpp_ctx *ctx, const int8_t *occ_dev, uint32_t W, uint32_t H, double resolution,
+                              double inflation_radius, int8_t *out_dev); // inflate.cu
+
+static inline int hpp_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,118 @@
+"""GPU parity: K3a/K3b heuristic fields through the C ABI vs the CPU oracle (bit-exact fp64)."""
+import numpy as np
+import pytest
+
+from tests.common import block_map, bits_equal, cfg3_map
+
+pytestmark = pytest.mark.gpu
+
+
+def _goal_clear(occ, gx, gy):
+    occ = occ.copy()
+    occ[max(0, gy - 1):gy + 2, max(0, gx - 1):gx + 2] = 0
+    return occ
+
+
+@pytest.mark.parametrize("W,H,p,blk,seed", [(50, 50, 0.1, 1, 1), (120, 90, 0.3, 4, 2), (200, 200, 0.2, 1, 3),
+                                            (300, 300, 0.3, 8, 4), (64, 64, 0.0, 1, 5), (65, 127, 0.15, 2, 6),
+                                            (701, 710, 0.1, 3, 7)])
+def test_heuristic_rs_bit_exact(ctx, W, H, p, blk, seed):
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    gx, gy = W // 2, H // 3
+    occ = _goal_clear(block_map(W, H, p, blk, seed), gx, gy)
+    occ[0, 0] = 100
+    m = hpp.Map(ctx, occ, 0.2)
+    got, rep = m.heuristic_rs((gx, gy), (0, 0))
+    want, q = O.heuristic_rs(occ, (gx, gy), (0, 0), quirks=True)
+    if not (q.h1_fired or q.h2_clamped):
+        assert bits_equal(got, want), f"{(got != want).sum()} cells differ"
+    exact, _ = O.heuristic_rs(occ, (gx, gy), (0, 0), quirks=False)
+    assert bits_equal(got, exact)
+    assert rep.reachable == int(np.isfinite(exact).sum())
+    assert rep.max_cost == exact[np.isfinite(exact)].max()
+    m.close()
+
+
+@pytest.mark.parametrize("W,H,p,blk,seed", [(50, 50, 0.1, 1, 1), (120, 90, 0.3, 4, 2), (200, 200, 0.2, 1, 3),
+                                            (300, 300, 0.3, 8, 4), (65, 127, 0.15, 2, 6)])
+def test_heuristic_dubins_bit_exact(ctx, W, H, p, blk, seed):
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    gx, gy = W // 2, H // 3
+    occ = _goal_clear(block_map(W, H, p, blk, seed), gx, gy)
+    m = hpp.Map(ctx, occ, 0.2)
+    got, rep = m.heuristic_dubins((gx, gy))
+    want = O.heuristic_dubins(occ, (gx, gy))
+    assert bits_equal(got, want), f"{(got != want).sum()} cells differ"
+    m.close()
+
+
+def test_heuristic_goal_on_obstacle_and_corner(ctx):
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ = block_map(100, 80, 0.2, 2, 3)
+    occ[10, 10] = 100
+    m = hpp.Map(ctx, occ, 0.2)
+    for goal in ((10, 10), (0, 0), (99, 79), (63, 63), (64, 64)):
+        got, _ = m.heuristic_rs(goal, (-5, -5))
+        assert bits_equal(got, O.heuristic_rs(occ, goal, (0, 0), quirks=False)[0])
+        got, _ = m.heuristic_dubins(goal)
+        assert bits_equal(got, O.heuristic_dubins(occ, goal))
+    m.close()
+
+
+def test_heuristic_quirk_report(ctx):
+    """On a map where the reference's progress check (H1) fires the device reports it instead of claiming parity."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ = block_map(400, 400, 0.05, 2, 7)
+    occ[200, 200] = 0
+    occ[10, 10] = 0
+    m = hpp.Map(ctx, occ, 0.2)
+    got, rep = m.heuristic_rs((200, 200), (10, 10))
+    ref, q = O.heuristic_rs(occ, (200, 200), (10, 10), quirks=True)
+    exact, _ = O.heuristic_rs(occ, (200, 200), (10, 10), quirks=False)
+    assert q.h1_fired and (ref != exact).any()
+    assert rep.h1_progress_break in (1, 2)
+    assert bits_equal(got, exact)
+    # start out of bounds: fires for certain once 70000 cells are settled
+    _, rep2 = m.heuristic_rs((200, 200), (-1, -1))
+    assert rep2.h1_progress_break == 1
+    m.close()
+
+
+def test_heuristic_bad_goal_is_an_error(ctx):
+    import hybrid_path_planning_b200 as hpp
+    m = hpp.Map(ctx, np.zeros((20, 20), np.int8), 0.2)
+    with pytest.raises(hpp.HppError):
+        m.heuristic_rs((20, 3), (0, 0))
+    m.close()
+
+
+def test_heuristic_cfg3_1024(ctx):
+    """cfg3 recipe at 1024^2 (the oracle takes ~0.2 s): bit-exact, and the reference's quirks provably idle."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ, goal = cfg3_map(1024, seed=1)
+    m = hpp.Map(ctx, occ, 0.2)
+    got, rep = m.heuristic_rs(goal, (0, 0))
+    want, q = O.heuristic_rs(occ, goal, (0, 0), quirks=True)
+    assert not q.h1_fired and not q.h2_clamped
+    assert rep.h1_progress_break == 0 and rep.h2_bucket_clamp == 0
+    assert bits_equal(got, want)
+    m.close()
+
+
+def test_heuristic_cfg3_full_size(ctx):
+    """BASELINE cfg3: 4096^2.  The oracle (reference-equivalent, ~3 s) is run in full: bit-exact field."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ, goal = cfg3_map(4096, seed=1)
+    m = hpp.Map(ctx, occ, 0.2)
+    got, rep = m.heuristic_rs(goal, (0, 0))
+    want, q = O.heuristic_rs(occ, goal, (0, 0), quirks=True)
+    assert not q.h1_fired and not q.h2_clamped
+    assert rep.h1_progress_break == 0 and rep.h2_bucket_clamp == 0
+    assert bits_equal(got, want), f"{(got != want).sum()} cells differ"
+    m.close()
