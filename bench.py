@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: "heuristic Mcells/s ... vs host CPU").
+
+Workload at N=1 (config.workload = "cfg3"): BASELINE.json configs[2], the configuration the north_star's target is
+quoted on -- "holonomic heuristic plus distance-layer EDT on a synthetic 4096x4096 random-obstacle grid".
+One step = one pass of the hot path over one map:  K1 (per-cell tables + obstacle/distance layers of the occupancy,
+what the reference's Grid_map constructor does per map message) + K3a (the RS holonomic-with-obstacles heuristic
+field from the goal, what HybridAstar::run does first).  value = 4096^2 cells x steps / device time, inputs resident
+in HBM.  e2e = the same step through the host-buffer C ABI (hpp_map_update + hpp_heuristic_rs): occupancy H2D from
+pinned memory, cost field D2H, inside the timed region.
+
+Extras on the same JSON line (rank 0, N=1): collision checks/s on cfg4 (8192^2 distance layer, 10^7 poses) and Hybrid
+A* queries/s on a cfg5 sample, each with a bounded CPU sample beside it.
+
+--impl reference times the reference's own CPU implementation of the same step (oracle/_ref/libref_rs.so = the
+reference's HybridAstar.cpp compiled -O2, when present; else the C oracle port) on all host cores, one field per core.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from tests.common import cfg3_map, parking_map, random_poses  # noqa: E402
+
+METRIC = "heuristic Mcells/s (cfg3: K1 distance layers + K3a RS holonomic heuristic field, 4096x4096 map)"
+UNIT = "Mcells/s"
+RES = 0.2
+HEUR_BYTES_PER_CELL = 9      # 1 B occupancy read + 8 B fp64 cost write
+EDT_BYTES_PER_CELL = 9       # 1 B read + 4 B obstacle + 4 B distance written
+COLLIDE_BYTES_PER_POSE = 89  # 24 B pose + 1 B verdict + 4 circles x 4 taps x 4 B
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+_REF_OCC = None  # the map, synthesised once in the parent and inherited by the forked workers
+
+
+def _ref_worker(args):
+    """One cfg3 step on one host core: Grid_map construction (layers) + heuristic field."""
+    goal = args
+    from oracle import pyorc as O
+    occ = _REF_OCC
+    if O.ref_available():
+        r = O.Ref(0, occ, RES)               # reference-side Grid_map (stand-in ctor builds the layers)
+        h = r.heuristic(goal)                # reference's own HybridAstar::holonomicCostsWithObstacles_planning
+    else:
+        O.edt_layers(occ, np.float32(RES))
+        h, _ = O.heuristic_rs(occ, goal, (0, 0), True)
+    return float(h[goal[1], goal[0]])
+
+
+def reference_arm(args):
+    import multiprocessing as mp
+    from oracle import pyorc as O
+    O.build()
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = min(os.cpu_count() or 1, args.ref_cores or 32)
+    side = args.side
+    c = side // 2
+    goals = [(c - 2 + (i % 5), c - 2 + ((i // 5) % 5)) for i in range(cores)]   # inside the cleared 5x5 goal patch
+    kind = "reference" if O.ref_available() else "port"
+    global _REF_OCC
+    _REF_OCC, _ = cfg3_map(side, seed=1)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        tasks = [goals[i] for i in range(cores)]
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, tasks)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_worker, tasks)
+        dt = time.perf_counter() - t0
+    cells = side * side * cores * args.steps
+    value = cells / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3", "map": f"{side}x{side} 8x8-block Bernoulli(0.30), seed 1", "resolution": RES,
+                   "fields_per_step": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps x {cores} concurrent fields (one per core, goals inside the "
+                                   f"cleared goal patch) of the cfg3 step: Grid_map layers + heuristic; wall clock "
+                                   f"over the process pool, map synthesis excluded",
+                         "flags": "-O2 -ffp-contract=off (upstream default is -O0)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = samples at or above the median (the sampler also sees the idle edges)
+        load = [s for s in sm if s >= statistics.median(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def ours_arm(args):
+    import torch
+    import hybrid_path_planning_b200 as hpp
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = hpp.Context(local_rank)          # raises when libhpp_b200.so or the GPU is missing: no fallback
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    side = args.side
+    # weak scaling: every rank owns its own map (independent maps/goals shard with no data-path collective)
+    occ, goal = cfg3_map(side, seed=1 + rank)
+    n = side * side
+    d_occ = torch.from_numpy(occ).cuda()
+    m = hpp.Map(ctx, (side, side), RES, device_occ=d_occ)
+    cost_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    goals = np.array([goal], np.int32)
+
+    def step_dev():
+        m.update_dev(d_occ)                                   # K1: cls + bit rows + obstacle/distance layers
+        m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost_dev)  # K3a: one field (synchronous: host polls convergence)
+
+    for _ in range(args.warmup):
+        step_dev()
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)                             # L2 flush, outside the per-step event pair
+            ev[k][0].record(stream)
+            m.update_dev(d_occ)
+            ev[k][1].record(stream)
+            m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost_dev)
+            ev[k][2].record(stream)
+    ctx.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    ms_steps = [e[0].elapsed_time(e[2]) for e in ev]
+    ms_edt = [e[0].elapsed_time(e[1]) for e in ev]
+    ms_heur = [e[1].elapsed_time(e[2]) for e in ev]
+    t_dev = sum(ms_steps) / 1e3
+    t_all = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    t_max = float(t_all.item())
+    value = n * args.steps * world / t_max / 1e6
+
+    # ---- e2e: the call a user of the reference API makes, host buffers in pinned memory
+    occ_pin = torch.from_numpy(occ).pin_memory()
+    cost_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    occ_h, cost_h = occ_pin.numpy(), cost_pin.numpy().reshape(side, side)
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        m.update(occ_h)
+        m.heuristic_rs(goal, (0, 0), out=cost_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        flush.fill_(1)
+        m.update(occ_h)                                       # H2D occupancy + K1 + sync
+        m.heuristic_rs(goal, (0, 0), out=cost_h)             # K3a + D2H cost field + sync
+    torch.cuda.synchronize()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    t_all = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    e2e_value = n * e2e_steps * world / float(t_all.item()) / 1e6
+    checksum = float(cost_h[goal[1], goal[0]] + np.nan_to_num(cost_h[goal[1], :], posinf=0.0).sum())
+
+    peak, peak_src = measured_peak()
+    heur_ms = statistics.mean(ms_heur)
+    achieved = HEUR_BYTES_PER_CELL * n / (heur_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("heuristic_field_dram_bytes")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3", "map": f"{side}x{side} 8x8-block Bernoulli(0.30), seed 1+rank", "resolution": RES,
+                   "step": "hpp_map_update_dev (K1) + hpp_heuristic_batch_dev (K3a, 1 field)", "per_rank": "own map",
+                   "l2": "flushed between steps by a 256 MiB write outside the per-step event pair; the cost field "
+                         "(134 MB) alone exceeds the 126 MB L2",
+                   "timing": "CUDA events on the library's stream, per step, summed; max over ranks"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(8 * n),
+                "steps": e2e_steps, "api": "hpp_map_update + hpp_heuristic_rs (host buffers, pinned)",
+                "checksum": checksum},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "heur_round_kernel (all relaxation rounds of one field)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes": HEUR_BYTES_PER_CELL * n,
+                     "ms": heur_ms,
+                     "k1_layers": {"ms": statistics.mean(ms_edt),
+                                   "achieved": EDT_BYTES_PER_CELL * n / (statistics.mean(ms_edt) / 1e3) / 1e9}},
+        "wall_s": t_wall,
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["extra"] = extras(ctx, torch, hpp, stream)
+        line["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(ctx, torch, hpp, stream):
+    """cfg4 (collision checks/s) and a cfg5 sample (queries/s), device numbers + bounded CPU samples."""
+    from oracle import pyorc as O
+    out = {}
+    # ---- cfg4: 8192^2 distance layer, 10^7 poses
+    side, npose = 8192, 10_000_000
+    occ, _ = cfg3_map(side, seed=2)
+    d_occ = torch.from_numpy(occ).cuda()
+    m = hpp.Map(ctx, (side, side), RES, device_occ=d_occ)
+    poses_h = random_poses(npose, side, side, margin=2.0, seed=3)
+    poses = torch.from_numpy(poses_h).cuda()
+    verd = torch.empty(npose, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        m.collide_circles_dev(poses, npose, verd)
+    ctx.sync()
+    ts = []
+    with torch.cuda.stream(stream):
+        for k in range(5):
+            flush.fill_(k)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            m.collide_circles_dev(poses, npose, verd)
+            b.record(stream)
+            ctx.sync()
+            ts.append(a.elapsed_time(b) / 1e3)
+    t = statistics.mean(ts)
+    peak, _ = measured_peak()
+    pin = torch.from_numpy(poses_h).pin_memory().numpy()
+    vout = torch.empty(npose, dtype=torch.uint8).pin_memory().numpy()
+    m.collide_circles(pin, out=vout)
+    t0 = time.perf_counter()
+    m.collide_circles(pin, out=vout)
+    t_e2e = time.perf_counter() - t0
+    ns = 200_000
+    om = O.Map(occ[:2048, :2048], RES)            # CPU sample: a 2048^2 corner of the same map
+    ps = random_poses(ns, 2048, 2048, margin=2.0, seed=4)
+    t0 = time.perf_counter()
+    vo = O.collide_circles(om, ps)
+    t_cpu = time.perf_counter() - t0
+    out["cfg4_collision"] = {
+        "checks_per_s": npose / t, "ms": t * 1e3, "colliding_fraction": float(verd.float().mean().item()),
+        "roofline": {"bound": "hbm", "achieved": COLLIDE_BYTES_PER_POSE * npose / t / 1e9, "peak": peak,
+                     "frac": COLLIDE_BYTES_PER_POSE * npose / t / 1e9 / peak, "unit": "GB/s"},
+        "e2e_checks_per_s": npose / t_e2e, "h2d_bytes": 24 * npose, "d2h_bytes": npose,
+        "cpu": {"checks_per_s": ns / t_cpu, "cores": 1, "kind": "port",
+                "sample": f"{ns} poses on a 2048^2 corner (python-loop overhead of the ctypes harness included)",
+                "colliding_fraction": float(vo.mean())}}
+    m.close()
+    del poses, verd, d_occ
+    # ---- cfg5 sample: 8 parking maps x 128 start/goal pairs, RS planner
+    nmaps, npairs = 8, 128
+    t_gpu = 0.0
+    t_cpu = 0.0
+    n_cpu = 0
+    solved = 0
+    for k in range(nmaps):
+        pm = parking_map(256, seed=k)
+        om = O.Map(pm, RES)
+        cand = random_poses(4000, 256, 256, margin=3.0, seed=100 + k)
+        free = cand[O.collide_circles(om, cand) == 0][:2 * npairs]
+        starts, goals = free[:npairs], free[npairs:2 * npairs]
+        mm = hpp.Map(ctx, pm, RES)
+        if k == 0:
+            mm.plan_batch(hpp.VARIANT_RS, starts[:8], goals[:8])     # warm-up
+        t0 = time.perf_counter()
+        plans, _ = mm.plan_batch(hpp.VARIANT_RS, starts, goals)
+        t_gpu += time.perf_counter() - t0
+        solved += int((plans["n_states"] > 1).sum())
+        if k == 0:
+            t0 = time.perf_counter()
+            for i in range(32):
+                O.run(om, 0, tuple(starts[i]), tuple(goals[i]), quirks=True)
+            t_cpu += time.perf_counter() - t0
+            n_cpu += 32
+        mm.close()
+    nq = nmaps * npairs
+    out["cfg5_queries"] = {"queries_per_s": nq / t_gpu, "queries": nq, "solved": solved,
+                           "api": "hpp_plan_batch (host buffers; heuristic fields + device-resident A*)",
+                           "cpu": {"queries_per_s": n_cpu / t_cpu, "cores": 1, "kind": "port", "sample": f"{n_cpu} queries"}}
+    return out
+
+
+def cpu_baseline(args):
+    """The reference arm on a bounded sample, in a child process (fork after CUDA init is unsafe)."""
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+               "--side", str(args.side)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0"})
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"value": None, "error": (r.stderr or "no output")[-300:]}
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "error": str(e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=4096)
+    ap.add_argument("--ref-cores", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3                 # timing rule: W >= 3
+        ours_arm(args)
+
+
+if __name__ == "__main__":
+    main()

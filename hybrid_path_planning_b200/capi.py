@@ -263,9 +263,9 @@ class Map:
         self.ctx.check(self.L.hpp_map_cells(self.h, xy.ctypes.data, len(xy), cell.ctypes.data, flags.ctypes.data))
         return cell, flags
 
-    def collide_circles(self, xyh):
+    def collide_circles(self, xyh, out=None):
         xyh = np.ascontiguousarray(xyh, np.float64).reshape(-1, 3)
-        v = np.empty(len(xyh), np.uint8)
+        v = np.empty(len(xyh), np.uint8) if out is None else out
         self.ctx.check(self.L.hpp_collide_circles(self.h, xyh.ctypes.data, len(xyh), v.ctypes.data))
         return v
 
@@ -281,8 +281,8 @@ class Map:
     def collide_sat_dev(self, xyh_dev, n, verdict_dev):
         self.ctx.check(self.L.hpp_collide_sat_dev(self.h, _ptr(xyh_dev), n, _ptr(verdict_dev)))
 
-    def heuristic_rs(self, goal, start=(0, 0)):
-        cost = np.empty((self.H, self.W), np.float64)
+    def heuristic_rs(self, goal, start=(0, 0), out=None):
+        cost = np.empty((self.H, self.W), np.float64) if out is None else out
         rep = QuirkReport()
         self.ctx.check(self.L.hpp_heuristic_rs(self.h, goal[0], goal[1], start[0], start[1], cost.ctypes.data,
                                                C.byref(rep)))
