@@ -8,227 +8,539 @@
 //     RS:      cost[v] = min_u fl(cost[u] + w(dir, v)),  w = 1.0 | 1.414, + 5.0 if an in-bounds 4-neighbour of
 //                                                          v is occupied   (RS/src/HybridAstar.cpp:386-390,:500-526)
 //     Dubins:  cost[v] = min(1000, min_u fl(cost[u] + fl(hypot(dir) + 10*cnt3x3(u))))  (DB/src/HybridAstar.cpp:198-221,:286-297)
-// over free cells v, which does not depend on the relaxation order.  The device therefore runs an
-// asynchronous, tile-local label-correcting relaxation:
-//   * the field is cut into 64x64 tiles; a CTA owns one active tile per round, stages the tile's costs with a
-//     one-cell halo and the per-cell class bytes in shared memory, and relaxes to the tile-local fixed point;
-//   * inside the tile only the frontier is touched: "changed" cells are kept as 64-bit row masks, dilated by
-//     one cell with shifts, and compacted into a dense work list with popc + a warp shuffle scan;
-//   * a tile whose border cells improved flags the neighbouring tiles for the next round; rounds are plain
-//     stream-ordered launches (no inter-CTA spinning), the host polls a convergence word every few rounds;
-//   * fields (goals) are a batch dimension: blockIdx.y.
+// over free cells v, which does not depend on the relaxation order (fl(a + w) is monotone in a).
+//
+// Device algorithm: ONE persistent cooperative kernel per batch of fields -- delta-stepping over tiles.
+//   * The field is cut into T x T tiles (T = 32*NB).  A CTA of NB*NB warps stages one tile (+ one-cell halo) of fp64
+//     costs in shared memory; every warp owns one 32x32 block of it, lane = row.  The frontier lives in REGISTERS:
+//     one 32-bit "needs evaluation" mask per lane; a changed cell is dilated to its 8 neighbours with shifts and
+//     two warp shuffles; block-border changes are posted to the neighbouring warp through a shared-memory mask
+//     (atomicOr), so warps relax asynchronously and only meet at one __syncthreads_or per PHASE_SWEEPS sweeps.
+//   * A cell is evaluated by PULL: min over its 8 neighbours, exactly the reference's additions (no FMA; min
+//     before add is legal because fl(a+w) is monotone).  Rows with many needed cells are evaluated one lane per
+//     column (ballot collects the changes), sparse rows one cell per lane -- no list compaction at all.
+//   * Cost window: a change whose new cost is >= bound is DEFERRED (bit kept in a per-tile mask in global memory)
+//     instead of propagated; a tile is scheduled when a neighbour posted a border change or when its cheapest
+//     deferred cell falls below the bound; when nothing is schedulable the bound advances to (global minimum of
+//     deferred costs) + delta.  This keeps expensive waves (the +5 near-obstacle cells) from running ahead of the
+//     cheap ones and being corrected later: 3 evaluations per cell instead of 27 on the cfg3 map.
+//   * Scheduling is done on the device by every CTA identically from read-only "current" tables (tile activity
+//     flags are triple-buffered, the deferred minima double-buffered), so a round costs exactly one group barrier;
+//     the host launches once and never polls.  Batches of fields are split over independent CTA groups.
 // Costs are fp64 with exactly the reference's additions (library built with -fmad=false).
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "hpp_internal.cuh"
 
-#define HT 64              // tile side
-#define HP (HT + 2)        // with halo
-#define H_THREADS 256
+namespace {
+
+constexpr int HB = 32;  // block side = one warp, lane = row
+constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
+constexpr int PHASE_SWEEPS = 8;
+constexpr int HEAVY_ROW = 6;  // rows with at least this many needed cells are evaluated lane-per-column
+
+// direction bits of the tile activity flags / out flags
+enum { DIR_N = 1, DIR_S = 2, DIR_W = 4, DIR_E = 8, DIR_NW = 16, DIR_NE = 32, DIR_SW = 64, DIR_SE = 128 };
 
 struct heur_weights {
-  // RS: [near][0 = cardinal, 1 = diagonal];  Dubins: [dir class][count 0..9]
-  double rs[2][2];
-  double db[2][10];
-  double init;  // +inf (RS) or 1000 (Dubins)
+  double rs[2][2];   // [near][0 = cardinal, 1 = diagonal]
+  double db[2][10];  // [diagonal][3x3 collision count of the SOURCE cell]
+  double init;       // +inf (RS) or 1000 (Dubins)
 };
 
-__global__ void __launch_bounds__(256) heur_init_kernel(double *__restrict__ cost, size_t n, size_t n_fields,
-                                                        const int32_t *__restrict__ goal_xy, int W, double init,
-                                                        uint8_t *__restrict__ act0, uint8_t *__restrict__ act1,
-                                                        int tiles_x, int n_tiles) {
-  const size_t total = n * n_fields;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) cost[i] = init;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n_tiles * n_fields; i += stride) {
-    act0[i] = 0;
-    act1[i] = 0;
+struct heur_args {
+  double *cost_all;                // [n_fields][H*W]
+  const uint32_t *occ_bits;        // bit-packed data > 0, pitch words per row
+  const uint32_t *near_bits;       // bit-packed CLS_NEAR4
+  const uint8_t *cls;              // class bytes (Dubins: 3x3 counts)
+  int pitch;
+  int W, H, tiles_x, tiles_y, n_tiles;
+  int n_fields;
+  uint32_t *act;                   // [n_fields][3][n_tiles]
+  unsigned long long *pmin;        // [n_fields][2][n_tiles]  cheapest deferred cost of the tile (bit pattern)
+  uint32_t *dmask;                 // [n_fields][n_tiles][NB*NB*32]  deferred cells
+  uint32_t *bar;                   // [n_groups][32]: count, generation
+  uint32_t *stats;                 // [n_fields][4]: rounds, tile visits, windows, sweeps of CTA rank 0
+  double delta;
+  int group_size, n_groups;
+  heur_weights wt;
+};
+
+template <int NB>
+struct tile_cfg {
+  static constexpr int T = NB * HB;
+  // row stride in doubles: even (16-byte aligned rows) and == 2 (mod 4), which keeps a warp whose lanes sit on 32
+  // different rows at (nearly) the same column at <= 2-way bank conflicts, for vertical and both diagonal fronts
+  static constexpr int S = T + 6;
+  static constexpr int ROWS = T + 2;
+  static constexpr int NBLK = NB * NB;
+  static constexpr int THREADS = NBLK * 32;
+};
+
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+
+// ---------------------------------------------------------------- group barrier (co-resident CTAs, cooperative launch)
+__device__ __forceinline__ void group_barrier(uint32_t *bar, int group_size) {
+  __syncthreads();
+  if (group_size > 1 && threadIdx.x == 0) {
+    volatile uint32_t *gen = bar + 1;
+    __threadfence();
+    const uint32_t g = *gen;
+    if (atomicAdd(bar, 1u) == (uint32_t)group_size - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- per-warp block state
+struct blk_state {
+  uint32_t need;   // cells of my row that must be (re-)evaluated
+  uint32_t defer;  // cells of my row whose latest change is not propagated yet (cost >= bound)
+  uint32_t freem;  // free, in-bounds cells of my row
+  uint32_t nearm;  // RS: near-obstacle cells of my row
+  uint32_t dirty;  // my row changed (needs write-back)
+  uint32_t posted; // I posted a border change to another warp of this CTA in this phase
+};
+
+template <int NB>
+__device__ __forceinline__ void post(uint32_t *s_inc, uint32_t *s_out, int bx, int by, int dx, int dy, int row, uint32_t bits,
+                                     blk_state &st) {
+  const int nx = bx + dx, ny = by + dy;
+  if (nx < 0 || nx >= NB || ny < 0 || ny >= NB) {
+    unsigned d;
+    if (dy < 0) d = dx < 0 ? DIR_NW : (dx > 0 ? DIR_NE : DIR_N);
+    else if (dy > 0) d = dx < 0 ? DIR_SW : (dx > 0 ? DIR_SE : DIR_S);
+    else d = dx < 0 ? DIR_W : DIR_E;
+    // a diagonal step that leaves the tile through an edge only (not the tile corner) is an edge post
+    if (dx != 0 && dy != 0) {
+      const bool xin = nx >= 0 && nx < NB, yin = ny >= 0 && ny < NB;
+      if (xin) d = dy < 0 ? DIR_N : DIR_S;
+      else if (yin) d = dx < 0 ? DIR_W : DIR_E;
+    }
+    atomicOr(s_out, d);
+  } else {
+    atomicOr(&s_inc[(ny * NB + nx) * 32 + row], bits);
+    st.posted = 1;
   }
 }
 
-__global__ void heur_seed_kernel(double *__restrict__ cost, size_t n, size_t n_fields,
-                                 const int32_t *__restrict__ goal_xy, int W, uint8_t *__restrict__ act0,
-                                 int tiles_x, int n_tiles) {
-  size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_fields) return;
-  int gx = goal_xy[2 * f], gy = goal_xy[2 * f + 1];
-  cost[f * n + (size_t)gy * W + gx] = 0.0;  // goal = 0 even if occupied (RS/src/HybridAstar.cpp:378)
-  act0[f * n_tiles + (size_t)(gy / HT) * tiles_x + gx / HT] = 1;
+// dilate the propagating changes p (one mask per lane = row) to the 8-neighbourhood: own block -> need masks,
+// across the block border -> the neighbour warp's incoming mask or the tile's out flags
+template <int NB>
+__device__ __forceinline__ void propagate(uint32_t p, blk_state &st, uint32_t *s_inc, uint32_t *s_out, int bx, int by,
+                                          int lane) {
+  const uint32_t h = p | (p << 1) | (p >> 1);
+  uint32_t hu = __shfl_up_sync(FULL, h, 1), hd = __shfl_down_sync(FULL, h, 1);
+  if (lane == 0) hu = 0;
+  if (lane == 31) hd = 0;
+  st.need |= (((p << 1) | (p >> 1)) | hu | hd) & st.freem;
+  const bool edge = (p & 0x80000001u) || ((lane == 0 || lane == 31) && p);
+  if (__any_sync(FULL, edge)) {
+    __threadfence_block();  // the cost stores of this sweep before the notifications
+    uint32_t pu = __shfl_up_sync(FULL, p, 1), pd = __shfl_down_sync(FULL, p, 1);
+    if (lane == 0) pu = 0;
+    if (lane == 31) pd = 0;
+    const uint32_t pv = p | pu | pd;
+    if (pv & 1u) post<NB>(s_inc, s_out, bx, by, -1, 0, lane, 0x80000000u, st);
+    if (pv >> 31) post<NB>(s_inc, s_out, bx, by, 1, 0, lane, 1u, st);
+    if (lane == 0 && p) {
+      post<NB>(s_inc, s_out, bx, by, 0, -1, 31, h, st);
+      if (p & 1u) post<NB>(s_inc, s_out, bx, by, -1, -1, 31, 0x80000000u, st);
+      if (p >> 31) post<NB>(s_inc, s_out, bx, by, 1, -1, 31, 1u, st);
+    }
+    if (lane == 31 && p) {
+      post<NB>(s_inc, s_out, bx, by, 0, 1, 0, h, st);
+      if (p & 1u) post<NB>(s_inc, s_out, bx, by, -1, 1, 0, 0x80000000u, st);
+      if (p >> 31) post<NB>(s_inc, s_out, bx, by, 1, 1, 0, 1u, st);
+    }
+  }
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(H_THREADS) heur_round_kernel(double *__restrict__ cost_all,
-                                                               const uint8_t *__restrict__ cls, int W, int H,
-                                                               int tiles_x, int tiles_y, heur_weights wt,
-                                                               uint8_t *__restrict__ act_cur,
-                                                               uint8_t *__restrict__ act_next,
-                                                               uint32_t *__restrict__ work, int first_round,
-                                                               uint32_t *__restrict__ visits) {
-  const int n_tiles = tiles_x * tiles_y;
-  const int tile = blockIdx.x, field = blockIdx.y;
-  uint8_t *my_flag = act_cur + (size_t)field * n_tiles + tile;
-  __shared__ int s_active;
-  if (threadIdx.x == 0) s_active = *my_flag;
-  __syncthreads();
-  if (!s_active) return;
+// weights held in registers (RS) / shared memory (Dubins table)
+struct eval_w {
+  double c0, d0, c1, d1;  // RS: cardinal / diagonal, plain and near-obstacle
+  double init;
+  const double *db;       // Dubins: [2][10] in shared memory
+};
 
+// evaluate one cell by pull.  e = shared index of the cell.  Returns the candidate cost.
+template <int VARIANT, int S>
+__device__ __forceinline__ double eval_cell(const volatile double *cs, const volatile uint8_t *cl, int e, bool near,
+                                            const eval_w &wt) {
+  if (VARIANT == HPP_VARIANT_RS) {
+    const double n = cs[e - S], s = cs[e + S], w = cs[e - 1], ea = cs[e + 1];
+    const double nw = cs[e - S - 1], ne = cs[e - S + 1], sw = cs[e + S - 1], se = cs[e + S + 1];
+    const double mc = dmin(dmin(n, s), dmin(w, ea));
+    const double md = dmin(dmin(nw, ne), dmin(sw, se));
+    const double wc = near ? wt.c1 : wt.c0, wd = near ? wt.d1 : wt.d0;
+    return dmin(mc + wc, md + wd);
+  } else {
+    double best = wt.init;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++) {
+        if (dx == 0 && dy == 0) continue;
+        const int u = e + dy * S + dx;
+        best = dmin(best, cs[u] + wt.db[((dx != 0 && dy != 0) ? 10 : 0) + (cl[u] & CLS_CNT_MASK)]);
+      }
+    return best;
+  }
+}
+
+// one sweep of my block: returns false when there was nothing to do
+template <int NB, int VARIANT>
+__device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_t *cl, uint32_t *s_inc, uint32_t *s_out,
+                                      blk_state &st, int blk, int bx, int by, int lane, double bound,
+                                      const eval_w &wt) {
+  constexpr int S = tile_cfg<NB>::S;
+  // border changes posted by the neighbouring warps
+  uint32_t inc = ((volatile uint32_t *)s_inc)[blk * 32 + lane];
+  if (__any_sync(FULL, inc != 0)) {
+    if (inc) inc = atomicExch(&s_inc[blk * 32 + lane], 0u);
+    __threadfence_block();
+    st.need |= inc & st.freem;
+  }
+  if (!__any_sync(FULL, st.need != 0)) return false;
+  const int ebase = (by * HB + 1) * S + bx * HB + 2;  // shared index of cell (row 0, col 0) of my block
+  uint32_t p = 0;
+  // rows with many needed cells: one lane per column
+  uint32_t heavy = __ballot_sync(FULL, __popc(st.need) >= HEAVY_ROW);
+  while (heavy) {
+    const int r = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    const uint32_t m = __shfl_sync(FULL, st.need, r);
+    const uint32_t nm = __shfl_sync(FULL, st.nearm, r);
+    const int e = ebase + r * S + lane;
+    const bool on = (m >> lane) & 1u;
+    const double c0 = cs[e];
+    const double best = eval_cell<VARIANT, S>(cs, cl, e, (nm >> lane) & 1u, wt);
+    const bool imp = on && best < c0;
+    if (imp) cs[e] = best;
+    const uint32_t bimp = __ballot_sync(FULL, imp);
+    const uint32_t blow = __ballot_sync(FULL, imp && best < bound);
+    if (lane == r) {
+      st.need = 0;
+      p |= blow;
+      st.defer = (st.defer | bimp) & ~blow;
+      if (bimp) st.dirty = 1;
+    }
+    __syncwarp();
+  }
+  // sparse rows: one cell per lane and iteration
+  while (__any_sync(FULL, st.need != 0)) {
+    const bool on = st.need != 0;
+    const int x = on ? __ffs(st.need) - 1 : 0;
+    st.need &= st.need - 1;
+    const int e = ebase + lane * S + x;
+    const double c0 = cs[e];
+    const double best = eval_cell<VARIANT, S>(cs, cl, e, (st.nearm >> x) & 1u, wt);
+    const bool imp = on && best < c0;
+    if (imp) {
+      cs[e] = best;
+      const uint32_t bit = 1u << x;
+      st.dirty = 1;
+      if (best < bound) {
+        p |= bit;
+        st.defer &= ~bit;
+      } else {
+        st.defer |= bit;
+      }
+    }
+    __syncwarp();
+  }
+  if (__any_sync(FULL, p != 0)) propagate<NB>(p, st, s_inc, s_out, bx, by, lane);
+  return true;
+}
+
+// ---------------------------------------------------------------- the persistent kernel
+template <int NB, int VARIANT>
+__global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(const __grid_constant__ heur_args a) {
+  using C = tile_cfg<NB>;
+  constexpr int T = C::T, S = C::S, ROWS = C::ROWS, NBLK = C::NBLK, THREADS = C::THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *cs = (double *)smem_raw;                                  // HP*HP costs
-  unsigned long long *need = (unsigned long long *)(cs + HP * HP);  // [HT]
-  unsigned long long *freem = need + HT;                            // [HT]
-  unsigned long long *chg = freem + HT;                             // [2][HT]
-  unsigned short *list = (unsigned short *)(chg + 2 * HT);          // [HT*HT]
-  unsigned char *cl = (unsigned char *)(list + HT * HT);            // HP*HP class bytes
-  __shared__ int s_total;
-  __shared__ unsigned s_border;
-  __shared__ int s_any;
+  double *cs_nv = (double *)smem_raw;                                   // ROWS * S
+  uint32_t *s_inc = (uint32_t *)(cs_nv + ROWS * S);                     // NBLK * 32
+  uint32_t *s_list = s_inc + NBLK * 32;                                 // THREADS
+  uint8_t *cl_nv = (uint8_t *)(s_list + THREADS);                       // ROWS * S (Dubins only)
+  volatile double *cs = cs_nv;
+  const volatile uint8_t *cl = cl_nv;
+  __shared__ unsigned long long s_gmin, s_pmin;
+  __shared__ uint32_t s_count, s_mine, s_out, s_warp_cnt[32];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int x0 = tx * HT, y0 = ty * HT;
-  double *cost = cost_all + (size_t)field * W * H;
-
-  // ---- stage tile + halo
-  for (int e = tid; e < HP * HP; e += H_THREADS) {
-    int r = e / HP, c = e - r * HP;
-    int gx = x0 + c - 1, gy = y0 + r - 1;
-    double v = wt.init;
-    unsigned char k = CLS_BLOCKED;
-    if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-      v = cost[(size_t)gy * W + gx];
-      k = cls[(size_t)gy * W + gx];
-    }
-    cs[e] = v;
-    cl[e] = k;
-  }
-  if (tid == 0) {
-    s_border = 0;
-    s_any = 0;
-    *my_flag = 0;
-  }
-  __syncthreads();
-  // free masks: warp w builds rows w, w+8, ...
-  for (int r = wid; r < HT; r += H_THREADS / 32) {
-    unsigned lo = __ballot_sync(0xffffffffu, !(cl[(r + 1) * HP + 1 + lane] & CLS_BLOCKED));
-    unsigned hi = __ballot_sync(0xffffffffu, !(cl[(r + 1) * HP + 33 + lane] & CLS_BLOCKED));
-    if (lane == 0) {
-      unsigned long long fm = (unsigned long long)lo | ((unsigned long long)hi << 32);
-      freem[r] = fm;
-      // first sweep: everything (first round = goal tile) or the ring next to the halo
-      unsigned long long ring = (r == 0 || r == HT - 1) ? ~0ull : (1ull | (1ull << 63));
-      need[r] = first_round ? fm : (fm & ring);
-      chg[r] = 0;
-      chg[HT + r] = 0;
-    }
-  }
+  const int bx = wid % NB, by = wid / NB;
+  const int group = blockIdx.x / a.group_size, grank = blockIdx.x % a.group_size;
+  if (group >= a.n_groups) return;  // spare CTAs (grid not a multiple of the group size)
+  uint32_t *bar = a.bar + group * 32;
+  const int W = a.W, H = a.H, n_tiles = a.n_tiles;
+  const size_t n = (size_t)W * H;
+  __shared__ double s_db[20];
+  if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
+  eval_w wt;
+  wt.c0 = a.wt.rs[0][0];
+  wt.d0 = a.wt.rs[0][1];
+  wt.c1 = a.wt.rs[1][0];
+  wt.d1 = a.wt.rs[1][1];
+  wt.init = a.wt.init;
+  wt.db = s_db;
   __syncthreads();
 
-  int sweep = 0;
-  for (;; sweep++) {
-    unsigned long long *chg_w = chg + (sweep & 1) * HT;        // written by this sweep's relax phase
-    const unsigned long long *chg_r = chg + ((sweep + 1) & 1) * HT;  // written by the previous sweep
-    // ---- warp 0: dilate the previous sweep's changes into this sweep's need masks and compact them
-    if (wid == 0) {
-      unsigned long long nd[2];
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const int r = lane * 2 + q;
-        unsigned long long m;
-        if (sweep == 0) {
-          m = need[r];
-        } else {
-          unsigned long long a = (r > 0) ? chg_r[r - 1] : 0ull, b = chg_r[r], c = (r < HT - 1) ? chg_r[r + 1] : 0ull;
-          unsigned long long ac = a | c;
-          m = (ac | (ac << 1) | (ac >> 1) | (b << 1) | (b >> 1)) & freem[r];
+  for (int field = group; field < a.n_fields; field += a.n_groups) {
+    double *cost = a.cost_all + (size_t)field * n;
+    uint32_t *act = a.act + (size_t)field * 3 * n_tiles;
+    unsigned long long *pmin = a.pmin + (size_t)field * 2 * n_tiles;
+    uint32_t *dmask = a.dmask + (size_t)field * n_tiles * NBLK * 32;
+    double bound = 0.0;
+    uint32_t rounds = 0, visits = 0, windows = 0, sweeps = 0;
+
+    for (uint32_t round = 0;; round++) {
+      // act buffers rotate: cur is read-only this round, next receives posts, clr is zeroed for the round after
+      uint32_t *act_cur = act + (round % 3) * n_tiles, *act_next = act + ((round + 1) % 3) * n_tiles,
+               *act_clr = act + ((round + 2) % 3) * n_tiles;
+      unsigned long long *pm_cur = pmin + (round & 1) * n_tiles, *pm_next = pmin + ((round + 1) & 1) * n_tiles;
+
+      // ---- pass 1: how many tiles are schedulable under the current bound, and the global minimum deferred cost
+      uint32_t total;
+      for (;;) {
+        if (tid == 0) {
+          s_count = 0;
+          s_gmin = INF_BITS;
         }
-        nd[q] = m;
-      }
-      __syncwarp();
-      // the buffer the coming relax phase writes was last read one sweep ago: clear it now
-      chg_w[lane * 2] = 0;
-      chg_w[lane * 2 + 1] = 0;
-      int cnt = __popcll(nd[0]) + __popcll(nd[1]);
-      int inc = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-      }
-      int off = inc - cnt;
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        unsigned long long m = nd[q];
-        const int r = lane * 2 + q;
-        while (m) {
-          int b = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          list[off++] = (unsigned short)(r * HT + b);
+        __syncthreads();
+        uint32_t cnt = 0;
+        unsigned long long mn = INF_BITS;
+        for (int t = tid; t < n_tiles; t += THREADS) {
+          const uint32_t af = __ldcg(act_cur + t);
+          const unsigned long long pm = __ldcg(pm_cur + t);
+          if (af != 0 || __longlong_as_double((long long)pm) < bound) cnt++;
+          mn = pm < mn ? pm : mn;
         }
+        for (int d = 16; d; d >>= 1) {
+          cnt += __shfl_down_sync(FULL, cnt, d);
+          const unsigned long long o = __shfl_down_sync(FULL, mn, d);
+          mn = o < mn ? o : mn;
+        }
+        if (lane == 0) {
+          if (cnt) atomicAdd(&s_count, cnt);
+          if (mn != INF_BITS) atomicMin(&s_gmin, mn);
+        }
+        __syncthreads();
+        total = s_count;
+        const unsigned long long g = s_gmin;
+        __syncthreads();
+        if (total != 0 || g == INF_BITS) break;
+        bound = __longlong_as_double((long long)g) + a.delta;  // open the next cost window
+        windows++;
       }
-      if (lane == 31) s_total = inc;
-    }
-    __syncthreads();
-    const int total = s_total;
-    if (total == 0) break;
-    // ---- relax the compacted frontier
-    for (int k = tid; k < total; k += H_THREADS) {
-      const int cell = list[k];
-      const int r = cell >> 6, c = cell & 63;
-      const int e = (r + 1) * HP + (c + 1);
-      double best;
-      if (VARIANT == HPP_VARIANT_RS) {
-        const double mc = fmin(fmin(cs[e - HP], cs[e + HP]), fmin(cs[e - 1], cs[e + 1]));
-        const double md = fmin(fmin(cs[e - HP - 1], cs[e - HP + 1]), fmin(cs[e + HP - 1], cs[e + HP + 1]));
-        const int nr = (cl[e] & CLS_NEAR4) ? 1 : 0;
-        best = fmin(mc + wt.rs[nr][0], md + wt.rs[nr][1]);
-      } else {
-        best = wt.init;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++) {
-            if (dx == 0 && dy == 0) continue;
-            const int u = e + dy * HP + dx;
-            const double w = wt.db[(dx != 0 && dy != 0) ? 1 : 0][cl[u] & CLS_CNT_MASK];
-            best = fmin(best, cs[u] + w);
+      if (total == 0) break;  // nothing active, nothing deferred: fixed point reached
+      rounds++;
+
+      // ---- pass 2: every CTA ranks the schedulable tiles identically; I take ranks == grank (mod group size).
+      // Housekeeping for the tiles t == grank (mod group size): carry an unscheduled tile's minimum over to the
+      // next round's table and zero the activity buffer of the round after.
+      uint32_t base_rank = 0;
+      for (int t0 = 0; t0 < n_tiles; t0 += THREADS) {
+        const int t = t0 + tid;
+        bool on = false;
+        if (t < n_tiles) {
+          const uint32_t af = __ldcg(act_cur + t);
+          const unsigned long long pm = __ldcg(pm_cur + t);
+          on = af != 0 || __longlong_as_double((long long)pm) < bound;
+          if (t % a.group_size == grank) {
+            if (!on) __stcg(pm_next + t, pm);
+            __stcg(act_clr + t, 0u);
           }
-      }
-      if (best < cs[e]) {
-        cs[e] = best;
-        atomicOr(&chg_w[r], 1ull << c);
-        unsigned bf = 0;
-        if (r == 0) bf |= 1u | (c == 0 ? 16u : 0u) | (c == HT - 1 ? 32u : 0u);
-        if (r == HT - 1) bf |= 2u | (c == 0 ? 64u : 0u) | (c == HT - 1 ? 128u : 0u);
-        if (c == 0) bf |= 4u;
-        if (c == HT - 1) bf |= 8u;
-        if (bf) atomicOr(&s_border, bf);
-        s_any = 1;
-      }
-    }
-    __syncthreads();
-  }
+        }
+        const uint32_t b = __ballot_sync(FULL, on);
+        if (lane == 0) s_warp_cnt[wid] = __popc(b);
+        if (tid == 0) s_mine = 0;
+        __syncthreads();
+        uint32_t pre = base_rank, chunk = 0;
+        for (int w = 0; w < THREADS / 32; w++) {
+          const uint32_t cw = s_warp_cnt[w];
+          if (w < wid) pre += cw;
+          chunk += cw;
+        }
+        if (on) {
+          const uint32_t rank = pre + __popc(b & ((1u << lane) - 1u));
+          if ((int)(rank % (uint32_t)a.group_size) == grank) s_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
+        }
+        base_rank += chunk;
+        __syncthreads();
+        const uint32_t mine = s_mine;
 
-  if (tid == 0) atomicAdd(visits, 1u);
-  if (!s_any) return;
-  // ---- write the interior back
-  for (int e = tid; e < HT * HT; e += H_THREADS) {
-    int r = e >> 6, c = e & 63;
-    int gx = x0 + c, gy = y0 + r;
-    if (gx < W && gy < H) cost[(size_t)gy * W + gx] = cs[(r + 1) * HP + c + 1];
-  }
-  // ---- wake the neighbours whose halo changed
-  if (tid < 8) {
-    const int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-    const int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-    if (s_border & (1u << tid)) {
-      int nx = tx + ddx[tid], ny = ty + ddy[tid];
-      if (nx >= 0 && nx < tiles_x && ny >= 0 && ny < tiles_y) {
-        __threadfence();
-        act_next[(size_t)field * n_tiles + ny * tiles_x + nx] = 1;
-        *work = 1u;
+        // ---- process my tiles of this chunk
+        for (uint32_t k = 0; k < mine; k++) {
+          const int tile = (int)s_list[k];
+          const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+          const int x0 = tx * T, y0 = ty * T;
+          visits++;
+          // stage costs (+ halo); out-of-bounds cells hold the initial value and are never free
+          for (int i = tid; i < ROWS * (T + 2); i += THREADS) {
+            const int r = i / (T + 2), c = i - r * (T + 2);
+            const int gx = x0 - 1 + c, gy = y0 - 1 + r;
+            double v = wt.init;
+            uint8_t k8 = CLS_BLOCKED | 9;
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+              v = __ldcg(cost + (size_t)gy * W + gx);
+              if (VARIANT == HPP_VARIANT_DUBINS) k8 = a.cls[(size_t)gy * W + gx];
+            }
+            cs_nv[r * S + c + 1] = v;
+            if (VARIANT == HPP_VARIANT_DUBINS) cl_nv[r * S + c + 1] = k8;
+          }
+          s_inc[tid] = 0;
+          if (tid == 0) {
+            s_out = 0;
+            s_pmin = INF_BITS;
+          }
+          // my row's masks
+          blk_state st;
+          {
+            const int gy = y0 + by * HB + lane, wx = (x0 >> 5) + bx;
+            uint32_t ob = 0xffffffffu, nb = 0;
+            if (gy < H && wx < a.pitch) {
+              ob = a.occ_bits[(size_t)gy * a.pitch + wx];
+              nb = a.near_bits[(size_t)gy * a.pitch + wx];
+              const int rem = W - (wx << 5);
+              if (rem < 32) ob |= ~((1u << rem) - 1u);
+            }
+            st.freem = ~ob;
+            st.nearm = nb;
+            st.need = 0;
+            st.dirty = 0;
+            st.posted = 0;
+            st.defer = __ldcg(dmask + ((size_t)tile * NBLK + wid) * 32 + lane);
+          }
+          const uint32_t af = __ldcg(act_cur + tile);
+          __syncthreads();
+          // ring cells facing a neighbour tile that posted a border change
+          if (af) {
+            if ((af & DIR_N) && by == 0 && lane == 0) st.need |= st.freem;
+            if ((af & DIR_S) && by == NB - 1 && lane == 31) st.need |= st.freem;
+            if ((af & DIR_W) && bx == 0) st.need |= st.freem & 1u;
+            if ((af & DIR_E) && bx == NB - 1) st.need |= st.freem & 0x80000000u;
+            if ((af & DIR_NW) && bx == 0 && by == 0 && lane == 0) st.need |= st.freem & 1u;
+            if ((af & DIR_NE) && bx == NB - 1 && by == 0 && lane == 0) st.need |= st.freem & 0x80000000u;
+            if ((af & DIR_SW) && bx == 0 && by == NB - 1 && lane == 31) st.need |= st.freem & 1u;
+            if ((af & DIR_SE) && bx == NB - 1 && by == NB - 1 && lane == 31) st.need |= st.freem & 0x80000000u;
+          }
+          // release the deferred cells that fell below the bound
+          {
+            const int ebase = (by * HB + 1) * S + bx * HB + 2;
+            uint32_t rel = 0;
+            for (uint32_t m = st.defer; m; m &= m - 1) {
+              const int x = __ffs(m) - 1;
+              if (cs[ebase + lane * S + x] < bound) rel |= 1u << x;
+            }
+            st.defer &= ~rel;
+            __syncwarp();
+            if (__any_sync(FULL, rel != 0)) propagate<NB>(rel, st, s_inc, &s_out, bx, by, lane);
+          }
+          // ---- relax to the tile-local fixed point under the bound
+          // (a warp that posted votes to continue: the receiver may already be waiting at the barrier)
+          for (;;) {
+            for (int k2 = 0; k2 < PHASE_SWEEPS; k2++) {
+              if (!sweep<NB, VARIANT>(cs, cl, s_inc, &s_out, st, wid, bx, by, lane, bound, wt)) break;
+              if (wid == 0) sweeps++;
+            }
+            const int more = __syncthreads_or((st.need != 0) || st.posted);
+            st.posted = 0;
+            if (!more) break;
+          }
+          // ---- write back: changed rows, deferred masks, cheapest deferred cost, notifications
+          {
+            const int ebase = (by * HB + 1) * S + bx * HB + 2;
+            unsigned long long mn = INF_BITS;
+            for (uint32_t m = st.defer; m; m &= m - 1) {
+              const int x = __ffs(m) - 1;
+              const unsigned long long v = (unsigned long long)__double_as_longlong(cs[ebase + lane * S + x]);
+              mn = v < mn ? v : mn;
+            }
+            for (int d = 16; d; d >>= 1) {
+              const unsigned long long o = __shfl_down_sync(FULL, mn, d);
+              mn = o < mn ? o : mn;
+            }
+            if (lane == 0 && mn != INF_BITS) atomicMin(&s_pmin, mn);
+            __stcg(dmask + ((size_t)tile * NBLK + wid) * 32 + lane, st.defer);
+            uint32_t dr = __ballot_sync(FULL, st.dirty != 0);
+            const int gx = x0 + bx * HB + lane;
+            while (dr) {
+              const int r = __ffs(dr) - 1;
+              dr &= dr - 1;
+              const int gy = y0 + by * HB + r;
+              if (gx < W && gy < H) __stcg(cost + (size_t)gy * W + gx, cs[ebase + r * S + lane]);
+            }
+          }
+          __syncthreads();
+          if (tid == 0) {
+            __stcg(pm_next + tile, s_pmin);
+            const uint32_t o = s_out;
+            if (o) {
+              __threadfence();
+              // the neighbour must evaluate the ring side FACING us
+#pragma unroll
+              for (int d = 0; d < 8; d++) {
+                constexpr int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+                constexpr int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+                constexpr uint32_t facing[8] = {DIR_S, DIR_N, DIR_E, DIR_W, DIR_SE, DIR_SW, DIR_NE, DIR_NW};
+                if (o & (1u << d)) {
+                  const int nx = tx + ddx[d], ny = ty + ddy[d];
+                  if (nx >= 0 && nx < a.tiles_x && ny >= 0 && ny < a.tiles_y)
+                    atomicOr(act_next + ny * a.tiles_x + nx, facing[d]);
+                }
+              }
+            }
+          }
+          __syncthreads();
+        }
       }
+      group_barrier(bar, a.group_size);
     }
+    if (grank == 0 && tid == 0) {
+      uint32_t *s = a.stats + field * 4;
+      s[0] = rounds;
+      s[2] = windows;
+      s[3] = sweeps;
+    }
+    if (tid == 0 && visits) atomicAdd(a.stats + field * 4 + 1, visits);
+    // the next field of this group reuses the barrier; everybody left the round loop on the same round
   }
+}
+
+// ---------------------------------------------------------------- init / seed / stats
+__global__ void __launch_bounds__(256) heur_init_kernel(double *__restrict__ cost, size_t total, double init,
+                                                        unsigned long long *__restrict__ pmin, size_t n_pmin) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = i0; i < total; i += stride) cost[i] = init;
+  for (size_t i = i0; i < n_pmin; i += stride) pmin[i] = INF_BITS;
+}
+
+template <int NB>
+__global__ void heur_seed_kernel(double *__restrict__ cost, size_t n, size_t n_fields, const int32_t *__restrict__ goal_xy,
+                                 int W, unsigned long long *__restrict__ pmin, uint32_t *__restrict__ dmask, int tiles_x,
+                                 int n_tiles) {
+  constexpr int T = tile_cfg<NB>::T, NBLK = tile_cfg<NB>::NBLK;
+  const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_fields) return;
+  const int gx = goal_xy[2 * f], gy = goal_xy[2 * f + 1];
+  cost[f * n + (size_t)gy * W + gx] = 0.0;  // goal = 0 even if occupied (RS/src/HybridAstar.cpp:378)
+  // the goal's "change" is a deferred cell of cost 0: the first window releases it
+  const int tile = (gy / T) * tiles_x + gx / T;
+  const int lx = gx % T, ly = gy % T;
+  const int blk = (ly / HB) * NB + lx / HB;
+  dmask[((f * n_tiles + tile) * NBLK + blk) * 32 + (ly % HB)] = 1u << (lx % HB);
+  pmin[f * 2 * n_tiles + tile] = 0ull;
 }
 
 // reachable count / max finite cost per field
@@ -256,7 +568,7 @@ __global__ void __launch_bounds__(256) heur_stats_kernel(const double *__restric
   }
 }
 
-static void make_weights(int variant, heur_weights *w) {
+void make_weights(int variant, heur_weights *w) {
   // RS/src/HybridAstar.cpp:389 (1.0 / 1.414) and :523 (movement_cost += 5.0)
   for (int nr = 0; nr < 2; nr++) {
     double c = 1.0, d = 1.414;
@@ -277,9 +589,144 @@ static void make_weights(int variant, heur_weights *w) {
   w->init = (variant == HPP_VARIANT_RS) ? INFINITY : 1000.0;
 }
 
-static size_t heur_smem_bytes() {
-  return sizeof(double) * HP * HP + sizeof(unsigned long long) * HT * 4 + sizeof(unsigned short) * HT * HT + HP * HP + 16;
+template <int NB>
+size_t heur_smem_bytes(int variant) {
+  using C = tile_cfg<NB>;
+  size_t b = sizeof(double) * C::ROWS * C::S + sizeof(uint32_t) * (C::NBLK * 32 + C::THREADS);
+  if (variant == HPP_VARIANT_DUBINS) b += (size_t)C::ROWS * C::S;
+  return b + 16;
 }
+
+double env_double(const char *name, double dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atof(s) : dflt;
+}
+
+template <int NB, int VARIANT>
+hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
+  using C = tile_cfg<NB>;
+  const size_t smem = heur_smem_bytes<NB>(VARIANT);
+  auto kern = heur_persist_kernel<NB, VARIANT>;
+  HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem));
+  if (per_sm < 1) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic kernel does not fit on an SM (%zu B shared)", smem);
+  const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", NB >= 4 ? 1 : 4);
+  if (per_sm > per_sm_cap) per_sm = per_sm_cap;
+  const int G = per_sm * c->sm_count;  // co-resident CTAs
+  // CTA groups: one field at a time per group.  A group never needs more CTAs than the widest ring of active
+  // tiles (about a quarter of the tiles); small maps get one CTA per field and many fields in flight.
+  int gs = ctas_per_field_hint > 0 ? ctas_per_field_hint : (a.n_tiles + 3) / 4;
+  if (ctas_per_field_hint <= 0 && (long long)gs * a.n_fields < G) gs = G / a.n_fields;  // few fields: share the whole GPU
+  if (gs > a.n_tiles) gs = a.n_tiles;  // never more CTAs than tiles
+  if (gs > G) gs = G;
+  if (gs < 1) gs = 1;
+  int n_groups = G / gs;
+  if (n_groups > a.n_fields) n_groups = a.n_fields;
+  a.group_size = gs;
+  a.n_groups = n_groups;
+  const int grid = gs * n_groups;
+  void *params[] = {&a};
+  HPP_CUDA(c, cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(C::THREADS), params, smem, c->stream));
+  HPP_LAUNCHED(c);
+  return HPP_OK;
+}
+
+template <int NB>
+hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_fields, double *cost_dev,
+                     hpp_quirk_report *reports) {
+  using C = tile_cfg<NB>;
+  hpp_ctx *c = m->ctx;
+  const int W = m->g.W, H = m->g.H;
+  const int tiles_x = hpp_div_up(W, C::T), tiles_y = hpp_div_up(H, C::T), n_tiles = tiles_x * tiles_y;
+  // scratch slot 2: act (3 x) | pmin (2 x) | dmask | barriers | stats | goals | field stats
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t act_b = al(sizeof(uint32_t) * 3 * n_tiles * n_fields);
+  const size_t pmin_b = al(sizeof(unsigned long long) * 2 * n_tiles * n_fields);
+  const size_t dmask_b = al(sizeof(uint32_t) * (size_t)n_tiles * C::NBLK * 32 * n_fields);
+  const size_t bar_b = al(sizeof(uint32_t) * 32 * (size_t)c->sm_count * 8);
+  const size_t stats_b = al(sizeof(uint32_t) * 4 * n_fields);
+  const size_t goals_b = al(n_fields * 8);
+  const size_t fstats_b = al(n_fields * 16);
+  void *scr;
+  hpp_status s = hpp_scratch(c, 2, act_b + pmin_b + dmask_b + bar_b + stats_b + goals_b + fstats_b, &scr);
+  if (s != HPP_OK) return s;
+  uint8_t *p = (uint8_t *)scr;
+  heur_args a;
+  memset(&a, 0, sizeof a);
+  a.act = (uint32_t *)p;                    p += act_b;
+  a.pmin = (unsigned long long *)p;         p += pmin_b;
+  a.dmask = (uint32_t *)p;                  p += dmask_b;
+  a.bar = (uint32_t *)p;                    p += bar_b;
+  a.stats = (uint32_t *)p;                  p += stats_b;
+  int32_t *d_goals = (int32_t *)p;          p += goals_b;
+  unsigned long long *d_fstats = (unsigned long long *)p;
+  void *h_stage;
+  s = hpp_pinned(c, 1, goals_b + stats_b + fstats_b, &h_stage);
+  if (s != HPP_OK) return s;
+  memcpy(h_stage, goal_xy, n_fields * 8);
+  HPP_CUDA(c, cudaMemcpyAsync(d_goals, h_stage, n_fields * 8, cudaMemcpyHostToDevice, c->stream));
+  // zero: act, dmask, barriers, stats (pmin is filled with +inf by the init kernel)
+  HPP_CUDA(c, cudaMemsetAsync(a.act, 0, act_b, c->stream));
+  HPP_CUDA(c, cudaMemsetAsync(a.dmask, 0, dmask_b + bar_b + stats_b, c->stream));
+
+  make_weights(variant, &a.wt);
+  a.cost_all = cost_dev;
+  a.occ_bits = m->d_occ_bits;
+  a.near_bits = m->d_near_bits;
+  a.cls = m->d_cls;
+  a.pitch = m->bits_pitch;
+  a.W = W;
+  a.H = H;
+  a.tiles_x = tiles_x;
+  a.tiles_y = tiles_y;
+  a.n_tiles = n_tiles;
+  a.n_fields = (int)n_fields;
+  a.delta = env_double("HPP_HEUR_DELTA", 2.0 * C::T);
+
+  const size_t total = m->n * n_fields;
+  size_t want = total / 1024 + 1;
+  const int grid = (int)(want < (size_t)c->sm_count * 16 ? want : (size_t)c->sm_count * 16);
+  heur_init_kernel<<<grid, 256, 0, c->stream>>>(cost_dev, total, a.wt.init, a.pmin, (size_t)2 * n_tiles * n_fields);
+  HPP_LAUNCHED(c);
+  heur_seed_kernel<NB><<<hpp_div_up((long long)n_fields, 128), 128, 0, c->stream>>>(cost_dev, m->n, n_fields, d_goals, W,
+                                                                                   a.pmin, a.dmask, tiles_x, n_tiles);
+  HPP_LAUNCHED(c);
+  const int hint = (int)env_double("HPP_HEUR_GROUP", 0);
+  s = (variant == HPP_VARIANT_RS) ? launch_persist<NB, HPP_VARIANT_RS>(c, a, hint)
+                                  : launch_persist<NB, HPP_VARIANT_DUBINS>(c, a, hint);
+  if (s != HPP_OK) return s;
+
+  if (reports) {
+    uint32_t *h_stats = (uint32_t *)((uint8_t *)h_stage + goals_b);
+    unsigned long long *h_fstats = (unsigned long long *)((uint8_t *)h_stage + goals_b + stats_b);
+    HPP_CUDA(c, cudaMemsetAsync(d_fstats, 0, n_fields * 16, c->stream));
+    dim3 sgrid(c->sm_count * 4, (unsigned)n_fields);
+    heur_stats_kernel<<<sgrid, 256, 0, c->stream>>>(cost_dev, m->n, variant == HPP_VARIANT_RS ? INFINITY : 1000.0, d_fstats);
+    HPP_LAUNCHED(c);
+    HPP_CUDA(c, cudaMemcpyAsync(h_stats, a.stats, n_fields * 16, cudaMemcpyDeviceToHost, c->stream));
+    HPP_CUDA(c, cudaMemcpyAsync(h_fstats, d_fstats, n_fields * 16, cudaMemcpyDeviceToHost, c->stream));
+    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t f = 0; f < n_fields; f++) {
+      hpp_quirk_report *r = &reports[f];
+      memset(r, 0, sizeof *r);
+      r->reachable = h_fstats[2 * f];
+      memcpy(&r->max_cost, &h_fstats[2 * f + 1], 8);
+      r->rounds = h_stats[4 * f];
+      r->tile_visits = h_stats[4 * f + 1];
+      if (variant == HPP_VARIANT_RS) {
+        const int MAX_COST = (W + H > 5000) ? W + H : 5000;  // RS/src/HybridAstar.cpp:395
+        r->h2_bucket_clamp = r->max_cost >= (double)(MAX_COST - 1);
+      }
+    }
+  } else {
+    // the relaxation is one stream-ordered launch; completion (and any device fault) is reported here
+    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return HPP_OK;
+}
+
+}  // namespace
 
 extern "C" hpp_status hpp_heuristic_batch_dev(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_fields,
                                               double *cost_dev, hpp_quirk_report *reports) {
@@ -292,93 +739,12 @@ extern "C" hpp_status hpp_heuristic_batch_dev(hpp_map *m, int variant, const int
                f, W, H);
   if (n_fields > 65535) HPP_FAIL(c, HPP_ERR_ARG, "at most 65535 fields per call");
   HPP_CUDA(c, cudaSetDevice(c->device));
-  const int tiles_x = hpp_div_up(W, HT), tiles_y = hpp_div_up(H, HT), n_tiles = tiles_x * tiles_y;
-  // scratch slot 2: act flags (2 x n_fields x n_tiles bytes) + goals + stats
-  const size_t act_bytes = ((size_t)n_tiles * n_fields + 255) & ~(size_t)255;
-  const size_t goals_bytes = ((n_fields * 8) + 255) & ~(size_t)255;
-  const size_t stats_bytes = n_fields * 16;
-  void *scr;
-  hpp_status s = hpp_scratch(c, 2, 2 * act_bytes + goals_bytes + stats_bytes, &scr);
-  if (s != HPP_OK) return s;
-  uint8_t *act[2] = {(uint8_t *)scr, (uint8_t *)scr + act_bytes};
-  int32_t *d_goals = (int32_t *)((uint8_t *)scr + 2 * act_bytes);
-  unsigned long long *d_stats = (unsigned long long *)((uint8_t *)scr + 2 * act_bytes + goals_bytes);
-  void *h_goals;
-  s = hpp_pinned(c, 1, goals_bytes + stats_bytes, &h_goals);
-  if (s != HPP_OK) return s;
-  memcpy(h_goals, goal_xy, n_fields * 8);
-  HPP_CUDA(c, cudaMemcpyAsync(d_goals, h_goals, n_fields * 8, cudaMemcpyHostToDevice, c->stream));
-
-  heur_weights wt;
-  make_weights(variant, &wt);
-  const size_t total = m->n * n_fields;
-  int grid = (int)((total / 256 + 1) < (size_t)c->sm_count * 16 ? (total / 256 + 1) : (size_t)c->sm_count * 16);
-  heur_init_kernel<<<grid, 256, 0, c->stream>>>(cost_dev, m->n, n_fields, d_goals, W, wt.init, act[0], act[1], tiles_x,
-                                               n_tiles);
-  HPP_LAUNCHED(c);
-  heur_seed_kernel<<<hpp_div_up((long long)n_fields, 128), 128, 0, c->stream>>>(cost_dev, m->n, n_fields, d_goals, W,
-                                                                               act[0], tiles_x, n_tiles);
-  HPP_LAUNCHED(c);
-
-  const size_t smem = heur_smem_bytes();
-  HPP_CUDA(c, cudaFuncSetAttribute(heur_round_kernel<HPP_VARIANT_RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  HPP_CUDA(c, cudaFuncSetAttribute(heur_round_kernel<HPP_VARIANT_DUBINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // convergence words: d_flags[0..15] = "round r woke somebody", d_flags[16] = tile visits
-  const int K = 16;
-  uint32_t *d_work = c->d_flags, *d_visits = c->d_flags + 16;
-  HPP_CUDA(c, cudaMemsetAsync(d_visits, 0, sizeof(uint32_t), c->stream));
-  dim3 rgrid(n_tiles, (unsigned)n_fields);
-  uint32_t round = 0;
-  bool done = false;
-  // every cell can only be improved finitely often; the bound below is a safety net against a logic error
-  const uint32_t max_rounds = 64u * (uint32_t)(tiles_x + tiles_y) * 64u + 1024u;
-  while (!done && round < max_rounds) {
-    HPP_CUDA(c, cudaMemsetAsync(d_work, 0, K * sizeof(uint32_t), c->stream));
-    for (int k = 0; k < K; k++, round++) {
-      if (variant == HPP_VARIANT_RS)
-        heur_round_kernel<HPP_VARIANT_RS><<<rgrid, H_THREADS, smem, c->stream>>>(
-            cost_dev, m->d_cls, W, H, tiles_x, tiles_y, wt, act[round & 1], act[(round + 1) & 1], d_work + k, round == 0,
-            d_visits);
-      else
-        heur_round_kernel<HPP_VARIANT_DUBINS><<<rgrid, H_THREADS, smem, c->stream>>>(
-            cost_dev, m->d_cls, W, H, tiles_x, tiles_y, wt, act[round & 1], act[(round + 1) & 1], d_work + k, round == 0,
-            d_visits);
-      HPP_LAUNCHED(c);
-    }
-    HPP_CUDA(c, cudaMemcpyAsync(c->h_flags, d_work, 17 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < K; k++)
-      if (c->h_flags[k] == 0) {
-        done = true;
-        round = round - K + k + 1;
-        break;
-      }
-  }
-  if (!done) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic relaxation did not converge in %u rounds", max_rounds);
-  const uint32_t visits = c->h_flags[16];
-
-  if (reports) {
-    HPP_CUDA(c, cudaMemsetAsync(d_stats, 0, stats_bytes, c->stream));
-    dim3 sgrid(c->sm_count * 4, (unsigned)n_fields);
-    heur_stats_kernel<<<sgrid, 256, 0, c->stream>>>(cost_dev, m->n, variant == HPP_VARIANT_RS ? INFINITY : 1000.0, d_stats);
-    HPP_LAUNCHED(c);
-    unsigned long long *h_stats = (unsigned long long *)((uint8_t *)h_goals + goals_bytes);
-    HPP_CUDA(c, cudaMemcpyAsync(h_stats, d_stats, stats_bytes, cudaMemcpyDeviceToHost, c->stream));
-    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (size_t f = 0; f < n_fields; f++) {
-      hpp_quirk_report *r = &reports[f];
-      memset(r, 0, sizeof *r);
-      r->reachable = h_stats[2 * f];
-      memcpy(&r->max_cost, &h_stats[2 * f + 1], 8);
-      r->rounds = round;
-      r->tile_visits = visits;
-      if (variant == HPP_VARIANT_RS) {
-        const int MAX_COST = (W + H > 5000) ? W + H : 5000;  // RS/src/HybridAstar.cpp:395
-        r->h2_bucket_clamp = r->max_cost >= (double)(MAX_COST - 1);
-      }
-    }
-  }
-  return HPP_OK;
+  // tile side: 128 (16 warps, one CTA per SM) for big maps, 64 (4 warps, several CTAs per SM) for small ones
+  int nb = (W >= 1024 || H >= 1024) ? 4 : 2;
+  const int env_nb = (int)env_double("HPP_HEUR_NB", 0);
+  if (env_nb == 2 || env_nb == 4) nb = env_nb;
+  return nb == 4 ? run_batch<4>(m, variant, goal_xy, n_fields, cost_dev, reports)
+                 : run_batch<2>(m, variant, goal_xy, n_fields, cost_dev, reports);
 }
 
 // H1 (RS/src/HybridAstar.cpp:452-472): every 70000 settled cells the reference stops if the start cell is

@@ -61,6 +61,7 @@ struct hpp_map {
   int8_t *d_occ;        // [y*W + x]
   uint8_t *d_cls;       // [y*W + x]
   uint32_t *d_occ_bits; // bit-packed "data > 0", pitch words per row
+  uint32_t *d_near_bits; // bit-packed CLS_NEAR4, same pitch
   int bits_pitch;
   uint16_t *d_g;        // pass-1 row distances of the EDT (scratch, kept for reuse)
   float *d_obstacle;    // [x + y*W]

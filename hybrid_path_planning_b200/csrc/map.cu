@@ -88,11 +88,11 @@ hpp_status hpp_pinned(hpp_ctx *c, int slot, size_t bytes, void **out) {
 // heuristics, and the bit-packed "data > 0" rows used by the SAT window scan.
 __global__ void __launch_bounds__(256) build_cls_kernel(const int8_t *__restrict__ occ, int W, int H,
                                                         uint8_t *__restrict__ cls, uint32_t *__restrict__ bits,
-                                                        int pitch) {
+                                                        uint32_t *__restrict__ near_bits, int pitch) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y;
   bool in = x < W;
-  bool blocked = false;
+  bool blocked = false, near = false;
   if (in) {
     auto col = [&](int xx, int yy) -> int {
       if (xx < 0 || xx >= W || yy < 0 || yy >= H) return 1;  // isInCollision: out of bounds = collision
@@ -109,16 +109,21 @@ __global__ void __launch_bounds__(256) build_cls_kernel(const int8_t *__restrict
       for (int dx = -1; dx <= 1; dx++) cnt += col(x + dx, y + dy);
     int near4 = inb_col(x - 1, y) | inb_col(x, y - 1) | inb_col(x + 1, y) | inb_col(x, y + 1);
     blocked = occ[(size_t)y * W + x] > 0;
+    near = near4 != 0;
     cls[(size_t)y * W + x] = (uint8_t)((blocked ? CLS_BLOCKED : 0) | (near4 ? CLS_NEAR4 : 0) | cnt);
   }
   unsigned m = __ballot_sync(0xffffffffu, in && blocked);
-  if ((threadIdx.x & 31) == 0 && (x >> 5) < pitch) bits[(size_t)y * pitch + (x >> 5)] = m;
+  unsigned mn = __ballot_sync(0xffffffffu, in && near);
+  if ((threadIdx.x & 31) == 0 && (x >> 5) < pitch) {
+    bits[(size_t)y * pitch + (x >> 5)] = m;
+    near_bits[(size_t)y * pitch + (x >> 5)] = mn;
+  }
 }
 
 hpp_status hpp_build_cls(hpp_map *m) {
   hpp_ctx *c = m->ctx;
   dim3 grid(hpp_div_up(m->g.W, 256), m->g.H);
-  build_cls_kernel<<<grid, 256, 0, c->stream>>>(m->d_occ, m->g.W, m->g.H, m->d_cls, m->d_occ_bits, m->bits_pitch);
+  build_cls_kernel<<<grid, 256, 0, c->stream>>>(m->d_occ, m->g.W, m->g.H, m->d_cls, m->d_occ_bits, m->d_near_bits, m->bits_pitch);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
@@ -192,6 +197,7 @@ static hpp_status map_alloc(hpp_ctx *c, uint32_t W, uint32_t H, float resolution
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_occ, m->n);
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_cls, m->n);
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_occ_bits, (size_t)m->bits_pitch * H * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_near_bits, (size_t)m->bits_pitch * H * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_g, m->n * sizeof(uint16_t));
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_obstacle, m->n * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_distance, m->n * sizeof(float));
@@ -262,6 +268,7 @@ extern "C" hpp_status hpp_map_destroy(hpp_map *m) {
   cudaFree(m->d_occ);
   cudaFree(m->d_cls);
   cudaFree(m->d_occ_bits);
+  cudaFree(m->d_near_bits);
   cudaFree(m->d_g);
   cudaFree(m->d_obstacle);
   cudaFree(m->d_distance);
