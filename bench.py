@@ -3,11 +3,13 @@
 
 Workload at N=1 (config.workload = "cfg3"): BASELINE.json configs[2], the configuration the north_star's target is
 quoted on -- "holonomic heuristic plus distance-layer EDT on a synthetic 4096x4096 random-obstacle grid".
-One step = one pass of the hot path over one map:  K1 (per-cell tables + obstacle/distance layers of the occupancy,
-what the reference's Grid_map constructor does per map message) + K3a (the RS holonomic-with-obstacles heuristic
-field from the goal, what HybridAstar::run does first).  value = 4096^2 cells x steps / device time, inputs resident
-in HBM.  e2e = the same step through the host-buffer C ABI (hpp_map_update + hpp_heuristic_rs): occupancy H2D from
-pinned memory, cost field D2H, inside the timed region.
+One step = one pass of the hot path over one map message and a batch of F queries on it (--fields, default 16, the
+same "one field per host core" batch the reference arm runs):  K1 (per-cell tables + obstacle/distance layers of the
+occupancy, what the reference's Grid_map constructor does per map message) + K3a (the RS holonomic-with-obstacles
+heuristic field of each query's goal, what HybridAstar::run does first).  value = F x 4096^2 cells x steps / device
+time, inputs resident in HBM.  e2e = the same step through the host-buffer C ABI (hpp_map_update +
+hpp_heuristic_batch): occupancy H2D from pinned memory, F cost fields D2H, inside the timed region.  The latency of a
+single field (F = 1, hpp_heuristic_rs) is reported under extra.single_field.
 
 Extras on the same JSON line (rank 0, N=1): collision checks/s on cfg4 (8192^2 distance layer, 10^7 poses) and Hybrid
 A* queries/s on a cfg5 sample, each with a bounded CPU sample beside it.
@@ -48,6 +50,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def patch_goals(side, k):
+    """k distinct goal cells inside the cleared 5x5 patch at the map centre (cfg3 recipe)"""
+    c = side // 2
+    return [(c - 2 + (i % 5), c - 2 + ((i // 5) % 5)) for i in range(k)]
+
+
 # --------------------------------------------------------------------------------------------- reference arm
 _REF_OCC = None  # the map, synthesised once in the parent and inherited by the forked workers
 
@@ -73,10 +81,10 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = min(os.cpu_count() or 1, args.ref_cores or 32)
+    cores = min(os.cpu_count() or 1, args.ref_cores or 64)
     side = args.side
     c = side // 2
-    goals = [(c - 2 + (i % 5), c - 2 + ((i // 5) % 5)) for i in range(cores)]   # inside the cleared 5x5 goal patch
+    goals = [patch_goals(side, 25)[i % 25] for i in range(cores)]   # inside the cleared 5x5 goal patch
     kind = "reference" if O.ref_available() else "port"
     global _REF_OCC
     _REF_OCC, _ = cfg3_map(side, seed=1)
@@ -184,13 +192,14 @@ def ours_arm(args):
     n = side * side
     d_occ = torch.from_numpy(occ).cuda()
     m = hpp.Map(ctx, (side, side), RES, device_occ=d_occ)
-    cost_dev = torch.empty(n, dtype=torch.float64, device="cuda")
+    F = args.fields
+    cost_dev = torch.empty(F * n, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    goals = np.array([goal], np.int32)
+    goals = np.array(patch_goals(side, F), np.int32)                   # distinct goal cells inside the cleared patch
 
     def step_dev():
         m.update_dev(d_occ)                                   # K1: cls + bit rows + obstacle/distance layers
-        m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost_dev)  # K3a: one field (synchronous: host polls convergence)
+        m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost_dev)  # K3a: F fields, one persistent launch
 
     for _ in range(args.warmup):
         step_dev()
@@ -223,34 +232,47 @@ def ours_arm(args):
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     t_max = float(t_all.item())
-    value = n * args.steps * world / t_max / 1e6
+    value = F * n * args.steps * world / t_max / 1e6
 
     # ---- e2e: the call a user of the reference API makes, host buffers in pinned memory
     occ_pin = torch.from_numpy(occ).pin_memory()
-    cost_pin = torch.empty(n, dtype=torch.float64).pin_memory()
-    occ_h, cost_h = occ_pin.numpy(), cost_pin.numpy().reshape(side, side)
+    cost_pin = torch.empty(F * n, dtype=torch.float64).pin_memory()
+    occ_h, cost_h = occ_pin.numpy(), cost_pin.numpy().reshape(F, side, side)
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
         m.update(occ_h)
-        m.heuristic_rs(goal, (0, 0), out=cost_h)
+        m.heuristic_batch(hpp.VARIANT_RS, goals, out=cost_h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         flush.fill_(1)
         m.update(occ_h)                                       # H2D occupancy + K1 + sync
-        m.heuristic_rs(goal, (0, 0), out=cost_h)             # K3a + D2H cost field + sync
+        m.heuristic_batch(hpp.VARIANT_RS, goals, out=cost_h)  # K3a x F + D2H of the F cost fields + sync
     torch.cuda.synchronize()
     barrier()
     t_e2e = time.perf_counter() - t0
     t_all = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    e2e_value = n * e2e_steps * world / float(t_all.item()) / 1e6
-    checksum = float(cost_h[goal[1], goal[0]] + np.nan_to_num(cost_h[goal[1], :], posinf=0.0).sum())
+    e2e_value = F * n * e2e_steps * world / float(t_all.item()) / 1e6
+    checksum = float(sum(np.nan_to_num(cost_h[f, goals[f][1], :], posinf=0.0).sum() for f in range(F)))
+    # latency of one field through the reference-shaped call (hpp_heuristic_rs = holonomicCostsWithObstacles_planning)
+    m.heuristic_rs(goal, (0, 0), out=cost_h[0])
+    ts1 = []
+    for _ in range(3):
+        flush.fill_(2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.heuristic_batch_dev(hpp.VARIANT_RS, goals[:1], cost_dev)
+        ctx.sync()
+        ts1.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    m.heuristic_rs(goal, (0, 0), out=cost_h[0])
+    t_single_e2e = time.perf_counter() - t0
 
     peak, peak_src = measured_peak()
     heur_ms = statistics.mean(ms_heur)
-    achieved = HEUR_BYTES_PER_CELL * n / (heur_ms / 1e3) / 1e9
+    achieved = HEUR_BYTES_PER_CELL * n * F / (heur_ms / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -263,26 +285,30 @@ def ours_arm(args):
         "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg3", "map": f"{side}x{side} 8x8-block Bernoulli(0.30), seed 1+rank", "resolution": RES,
-                   "step": "hpp_map_update_dev (K1) + hpp_heuristic_batch_dev (K3a, 1 field)", "per_rank": "own map",
-                   "l2": "flushed between steps by a 256 MiB write outside the per-step event pair; the cost field "
+                   "fields_per_step": F, "goals": "distinct cells of the cleared 5x5 goal patch",
+                   "step": f"hpp_map_update_dev (K1) + hpp_heuristic_batch_dev (K3a, {F} fields in one launch)",
+                   "per_rank": "own map",
+                   "l2": "flushed between steps by a 256 MiB write outside the per-step event pair; one cost field "
                          "(134 MB) alone exceeds the 126 MB L2",
                    "timing": "CUDA events on the library's stream, per step, summed; max over ranks"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(8 * n),
-                "steps": e2e_steps, "api": "hpp_map_update + hpp_heuristic_rs (host buffers, pinned)",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(8 * n * F),
+                "steps": e2e_steps, "api": "hpp_map_update + hpp_heuristic_batch (host buffers, pinned)",
                 "checksum": checksum},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "heur_round_kernel (all relaxation rounds of one field)",
+        "roofline": {"bound": "hbm", "kernel": f"heur_persist_kernel (one persistent launch, {F} fields)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes": HEUR_BYTES_PER_CELL * n,
+                     "peak_source": peak_src, "algorithmic_bytes": HEUR_BYTES_PER_CELL * n * F,
                      "ms": heur_ms,
                      "k1_layers": {"ms": statistics.mean(ms_edt),
                                    "achieved": EDT_BYTES_PER_CELL * n / (statistics.mean(ms_edt) / 1e3) / 1e9}},
         "wall_s": t_wall,
     }
 
+    line["extra"] = {"single_field": {"ms_device": min(ts1) * 1e3, "mcells_per_s_device": n / min(ts1) / 1e6,
+                                      "ms_e2e": t_single_e2e * 1e3, "api": "hpp_heuristic_rs (host buffer, D2H inside)"}}
     if rank == 0 and world == 1 and not args.no_extras:
-        line["extra"] = extras(ctx, torch, hpp, stream)
+        line["extra"].update(extras(ctx, torch, hpp, stream))
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -395,6 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=4096)
+    ap.add_argument("--fields", type=int, default=16, help="goal fields (queries) per step, <= 25")
     ap.add_argument("--ref-cores", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

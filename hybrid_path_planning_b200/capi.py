@@ -91,6 +91,7 @@ def lib():
             "hpp_heuristic_rs": [vp, i32, i32, i32, i32, vp, C.POINTER(QuirkReport)],
             "hpp_heuristic_dubins": [vp, i32, i32, vp, C.POINTER(QuirkReport)],
             "hpp_heuristic_batch_dev": [vp, C.c_int, vp, sz, vp, vp],
+            "hpp_heuristic_batch": [vp, C.c_int, vp, sz, vp, vp],
             "hpp_expand": [vp, C.c_int, vp, sz, vp],
             "hpp_expand_dev": [vp, C.c_int, vp, sz, vp],
             "hpp_rs_shot": [vp, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)],
@@ -300,6 +301,16 @@ class Map:
         self.ctx.check(self.L.hpp_heuristic_batch_dev(self.h, variant, goals.ctypes.data, len(goals), _ptr(cost_dev),
                                                       C.cast(reps, C.c_void_p) if reps is not None else None))
         return reps
+
+    def heuristic_batch(self, variant, goals, out=None, want_reports=False):
+        """n goal cells -> n fields in a host buffer [n, H, W] (pass a pinned `out` to avoid the staging copy)"""
+        goals = np.ascontiguousarray(goals, np.int32).reshape(-1, 2)
+        cost = out if out is not None else np.empty((len(goals), self.H, self.W), np.float64)
+        assert cost.dtype == np.float64 and cost.size == len(goals) * self.n and cost.flags.c_contiguous
+        reps = (QuirkReport * len(goals))() if want_reports else None
+        self.ctx.check(self.L.hpp_heuristic_batch(self.h, variant, goals.ctypes.data, len(goals), cost.ctypes.data,
+                                                  C.cast(reps, C.c_void_p) if reps is not None else None))
+        return (cost, reps) if want_reports else cost
 
     def num_commands(self, variant):
         return int(self.L.hpp_num_commands(C.byref(self.params), variant))

@@ -32,6 +32,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "hpp_internal.cuh"
 
 namespace {
@@ -40,7 +42,6 @@ constexpr int HB = 32;  // block side = one warp, lane = row
 constexpr unsigned FULL = 0xffffffffu;
 constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
 constexpr int PHASE_SWEEPS = 8;
-constexpr int HEAVY_ROW = 6;  // rows with at least this many needed cells are evaluated lane-per-column
 
 // direction bits of the tile activity flags / out flags
 enum { DIR_N = 1, DIR_S = 2, DIR_W = 4, DIR_E = 8, DIR_NW = 16, DIR_NE = 32, DIR_SW = 64, DIR_SE = 128 };
@@ -64,7 +65,10 @@ struct heur_args {
   uint32_t *dmask;                 // [n_fields][n_tiles][NB*NB*32]  deferred cells
   uint32_t *bar;                   // [n_groups][32]: count, generation
   uint32_t *stats;                 // [n_fields][4]: rounds, tile visits, windows, sweeps of CTA rank 0
-  double delta;
+  unsigned long long *prof;        // optional [grid][8] cycle counters (HPP_HEUR_DEBUG): schedule, stage, solve,
+                                   // write-back, barrier wait, tiles, phases, longest single solve
+  double delta;                    // width of the global cost window
+  double delta_in;                 // width of the sub-windows inside a tile visit
   int group_size, n_groups;
   heur_weights wt;
 };
@@ -109,6 +113,7 @@ struct blk_state {
   uint32_t nearm;  // RS: near-obstacle cells of my row
   uint32_t dirty;  // my row changed (needs write-back)
   uint32_t posted; // I posted a border change to another warp of this CTA in this phase
+  uint32_t c_heavy, c_sparse, c_on, c_imp, c_sweeps;  // profiling counters (warp-uniform except c_on/c_imp: lane sums)
 };
 
 template <int NB>
@@ -133,34 +138,46 @@ __device__ __forceinline__ void post(uint32_t *s_inc, uint32_t *s_out, int bx, i
   }
 }
 
-// dilate the propagating changes p (one mask per lane = row) to the 8-neighbourhood: own block -> need masks,
-// across the block border -> the neighbour warp's incoming mask or the tile's out flags
+// Cells that a changed cell may improve, as three row masks per lane: bit (x+1) <-> column x (bits 0 and 33 are the
+// columns just outside the block) of the row above / my row / the row below.
+struct push3 {
+  unsigned long long up, own, dn;
+};
+
+// nmask: bit 0 NW, 1 N, 2 NE, 3 W, 4 E, 5 SW, 6 S, 7 SE  (neighbours of column x of my row)
+__device__ __forceinline__ void add_push(push3 &ps, int x, uint32_t nmask) {
+  ps.up |= (unsigned long long)(nmask & 7u) << x;
+  ps.own |= (unsigned long long)(((nmask >> 3) & 1u) | ((nmask >> 2) & 4u)) << x;
+  ps.dn |= (unsigned long long)((nmask >> 5) & 7u) << x;
+}
+
+// exchange the row masks between neighbouring lanes (= rows), turn them into need bits of my block, and post
+// what leaves the block to the neighbouring warp's incoming mask or to the tile's out flags
 template <int NB>
-__device__ __forceinline__ void propagate(uint32_t p, blk_state &st, uint32_t *s_inc, uint32_t *s_out, int bx, int by,
+__device__ __forceinline__ void propagate(const push3 &ps, blk_state &st, uint32_t *s_inc, uint32_t *s_out, int bx, int by,
                                           int lane) {
-  const uint32_t h = p | (p << 1) | (p >> 1);
-  uint32_t hu = __shfl_up_sync(FULL, h, 1), hd = __shfl_down_sync(FULL, h, 1);
-  if (lane == 0) hu = 0;
-  if (lane == 31) hd = 0;
-  st.need |= (((p << 1) | (p >> 1)) | hu | hd) & st.freem;
-  const bool edge = (p & 0x80000001u) || ((lane == 0 || lane == 31) && p);
+  unsigned long long from_above = __shfl_up_sync(FULL, ps.dn, 1), from_below = __shfl_down_sync(FULL, ps.up, 1);
+  if (lane == 0) from_above = 0;
+  if (lane == 31) from_below = 0;
+  const unsigned long long tot = ps.own | from_above | from_below;
+  st.need |= (uint32_t)(tot >> 1) & st.freem;
+  const bool spill_l = tot & 1ull, spill_r = (tot >> 33) & 1ull;
+  const bool edge = spill_l || spill_r || (lane == 0 && ps.up) || (lane == 31 && ps.dn);
   if (__any_sync(FULL, edge)) {
     __threadfence_block();  // the cost stores of this sweep before the notifications
-    uint32_t pu = __shfl_up_sync(FULL, p, 1), pd = __shfl_down_sync(FULL, p, 1);
-    if (lane == 0) pu = 0;
-    if (lane == 31) pd = 0;
-    const uint32_t pv = p | pu | pd;
-    if (pv & 1u) post<NB>(s_inc, s_out, bx, by, -1, 0, lane, 0x80000000u, st);
-    if (pv >> 31) post<NB>(s_inc, s_out, bx, by, 1, 0, lane, 1u, st);
-    if (lane == 0 && p) {
-      post<NB>(s_inc, s_out, bx, by, 0, -1, 31, h, st);
-      if (p & 1u) post<NB>(s_inc, s_out, bx, by, -1, -1, 31, 0x80000000u, st);
-      if (p >> 31) post<NB>(s_inc, s_out, bx, by, 1, -1, 31, 1u, st);
+    if (spill_l) post<NB>(s_inc, s_out, bx, by, -1, 0, lane, 0x80000000u, st);
+    if (spill_r) post<NB>(s_inc, s_out, bx, by, 1, 0, lane, 1u, st);
+    if (lane == 0 && ps.up) {
+      const uint32_t mid = (uint32_t)(ps.up >> 1);
+      if (mid) post<NB>(s_inc, s_out, bx, by, 0, -1, 31, mid, st);
+      if (ps.up & 1ull) post<NB>(s_inc, s_out, bx, by, -1, -1, 31, 0x80000000u, st);
+      if ((ps.up >> 33) & 1ull) post<NB>(s_inc, s_out, bx, by, 1, -1, 31, 1u, st);
     }
-    if (lane == 31 && p) {
-      post<NB>(s_inc, s_out, bx, by, 0, 1, 0, h, st);
-      if (p & 1u) post<NB>(s_inc, s_out, bx, by, -1, 1, 0, 0x80000000u, st);
-      if (p >> 31) post<NB>(s_inc, s_out, bx, by, 1, 1, 0, 1u, st);
+    if (lane == 31 && ps.dn) {
+      const uint32_t mid = (uint32_t)(ps.dn >> 1);
+      if (mid) post<NB>(s_inc, s_out, bx, by, 0, 1, 0, mid, st);
+      if (ps.dn & 1ull) post<NB>(s_inc, s_out, bx, by, -1, 1, 0, 0x80000000u, st);
+      if ((ps.dn >> 33) & 1ull) post<NB>(s_inc, s_out, bx, by, 1, 1, 0, 1u, st);
     }
   }
 }
@@ -172,29 +189,40 @@ struct eval_w {
   const double *db;       // Dubins: [2][10] in shared memory
 };
 
-// evaluate one cell by pull.  e = shared index of the cell.  Returns the candidate cost.
+// Evaluate one cell by PULL (e = shared index of the cell): returns the candidate cost, and in nmask the neighbours
+// that a cell of cost `best` could still improve (a superset: the cheapest possible edge weight is used for RS, the
+// exact source-dependent weight for Dubins), so that settled cells behind the wave front are not re-evaluated.
 template <int VARIANT, int S>
 __device__ __forceinline__ double eval_cell(const volatile double *cs, const volatile uint8_t *cl, int e, bool near,
-                                            const eval_w &wt) {
+                                            const eval_w &wt, uint32_t &nmask) {
+  const double nw = cs[e - S - 1], n = cs[e - S], ne = cs[e - S + 1], w = cs[e - 1], ea = cs[e + 1];
+  const double sw = cs[e + S - 1], s = cs[e + S], se = cs[e + S + 1];
+  double best, t1, t2;
   if (VARIANT == HPP_VARIANT_RS) {
-    const double n = cs[e - S], s = cs[e + S], w = cs[e - 1], ea = cs[e + 1];
-    const double nw = cs[e - S - 1], ne = cs[e - S + 1], sw = cs[e + S - 1], se = cs[e + S + 1];
     const double mc = dmin(dmin(n, s), dmin(w, ea));
     const double md = dmin(dmin(nw, ne), dmin(sw, se));
     const double wc = near ? wt.c1 : wt.c0, wd = near ? wt.d1 : wt.d0;
-    return dmin(mc + wc, md + wd);
+    best = dmin(mc + wc, md + wd);
+    t1 = best + wt.c0;
+    t2 = best + wt.d0;
   } else {
-    double best = wt.init;
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-      for (int dx = -1; dx <= 1; dx++) {
-        if (dx == 0 && dy == 0) continue;
-        const int u = e + dy * S + dx;
-        best = dmin(best, cs[u] + wt.db[((dx != 0 && dy != 0) ? 10 : 0) + (cl[u] & CLS_CNT_MASK)]);
-      }
-    return best;
+    const double *db = wt.db;
+    best = wt.init;
+    best = dmin(best, nw + db[10 + (cl[e - S - 1] & CLS_CNT_MASK)]);
+    best = dmin(best, n + db[cl[e - S] & CLS_CNT_MASK]);
+    best = dmin(best, ne + db[10 + (cl[e - S + 1] & CLS_CNT_MASK)]);
+    best = dmin(best, w + db[cl[e - 1] & CLS_CNT_MASK]);
+    best = dmin(best, ea + db[cl[e + 1] & CLS_CNT_MASK]);
+    best = dmin(best, sw + db[10 + (cl[e + S - 1] & CLS_CNT_MASK)]);
+    best = dmin(best, s + db[cl[e + S] & CLS_CNT_MASK]);
+    best = dmin(best, se + db[10 + (cl[e + S + 1] & CLS_CNT_MASK)]);
+    const int k = cl[e] & CLS_CNT_MASK;  // as a SOURCE this cell charges its own 3x3 count
+    t1 = best + db[k];
+    t2 = best + db[10 + k];
   }
+  nmask = (t2 < nw ? 1u : 0u) | (t1 < n ? 2u : 0u) | (t2 < ne ? 4u : 0u) | (t1 < w ? 8u : 0u) | (t1 < ea ? 16u : 0u) |
+          (t2 < sw ? 32u : 0u) | (t1 < s ? 64u : 0u) | (t2 < se ? 128u : 0u);
+  return best;
 }
 
 // one sweep of my block: returns false when there was nothing to do
@@ -211,10 +239,25 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     st.need |= inc & st.freem;
   }
   if (!__any_sync(FULL, st.need != 0)) return false;
+  st.c_sweeps++;
   const int ebase = (by * HB + 1) * S + bx * HB + 2;  // shared index of cell (row 0, col 0) of my block
-  uint32_t p = 0;
-  // rows with many needed cells: one lane per column
-  uint32_t heavy = __ballot_sync(FULL, __popc(st.need) >= HEAVY_ROW);
+  push3 ps = {0ull, 0ull, 0ull};
+  // Split the rows into "heavy" ones (evaluated one lane per column, one iteration per row) and "sparse" ones (one
+  // cell per lane and iteration, as many iterations as the fullest sparse row): pick the threshold that minimises
+  // the iteration count of this sweep.
+  const int cnt = __popc(st.need);
+  int thr = 33, best_cost = __reduce_max_sync(FULL, cnt);  // everything sparse
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    constexpr int cand[7] = {2, 3, 4, 6, 8, 12, 20};
+    const int t = cand[k];
+    const int c = __popc(__ballot_sync(FULL, cnt >= t)) + (t - 1);
+    if (t - 1 < best_cost && c < best_cost) {
+      best_cost = c;
+      thr = t;
+    }
+  }
+  uint32_t heavy = __ballot_sync(FULL, cnt >= thr);
   while (heavy) {
     const int r = __ffs(heavy) - 1;
     heavy &= heavy - 1;
@@ -222,49 +265,83 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     const uint32_t nm = __shfl_sync(FULL, st.nearm, r);
     const int e = ebase + r * S + lane;
     const bool on = (m >> lane) & 1u;
+    st.c_heavy++;
+    st.c_on += on;
     const double c0 = cs[e];
-    const double best = eval_cell<VARIANT, S>(cs, cl, e, (nm >> lane) & 1u, wt);
+    uint32_t nmask;
+    const double best = eval_cell<VARIANT, S>(cs, cl, e, (nm >> lane) & 1u, wt, nmask);
     const bool imp = on && best < c0;
     if (imp) cs[e] = best;
+    const bool low = imp && best < bound;
+    st.c_imp += imp;
+    if (!low) nmask = 0;
     const uint32_t bimp = __ballot_sync(FULL, imp);
-    const uint32_t blow = __ballot_sync(FULL, imp && best < bound);
+    const uint32_t blow = __ballot_sync(FULL, low);
+    const unsigned long long up = (unsigned long long)__ballot_sync(FULL, nmask & 1u) |
+                                  ((unsigned long long)__ballot_sync(FULL, nmask & 2u) << 1) |
+                                  ((unsigned long long)__ballot_sync(FULL, nmask & 4u) << 2);
+    const unsigned long long own = (unsigned long long)__ballot_sync(FULL, nmask & 8u) |
+                                   ((unsigned long long)__ballot_sync(FULL, nmask & 16u) << 2);
+    const unsigned long long dn = (unsigned long long)__ballot_sync(FULL, nmask & 32u) |
+                                  ((unsigned long long)__ballot_sync(FULL, nmask & 64u) << 1) |
+                                  ((unsigned long long)__ballot_sync(FULL, nmask & 128u) << 2);
     if (lane == r) {
       st.need = 0;
-      p |= blow;
+      ps.up |= up;
+      ps.own |= own;
+      ps.dn |= dn;
       st.defer = (st.defer | bimp) & ~blow;
       if (bimp) st.dirty = 1;
     }
     __syncwarp();
   }
-  // sparse rows: one cell per lane and iteration
+  // sparse rows: two cells per lane and iteration (independent evaluations overlap their latencies)
   while (__any_sync(FULL, st.need != 0)) {
-    const bool on = st.need != 0;
-    const int x = on ? __ffs(st.need) - 1 : 0;
+    st.c_sparse++;
+    const bool on0 = st.need != 0;
+    const int x0 = on0 ? __ffs(st.need) - 1 : 0;
     st.need &= st.need - 1;
-    const int e = ebase + lane * S + x;
-    const double c0 = cs[e];
-    const double best = eval_cell<VARIANT, S>(cs, cl, e, (st.nearm >> x) & 1u, wt);
-    const bool imp = on && best < c0;
-    if (imp) {
-      cs[e] = best;
-      const uint32_t bit = 1u << x;
+    const bool on1 = st.need != 0;
+    const int x1 = on1 ? __ffs(st.need) - 1 : 0;
+    st.need &= st.need - 1;
+    st.c_on += (on0 ? 1 : 0) + (on1 ? 1 : 0);
+    const int e0 = ebase + lane * S + x0, e1 = ebase + lane * S + x1;
+    const double c0 = cs[e0], c1 = cs[e1];
+    uint32_t nm0, nm1;
+    const double b0 = eval_cell<VARIANT, S>(cs, cl, e0, (st.nearm >> x0) & 1u, wt, nm0);
+    const double b1 = eval_cell<VARIANT, S>(cs, cl, e1, (st.nearm >> x1) & 1u, wt, nm1);
+    const bool imp0 = on0 && b0 < c0, imp1 = on1 && b1 < c1;
+    if (imp0) {
+      st.c_imp++;
+      cs[e0] = b0;
       st.dirty = 1;
-      if (best < bound) {
-        p |= bit;
-        st.defer &= ~bit;
+      if (b0 < bound) {
+        add_push(ps, x0, nm0);
+        st.defer &= ~(1u << x0);
       } else {
-        st.defer |= bit;
+        st.defer |= 1u << x0;
+      }
+    }
+    if (imp1) {
+      st.c_imp++;
+      cs[e1] = b1;
+      st.dirty = 1;
+      if (b1 < bound) {
+        add_push(ps, x1, nm1);
+        st.defer &= ~(1u << x1);
+      } else {
+        st.defer |= 1u << x1;
       }
     }
     __syncwarp();
   }
-  if (__any_sync(FULL, p != 0)) propagate<NB>(p, st, s_inc, s_out, bx, by, lane);
+  if (__any_sync(FULL, (ps.up | ps.own | ps.dn) != 0ull)) propagate<NB>(ps, st, s_inc, s_out, bx, by, lane);
   return true;
 }
 
 // ---------------------------------------------------------------- the persistent kernel
 template <int NB, int VARIANT>
-__global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(const __grid_constant__ heur_args a) {
+__global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : 4) heur_persist_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<NB>;
   constexpr int T = C::T, S = C::S, ROWS = C::ROWS, NBLK = C::NBLK, THREADS = C::THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -274,7 +351,7 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
   uint8_t *cl_nv = (uint8_t *)(s_list + THREADS);                       // ROWS * S (Dubins only)
   volatile double *cs = cs_nv;
   const volatile uint8_t *cl = cl_nv;
-  __shared__ unsigned long long s_gmin, s_pmin;
+  __shared__ unsigned long long s_gmin, s_minp[2];
   __shared__ uint32_t s_count, s_mine, s_out, s_warp_cnt[32];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -302,6 +379,14 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
     uint32_t *dmask = a.dmask + (size_t)field * n_tiles * NBLK * 32;
     double bound = 0.0;
     uint32_t rounds = 0, visits = 0, windows = 0, sweeps = 0;
+    unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tk = clock64();
+#define PF_MARK(i)                         \
+  if (a.prof) {                            \
+    const long long now_ = clock64();      \
+    pf[i] += (unsigned long long)(now_ - tk); \
+    tk = now_;                             \
+  }
 
     for (uint32_t round = 0;; round++) {
       // act buffers rotate: cur is read-only this round, next receives posts, clr is zeroed for the round after
@@ -373,7 +458,7 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
         }
         if (on) {
           const uint32_t rank = pre + __popc(b & ((1u << lane) - 1u));
-          if ((int)(rank % (uint32_t)a.group_size) == grank) s_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
+          if ((int)((rank + round) % (uint32_t)a.group_size) == grank) s_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
         }
         base_rank += chunk;
         __syncthreads();
@@ -385,6 +470,7 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
           const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
           const int x0 = tx * T, y0 = ty * T;
           visits++;
+          PF_MARK(0);
           // stage costs (+ halo); out-of-bounds cells hold the initial value and are never free
           for (int i = tid; i < ROWS * (T + 2); i += THREADS) {
             const int r = i / (T + 2), c = i - r * (T + 2);
@@ -401,7 +487,8 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
           s_inc[tid] = 0;
           if (tid == 0) {
             s_out = 0;
-            s_pmin = INF_BITS;
+            s_minp[0] = INF_BITS;
+            s_minp[1] = INF_BITS;
           }
           // my row's masks
           blk_state st;
@@ -419,10 +506,12 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
             st.need = 0;
             st.dirty = 0;
             st.posted = 0;
+            st.c_heavy = st.c_sparse = st.c_on = st.c_imp = st.c_sweeps = 0;
             st.defer = __ldcg(dmask + ((size_t)tile * NBLK + wid) * 32 + lane);
           }
           const uint32_t af = __ldcg(act_cur + tile);
           __syncthreads();
+          PF_MARK(1);
           // ring cells facing a neighbour tile that posted a border change
           if (af) {
             if ((af & DIR_N) && by == 0 && lane == 0) st.need |= st.freem;
@@ -434,31 +523,25 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
             if ((af & DIR_SW) && bx == 0 && by == NB - 1 && lane == 31) st.need |= st.freem & 1u;
             if ((af & DIR_SE) && bx == NB - 1 && by == NB - 1 && lane == 31) st.need |= st.freem & 0x80000000u;
           }
-          // release the deferred cells that fell below the bound
-          {
-            const int ebase = (by * HB + 1) * S + bx * HB + 2;
-            uint32_t rel = 0;
-            for (uint32_t m = st.defer; m; m &= m - 1) {
-              const int x = __ffs(m) - 1;
-              if (cs[ebase + lane * S + x] < bound) rel |= 1u << x;
+          // ---- relax to the tile-local fixed point under the bound, in sub-windows of delta_in: changes whose cost
+          // is >= lb wait in the deferred masks until the tile has nothing cheaper left, then lb moves to (cheapest
+          // deferred cost) + delta_in.  This is delta-stepping inside the tile: it keeps the front thin and close
+          // to cost order, so a cell is improved about once instead of twice.
+          double lb = 0.0;  // first pass: only the ring cells flagged by the neighbour tiles are evaluated
+          unsigned long long gmin_left = INF_BITS;
+          for (int it = 0;; it++) {
+            // (a warp that posted votes to continue: the receiver may already be waiting at the barrier)
+            for (;;) {
+              for (int k2 = 0; k2 < PHASE_SWEEPS; k2++) {
+                if (!sweep<NB, VARIANT>(cs, cl, s_inc, &s_out, st, wid, bx, by, lane, lb, wt)) break;
+                if (wid == 0) sweeps++;
+              }
+              const int more = __syncthreads_or((st.need != 0) || st.posted);
+              st.posted = 0;
+              pf[6]++;
+              if (!more) break;
             }
-            st.defer &= ~rel;
-            __syncwarp();
-            if (__any_sync(FULL, rel != 0)) propagate<NB>(rel, st, s_inc, &s_out, bx, by, lane);
-          }
-          // ---- relax to the tile-local fixed point under the bound
-          // (a warp that posted votes to continue: the receiver may already be waiting at the barrier)
-          for (;;) {
-            for (int k2 = 0; k2 < PHASE_SWEEPS; k2++) {
-              if (!sweep<NB, VARIANT>(cs, cl, s_inc, &s_out, st, wid, bx, by, lane, bound, wt)) break;
-              if (wid == 0) sweeps++;
-            }
-            const int more = __syncthreads_or((st.need != 0) || st.posted);
-            st.posted = 0;
-            if (!more) break;
-          }
-          // ---- write back: changed rows, deferred masks, cheapest deferred cost, notifications
-          {
+            // cheapest deferred cell of the tile
             const int ebase = (by * HB + 1) * S + bx * HB + 2;
             unsigned long long mn = INF_BITS;
             for (uint32_t m = st.defer; m; m &= m - 1) {
@@ -467,10 +550,48 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
               mn = v < mn ? v : mn;
             }
             for (int d = 16; d; d >>= 1) {
-              const unsigned long long o = __shfl_down_sync(FULL, mn, d);
+              const unsigned long long o = __shfl_xor_sync(FULL, mn, d);
               mn = o < mn ? o : mn;
             }
-            if (lane == 0 && mn != INF_BITS) atomicMin(&s_pmin, mn);
+            if (lane == 0 && mn != INF_BITS) atomicMin(&s_minp[it & 1], mn);
+            __syncthreads();
+            gmin_left = s_minp[it & 1];
+            if (tid == 0) s_minp[(it + 1) & 1] = INF_BITS;
+            const double gm = __longlong_as_double((long long)gmin_left);
+            if (gmin_left == INF_BITS || !(gm < bound)) break;
+            lb = gm + a.delta_in;
+            if (lb > bound) lb = bound;
+            // release the deferred cells that fell below lb
+            uint32_t rel = 0;
+            push3 ps = {0ull, 0ull, 0ull};
+            for (uint32_t m = st.defer; m; m &= m - 1) {
+              const int x = __ffs(m) - 1;
+              if (cs[ebase + lane * S + x] < lb) {
+                rel |= 1u << x;
+                add_push(ps, x, 0xffu);  // all eight neighbours: the exact set is not known any more
+              }
+            }
+            st.defer &= ~rel;
+            __syncwarp();
+            if (__any_sync(FULL, rel != 0)) propagate<NB>(ps, st, s_inc, &s_out, bx, by, lane);
+          }
+          if (a.prof) {
+            unsigned long long *pw = a.prof + (size_t)gridDim.x * 8;
+            if (lane == 0) {
+              atomicAdd(pw + 0, (unsigned long long)st.c_heavy);
+              atomicAdd(pw + 1, (unsigned long long)st.c_sparse);
+              atomicAdd(pw + 4, (unsigned long long)st.c_sweeps);
+            }
+            atomicAdd(pw + 2, (unsigned long long)st.c_on);
+            atomicAdd(pw + 3, (unsigned long long)st.c_imp);
+            const unsigned long long d = (unsigned long long)(clock64() - tk);
+            if (d > pf[7]) pf[7] = d;
+            pf[5]++;
+          }
+          PF_MARK(2);
+          // ---- write back: changed rows, deferred masks, cheapest deferred cost, notifications
+          {
+            const int ebase = (by * HB + 1) * S + bx * HB + 2;
             __stcg(dmask + ((size_t)tile * NBLK + wid) * 32 + lane, st.defer);
             uint32_t dr = __ballot_sync(FULL, st.dirty != 0);
             const int gx = x0 + bx * HB + lane;
@@ -483,7 +604,7 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
           }
           __syncthreads();
           if (tid == 0) {
-            __stcg(pm_next + tile, s_pmin);
+            __stcg(pm_next + tile, gmin_left);
             const uint32_t o = s_out;
             if (o) {
               __threadfence();
@@ -502,10 +623,16 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, 1) heur_persist_kernel(
             }
           }
           __syncthreads();
+          PF_MARK(3);
         }
       }
+      PF_MARK(0);
       group_barrier(bar, a.group_size);
+      PF_MARK(4);
     }
+#undef PF_MARK
+    if (a.prof && tid == 0)
+      for (int i = 0; i < 8; i++) a.prof[blockIdx.x * 8 + i] = pf[i];
     if (grank == 0 && tid == 0) {
       uint32_t *s = a.stats + field * 4;
       s[0] = rounds;
@@ -614,10 +741,10 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", NB >= 4 ? 1 : 4);
   if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   const int G = per_sm * c->sm_count;  // co-resident CTAs
-  // CTA groups: one field at a time per group.  A group never needs more CTAs than the widest ring of active
-  // tiles (about a quarter of the tiles); small maps get one CTA per field and many fields in flight.
-  int gs = ctas_per_field_hint > 0 ? ctas_per_field_hint : (a.n_tiles + 3) / 4;
-  if (ctas_per_field_hint <= 0 && (long long)gs * a.n_fields < G) gs = G / a.n_fields;  // few fields: share the whole GPU
+  // CTA groups: one field at a time per group, the groups never synchronise with each other.  A tile solve is a
+  // latency chain on a few warps, so a single field cannot fill the GPU (its CTAs mostly wait for the slowest tile
+  // of the round); with several fields the GPU is shared evenly, down to one CTA per field (no barrier at all).
+  int gs = ctas_per_field_hint > 0 ? ctas_per_field_hint : G / a.n_fields;
   if (gs > a.n_tiles) gs = a.n_tiles;  // never more CTAs than tiles
   if (gs > G) gs = G;
   if (gs < 1) gs = 1;
@@ -683,6 +810,16 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.n_tiles = n_tiles;
   a.n_fields = (int)n_fields;
   a.delta = env_double("HPP_HEUR_DELTA", 2.0 * C::T);
+  a.delta_in = env_double("HPP_HEUR_DELTA_IN", 16.0);
+  const bool debug = getenv("HPP_HEUR_DEBUG") != nullptr;
+  const size_t prof_n = (size_t)c->sm_count * 8 * 8 + 8;
+  if (debug) {
+    void *pp;
+    s = hpp_scratch(c, 1, prof_n * 8, &pp);
+    if (s != HPP_OK) return s;
+    a.prof = (unsigned long long *)pp;
+    HPP_CUDA(c, cudaMemsetAsync(a.prof, 0, prof_n * 8, c->stream));
+  }
 
   const size_t total = m->n * n_fields;
   size_t want = total / 1024 + 1;
@@ -697,6 +834,32 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
                                   : launch_persist<NB, HPP_VARIANT_DUBINS>(c, a, hint);
   if (s != HPP_OK) return s;
 
+  if (debug) {
+    const int grid = a.group_size * a.n_groups;
+    std::vector<unsigned long long> hp((size_t)grid * 8 + 8);
+    HPP_CUDA(c, cudaMemcpyAsync(hp.data(), a.prof, hp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+    const char *nm[8] = {"schedule", "stage", "solve", "writeback", "barrier", "tiles", "phases", "max_solve"};
+    for (int i = 0; i < 8; i++) {
+      unsigned long long sum = 0, mx = 0;
+      for (int b = 0; b < grid; b++) {
+        sum += hp[(size_t)b * 8 + i];
+        if (hp[(size_t)b * 8 + i] > mx) mx = hp[(size_t)b * 8 + i];
+      }
+      fprintf(stderr, "[hpp heur prof] %-9s mean/CTA=%12.0f max=%12llu cta0=%12llu\n", nm[i], (double)sum / grid, mx, hp[i]);
+    }
+    {
+      const unsigned long long *pw = hp.data() + (size_t)grid * 8;
+      fprintf(stderr, "[hpp heur prof] warp totals: sweeps=%llu heavy_iter=%llu sparse_iter=%llu evals=%llu improved=%llu\n", pw[4],
+              pw[0], pw[1], pw[2], pw[3]);
+    }
+    uint32_t *h_stats = (uint32_t *)((uint8_t *)h_stage + goals_b);
+    HPP_CUDA(c, cudaMemcpyAsync(h_stats, a.stats, n_fields * 16, cudaMemcpyDeviceToHost, c->stream));
+    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t f = 0; f < n_fields && f < 4; f++)
+      fprintf(stderr, "[hpp heur] NB=%d delta=%g groups=%d x %d CTAs, field %zu: rounds=%u visits=%u windows=%u sweeps(cta0,warp0)=%u\n",
+              NB, a.delta, a.n_groups, a.group_size, f, h_stats[4 * f], h_stats[4 * f + 1], h_stats[4 * f + 2], h_stats[4 * f + 3]);
+  }
   if (reports) {
     uint32_t *h_stats = (uint32_t *)((uint8_t *)h_stage + goals_b);
     unsigned long long *h_fstats = (unsigned long long *)((uint8_t *)h_stage + goals_b + stats_b);
@@ -745,6 +908,33 @@ extern "C" hpp_status hpp_heuristic_batch_dev(hpp_map *m, int variant, const int
   if (env_nb == 2 || env_nb == 4) nb = env_nb;
   return nb == 4 ? run_batch<4>(m, variant, goal_xy, n_fields, cost_dev, reports)
                  : run_batch<2>(m, variant, goal_xy, n_fields, cost_dev, reports);
+}
+
+// host-buffer batch: n_fields goal cells on one map, fields returned in cost (n_fields x W*H doubles, pinned memory
+// recommended).  The fields are solved in chunks on the device and copied out chunk by chunk.
+extern "C" hpp_status hpp_heuristic_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_fields, double *cost,
+                                          hpp_quirk_report *reports) {
+  if (!m || !goal_xy || !cost || n_fields == 0) return HPP_ERR_ARG;
+  hpp_ctx *c = m->ctx;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  size_t free_b = 0, total_b = 0;
+  HPP_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  const size_t field_b = m->n * sizeof(double);
+  size_t chunk = n_fields;
+  const size_t have = c->d_scratch_bytes[3] + free_b / 2;
+  if (chunk * field_b > have) chunk = have / field_b;
+  if (chunk < 1) HPP_FAIL(c, HPP_ERR_NOMEM, "not enough device memory for one heuristic field");
+  void *d_cost;
+  hpp_status s = hpp_scratch(c, 3, chunk * field_b, &d_cost);
+  if (s != HPP_OK) return s;
+  for (size_t f0 = 0; f0 < n_fields; f0 += chunk) {
+    const size_t nf = n_fields - f0 < chunk ? n_fields - f0 : chunk;
+    s = hpp_heuristic_batch_dev(m, variant, goal_xy + 2 * f0, nf, (double *)d_cost, reports ? reports + f0 : nullptr);
+    if (s != HPP_OK) return s;
+    HPP_CUDA(c, cudaMemcpyAsync(cost + f0 * m->n, d_cost, nf * field_b, cudaMemcpyDeviceToHost, c->stream));
+    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return HPP_OK;
 }
 
 // H1 (RS/src/HybridAstar.cpp:452-472): every 70000 settled cells the reference stops if the start cell is

@@ -142,6 +142,11 @@ hpp_status hpp_heuristic_dubins(hpp_map *map, int32_t goal_x, int32_t goal_y, do
 hpp_status hpp_heuristic_batch_dev(hpp_map *map, int variant, const int32_t *goal_xy, size_t n_fields,
                                    double *cost_dev, hpp_quirk_report *reports /* n_fields or NULL */);
 
+/* same with a host output buffer: cost = n_fields x W*H doubles (pinned memory recommended); the multi-query
+ * driver's form of holonomicCostsWithObstacles_planning (one field per distinct goal cell of a batch of queries) */
+hpp_status hpp_heuristic_batch(hpp_map *map, int variant, const int32_t *goal_xy, size_t n_fields, double *cost,
+                               hpp_quirk_report *reports /* n_fields or NULL */);
+
 /* ---------------------------------------------------------------- successor expansion
  * Replaces HybridAstar::GetnextNeighbours + PathCost (RS/include/HybridAstar.h:52-53,
  * RS/src/HybridAstar.cpp:25-107; DB/src/HybridAstar.cpp:23-105) for n parents at once. */
