@@ -77,6 +77,7 @@ def lib():
             "hpp_map_create": [vp, vp, u32, u32, C.c_float, dbl, dbl, C.POINTER(Params), C.POINTER(vp)],
             "hpp_map_create_dev": [vp, vp, u32, u32, C.c_float, dbl, dbl, C.POINTER(Params), C.POINTER(vp)],
             "hpp_map_destroy": [vp],
+            "hpp_map_set_params": [vp, C.POINTER(Params)],
             "hpp_map_update": [vp, vp],
             "hpp_map_update_dev": [vp, vp],
             "hpp_map_layers": [vp, vp, vp],

@@ -261,6 +261,13 @@ extern "C" hpp_status hpp_map_update_dev(hpp_map *m, const int8_t *occ_dev) {
   return map_build(m);
 }
 
+extern "C" hpp_status hpp_map_set_params(hpp_map *m, const hpp_params *params) {
+  if (!m || !params) return HPP_ERR_ARG;
+  if (params->path_length > HPP_MAX_SIM) HPP_FAIL(m->ctx, HPP_ERR_UNSUPPORTED, "pathLength > %d", HPP_MAX_SIM);
+  setup_car(&m->car, params);
+  return HPP_OK;
+}
+
 extern "C" hpp_status hpp_map_destroy(hpp_map *m) {
   if (!m) return HPP_ERR_ARG;
   cudaSetDevice(m->ctx->device);

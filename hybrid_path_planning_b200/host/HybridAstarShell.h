@@ -1,0 +1,59 @@
+// HybridAstarShell.h -- drop-in for the reference's HybridAstar of both packages (RS/include/HybridAstar.h:44-96,
+// DB/include/HybridAstar.h:33-83): same constructor and public methods, bodies call the C ABI.
+//   HybridAstar        reeds_shepp_hybrid_astar  (26 motion commands, circle footprint, Reeds-Shepp shots)
+//   HybridAstarDubins  dubins_hybrid_star        (13 forward commands, SAT footprint, Dubins shots)
+// A package selects its class with `using HybridAstar = HybridAstarDubins;`.
+// run() hands the whole query to hpp_plan_batch: heuristic field, open list, shots and expansions stay on the device;
+// pop order, tie-breaking, the 3500-iteration cap and the failure convention (a 1-state path = the goal) follow
+// RS/src/HybridAstar.cpp:553-729.  run_batch() is the multi-query form (one call, n queries).
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "GridMapShell.h"
+
+template <int VARIANT>
+class HybridAstarT {
+ public:
+  HybridAstarT(Grid_map grid_map, CarData car_data, double simulationLength, double step_car);
+
+  std::vector<State> run(State start_state, State goal_state);
+  std::vector<std::vector<State>> run_batch(const std::vector<State> &starts, const std::vector<State> &goals);
+
+  // RS/include/HybridAstar.h:52-53 / DB/include/HybridAstar.h:41-42
+  std::vector<std::shared_ptr<planner::Node>> GetnextNeighbours(const std::shared_ptr<planner::Node> &current_node);
+  // RS/include/HybridAstar.h:56 (reeds_shepp_Path) / DB/include/HybridAstar.h:47 (dubins_Path): nullptr = no shot
+  std::shared_ptr<planner::Node> analyticShot(const std::shared_ptr<planner::Node> &current_Node,
+                                              const std::shared_ptr<planner::Node> &goal_Node);
+  std::shared_ptr<planner::Node> reeds_shepp_Path(const std::shared_ptr<planner::Node> &c,
+                                                  const std::shared_ptr<planner::Node> &g) {
+    return analyticShot(c, g);
+  }
+  std::shared_ptr<planner::Node> dubins_Path(const std::shared_ptr<planner::Node> &c,
+                                             const std::shared_ptr<planner::Node> &g) {
+    return analyticShot(c, g);
+  }
+  // RS/include/HybridAstar.h:62: cost per cell, row-major [y*W + x], +inf (RS) / 1000 (Dubins) where unreachable
+  std::vector<double> holonomicCostsWithObstacles_planning(const std::shared_ptr<planner::Node> &GoalNode);
+  // DB/include/HybridAstar.h:51 form: one HolonomicNode per cell (only ->cost is meaningful, as in the caller)
+  std::vector<std::shared_ptr<planner::HolonomicNode>> holonomicCostsWithObstacles_nodes(
+      const std::shared_ptr<planner::Node> &GoalNode);
+  // set when the last heuristic call hit an input on which the reference's sequential quirks (H1/H2) may fire
+  const hpp_quirk_report &lastQuirkReport() const { return report_; }
+
+ private:
+  State withCell(State s) const;
+  Grid_map grid_map_;
+  CarData car_data_;
+  double simulationLength, step_car;
+  State start_state_;
+  hpp_quirk_report report_{};
+};
+
+using HybridAstar = HybridAstarT<HPP_VARIANT_RS>;
+using HybridAstarDubins = HybridAstarT<HPP_VARIANT_DUBINS>;
+
+// drop-in for map_inflate_node::InflateMap + CreateInflatedOccupancyGrid (MI/src/map_inflate_node.cpp:17,:118-161):
+// occupancy in, inflated occupancy out (same geometry), through hpp_inflate.
+std::vector<int8_t> InflateOccupancy(const std::vector<int8_t> &occ, uint32_t width, uint32_t height, double resolution,
+                                     double inflation_radius);

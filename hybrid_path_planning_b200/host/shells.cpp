@@ -1,0 +1,251 @@
+// shells.cpp -- bodies of the host shells (GridMapShell.h, HybridAstarShell.h): marshalling only, every computation
+// is a C-ABI call into libhpp_b200.so.  Errors of the library become std::runtime_error (the reference's own
+// conventions -- nullptr shot, 1-state failure path -- are kept as return values).
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#include "HybridAstarShell.h"
+
+namespace hpp_host {
+
+hpp_ctx *thread_ctx() {
+  struct Holder {
+    hpp_ctx *ctx = nullptr;
+    ~Holder() {
+      if (ctx) hpp_ctx_destroy(ctx);
+    }
+  };
+  static thread_local Holder h;
+  if (!h.ctx) {
+    const char *d = std::getenv("HPP_DEVICE");
+    const hpp_status st = hpp_ctx_create(d ? std::atoi(d) : 0, &h.ctx);
+    if (st != HPP_OK) throw std::runtime_error("hpp_ctx_create failed: no usable B200 (there is no CPU fallback)");
+  }
+  return h.ctx;
+}
+
+void fail(hpp_ctx *ctx, hpp_status st, const char *what) {
+  throw std::runtime_error(std::string(what) + ": status " + std::to_string((int)st) + ": " + hpp_last_error(ctx));
+}
+
+}  // namespace hpp_host
+
+using hpp_host::check;
+
+// ---------------------------------------------------------------------------------------------- Grid_map
+void Grid_map::init(const int8_t *occ, std::size_t n, uint32_t w, uint32_t h, float res, double ox, double oy) {
+  if (n != (std::size_t)w * h) throw std::runtime_error("Grid_map: data size does not match width*height");
+  resolution = res;  // float -> double, like the reference (hazard H6)
+  originX = ox;
+  originY = oy;
+  width = w;
+  height = h;
+  Max_origin_x = originX + width * resolution;
+  Max_origin_y = originY + height * resolution;
+  occ_ = std::make_shared<std::vector<int8_t>>(occ, occ + n);
+  auto handle = std::make_shared<hpp_host::MapHandle>();
+  handle->ctx = hpp_host::thread_ctx();
+  // default vehicle until setcarData (the reference's Grid_map also starts with a default-constructed CarData)
+  const hpp_params p = CarData(0.6, 2.75, 1.1, 1.2, 1.9).params(path_length_, step_car_);
+  check(handle->ctx, hpp_map_create(handle->ctx, occ, w, h, res, ox, oy, &p, &handle->map), "hpp_map_create");
+  h_ = handle;
+}
+
+void Grid_map::setcarData(const CarData &car_data) { setPlannerParams(car_data, path_length_, step_car_); }
+
+void Grid_map::setPlannerParams(const CarData &car_data, double pathLength, double step_car) {
+  car_ = car_data;
+  path_length_ = pathLength;
+  step_car_ = step_car;
+  if (!h_) return;
+  const hpp_params p = car_.params(path_length_, step_car_);
+  check(h_->ctx, hpp_map_set_params(h_->map, &p), "hpp_map_set_params");
+}
+
+bool Grid_map::isSingleStateCollisionFree(const State &s) {
+  const double xyh[3] = {s.x, s.y, s.heading};
+  uint8_t v = 1;
+  check(h_->ctx, hpp_collide_circles(h_->map, xyh, 1, &v), "hpp_collide_circles");
+  return v != 0;
+}
+
+bool Grid_map::checkCollisionSat(const State &s) {
+  const double xyh[3] = {s.x, s.y, s.heading};
+  uint8_t v = 1;
+  check(h_->ctx, hpp_collide_sat(h_->map, xyh, 1, &v), "hpp_collide_sat");
+  return v != 0;
+}
+
+bool Grid_map::isInCollision(int x, int y) const {
+  if (!isPointInBounds(x, y)) return true;
+  return (*occ_)[(std::size_t)toCellIndex(x, y)] > 0;
+}
+
+void Grid_map::layers(float *obstacle, float *distance) const {
+  check(h_->ctx, hpp_map_layers(h_->map, obstacle, distance), "hpp_map_layers");
+}
+
+// ---------------------------------------------------------------------------------------------- HybridAstar
+template <int V>
+HybridAstarT<V>::HybridAstarT(Grid_map grid_map, CarData car_data, double simulationLength_, double step_car_)
+    : grid_map_(grid_map), car_data_(car_data), simulationLength(simulationLength_), step_car(step_car_) {
+  grid_map_.setPlannerParams(car_data_, simulationLength, step_car);
+}
+
+template <int V>
+State HybridAstarT<V>::withCell(State s) const {
+  int cx, cy;
+  std::tie(cx, cy) = grid_map_.toCellID(s);
+  s.gridx = cx;
+  s.gridy = cy;
+  return s;
+}
+
+static std::vector<State> states_from(const double *t, int n) {
+  std::vector<State> out((std::size_t)n);
+  for (int i = 0; i < n; i++) {
+    out[i].x = t[5 * i];
+    out[i].y = t[5 * i + 1];
+    out[i].heading = t[5 * i + 2];
+    out[i].gridx = t[5 * i + 3];
+    out[i].gridy = t[5 * i + 4];
+  }
+  return out;
+}
+
+template <int V>
+std::vector<std::vector<State>> HybridAstarT<V>::run_batch(const std::vector<State> &starts,
+                                                           const std::vector<State> &goals) {
+  const std::size_t n = starts.size();
+  if (goals.size() != n) throw std::runtime_error("run_batch: starts and goals differ in length");
+  std::vector<std::vector<State>> out(n);
+  if (n == 0) return out;
+  std::vector<double> s(3 * n), g(3 * n);
+  for (std::size_t i = 0; i < n; i++) {
+    s[3 * i] = starts[i].x, s[3 * i + 1] = starts[i].y, s[3 * i + 2] = starts[i].heading;
+    g[3 * i] = goals[i].x, g[3 * i + 1] = goals[i].y, g[3 * i + 2] = goals[i].heading;
+  }
+  std::vector<hpp_plan> plans(n);
+  std::vector<double> traj;
+  std::size_t cap = 4096 * n, used = 0;
+  for (;;) {
+    traj.resize(cap * 5);
+    const hpp_status st =
+        hpp_plan_batch(grid_map_.handle(), V, s.data(), g.data(), n, plans.data(), traj.data(), cap, &used);
+    if (st == HPP_ERR_CAPACITY) {
+      cap = used > cap ? used : cap * 2;
+      continue;
+    }
+    check(grid_map_.ctx(), st, "hpp_plan_batch");
+    break;
+  }
+  for (std::size_t i = 0; i < n; i++) out[i] = states_from(traj.data() + 5 * plans[i].traj_offset, plans[i].n_states);
+  return out;
+}
+
+template <int V>
+std::vector<State> HybridAstarT<V>::run(State start_state, State goal_state) {
+  start_state_ = withCell(start_state);
+  return run_batch({start_state}, {goal_state})[0];
+}
+
+template <int V>
+std::vector<std::shared_ptr<planner::Node>> HybridAstarT<V>::GetnextNeighbours(
+    const std::shared_ptr<planner::Node> &cur) {
+  hpp_node in;
+  std::memset(&in, 0, sizeof in);
+  in.x = cur->Current_state.x;
+  in.y = cur->Current_state.y;
+  in.heading = cur->Current_state.heading;
+  in.cost = cur->Cost_path;
+  in.steer = cur->steeringAngle;
+  in.direction = cur->direction;
+  const hpp_params p = car_data_.params(simulationLength, step_car);
+  const int nc = hpp_num_commands(&p, V);
+  std::vector<hpp_child> kids((std::size_t)nc);
+  check(grid_map_.ctx(), hpp_expand(grid_map_.handle(), V, &in, 1, kids.data()), "hpp_expand");
+  int sim = 0;
+  while (sim < simulationLength && sim < HPP_MAX_SIM) sim++;
+  std::vector<std::shared_ptr<planner::Node>> out;
+  for (const hpp_child &k : kids) {
+    if (!k.valid) continue;  // the reference drops a rollout when any of its states collides
+    std::vector<State> traj = states_from(&k.traj[0][0], sim);
+    out.push_back(std::make_shared<planner::Node>(traj.back(), traj, k.cost, k.steer, k.direction, cur));
+  }
+  return out;
+}
+
+template <int V>
+std::shared_ptr<planner::Node> HybridAstarT<V>::analyticShot(const std::shared_ptr<planner::Node> &cur,
+                                                             const std::shared_ptr<planner::Node> &goal) {
+  hpp_node in;
+  std::memset(&in, 0, sizeof in);
+  in.x = cur->Current_state.x;
+  in.y = cur->Current_state.y;
+  in.heading = cur->Current_state.heading;
+  in.cost = cur->Cost_path;
+  in.steer = cur->steeringAngle;
+  in.direction = cur->direction;
+  const double g[3] = {goal->Current_state.x, goal->Current_state.y, goal->Current_state.heading};
+  hpp_shot shot;
+  std::vector<double> samples;
+  std::size_t cap = 8192, used = 0;
+  for (;;) {
+    samples.resize(cap * 5);
+    const hpp_status st = (V == HPP_VARIANT_RS)
+                              ? hpp_rs_shot(grid_map_.handle(), &in, 1, g, 0, &shot, samples.data(), cap, &used)
+                              : hpp_dubins_shot(grid_map_.handle(), &in, 1, g, 0, &shot, samples.data(), cap, &used);
+    if (st == HPP_ERR_CAPACITY) {
+      cap = used > cap ? used : cap * 2;
+      continue;
+    }
+    check(grid_map_.ctx(), st, "analytic shot");
+    break;
+  }
+  if (!shot.found) return nullptr;
+  std::vector<State> traj = states_from(samples.data() + 5 * shot.sample_offset, shot.n_samples);
+  // RS/src/HybridAstar.cpp:196-206: the shot node carries direction 1, steering 0
+  return std::make_shared<planner::Node>(traj.back(), traj, shot.cost, 0.0, 1, cur);
+}
+
+template <int V>
+std::vector<double> HybridAstarT<V>::holonomicCostsWithObstacles_planning(const std::shared_ptr<planner::Node> &goal) {
+  const State gs = withCell(goal->Current_state);
+  std::vector<double> cost((std::size_t)grid_map_.getWidth() * grid_map_.getHeight());
+  const hpp_status st =
+      (V == HPP_VARIANT_RS)
+          ? hpp_heuristic_rs(grid_map_.handle(), (int)gs.gridx, (int)gs.gridy, (int)start_state_.gridx,
+                             (int)start_state_.gridy, cost.data(), &report_)
+          : hpp_heuristic_dubins(grid_map_.handle(), (int)gs.gridx, (int)gs.gridy, cost.data(), &report_);
+  check(grid_map_.ctx(), st, "heuristic");
+  return cost;
+}
+
+template <int V>
+std::vector<std::shared_ptr<planner::HolonomicNode>> HybridAstarT<V>::holonomicCostsWithObstacles_nodes(
+    const std::shared_ptr<planner::Node> &goal) {
+  const std::vector<double> cost = holonomicCostsWithObstacles_planning(goal);
+  std::vector<std::shared_ptr<planner::HolonomicNode>> out(cost.size());
+  const int W = (int)grid_map_.getWidth();
+  for (std::size_t i = 0; i < cost.size(); i++) {
+    State s;
+    s.gridx = (double)((int)i % W);
+    s.gridy = (double)((int)i / W);
+    out[i] = std::make_shared<planner::HolonomicNode>(s, cost[i], std::weak_ptr<planner::HolonomicNode>());
+  }
+  return out;
+}
+
+template class HybridAstarT<HPP_VARIANT_RS>;
+template class HybridAstarT<HPP_VARIANT_DUBINS>;
+
+// ---------------------------------------------------------------------------------------------- map_inflate
+std::vector<int8_t> InflateOccupancy(const std::vector<int8_t> &occ, uint32_t width, uint32_t height, double resolution,
+                                     double inflation_radius) {
+  if (occ.size() != (std::size_t)width * height) throw std::runtime_error("InflateOccupancy: size mismatch");
+  std::vector<int8_t> out(occ.size());
+  hpp_ctx *ctx = hpp_host::thread_ctx();
+  check(ctx, hpp_inflate(ctx, occ.data(), width, height, resolution, inflation_radius, out.data()), "hpp_inflate");
+  return out;
+}

@@ -79,6 +79,9 @@ hpp_status hpp_map_create(hpp_ctx *ctx, const int8_t *occ, uint32_t W, uint32_t 
 hpp_status hpp_map_create_dev(hpp_ctx *ctx, const int8_t *occ_dev, uint32_t W, uint32_t H, float resolution,
                               double origin_x, double origin_y, const hpp_params *params, hpp_map **out);
 hpp_status hpp_map_destroy(hpp_map *map);
+/* Grid_map::setcarData (RS/include/Grid_map.h:99, RS/src/Grid_map.cpp:217-220): replace the vehicle / planner
+ * parameters of an existing map (footprint circles, rectangle, motion commands); no device work */
+hpp_status hpp_map_set_params(hpp_map *map, const hpp_params *params);
 /* re-run the layer build on new occupancy of the same geometry (the reference rebuilds its Grid_map on
  * every 1 Hz map message, RS/src/main_path_planning.cpp:63-69) */
 hpp_status hpp_map_update(hpp_map *map, const int8_t *occ);
