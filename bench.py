@@ -3,8 +3,8 @@
 
 Workload at N=1 (config.workload = "cfg3"): BASELINE.json configs[2], the configuration the north_star's target is
 quoted on -- "holonomic heuristic plus distance-layer EDT on a synthetic 4096x4096 random-obstacle grid".
-One step = one pass of the hot path over one map message and a batch of F queries on it (--fields, default 16, the
-same "one field per host core" batch the reference arm runs):  K1 (per-cell tables + obstacle/distance layers of the
+One step = one pass of the hot path over one map message and a batch of F queries on it (--fields, default 64; the
+reference arm runs the same kind of batch, one field per host core):  K1 (per-cell tables + obstacle/distance layers of the
 occupancy, what the reference's Grid_map constructor does per map message) + K3a (the RS holonomic-with-obstacles
 heuristic field of each query's goal, what HybridAstar::run does first).  value = F x 4096^2 cells x steps / device
 time, inputs resident in HBM.  e2e = the same step through the host-buffer C ABI (hpp_map_update +
@@ -51,9 +51,20 @@ def measured_peak():
 
 
 def patch_goals(side, k):
-    """k distinct goal cells inside the cleared 5x5 patch at the map centre (cfg3 recipe)"""
+    """k goal cells: the 25 cells of the cleared 5x5 patch at the map centre (cfg3 recipe) first, then free cells
+    drawn with a fixed seed from the central quarter of the map (seed-1 map; every rank uses the same cell list and
+    clears nothing else, so a drawn cell may be occupied on another rank's map -- the goal expands even then,
+    RS/src/HybridAstar.cpp:378)"""
     c = side // 2
-    return [(c - 2 + (i % 5), c - 2 + ((i // 5) % 5)) for i in range(k)]
+    g = [(c - 2 + (i % 5), c - 2 + ((i // 5) % 5)) for i in range(min(k, 25))]
+    if k > 25:
+        occ, _ = cfg3_map(side, seed=1)
+        rng = np.random.default_rng(12345)
+        while len(g) < k:
+            x, y = (int(v) for v in rng.integers(side // 4, 3 * side // 4, 2))
+            if occ[y, x] == 0 and (x, y) not in g:
+                g.append((x, y))
+    return g
 
 
 # --------------------------------------------------------------------------------------------- reference arm
@@ -84,7 +95,7 @@ def reference_arm(args):
     cores = min(os.cpu_count() or 1, args.ref_cores or 64)
     side = args.side
     c = side // 2
-    goals = [patch_goals(side, 25)[i % 25] for i in range(cores)]   # inside the cleared 5x5 goal patch
+    goals = patch_goals(side, cores)   # same goal list as the device arm
     kind = "reference" if O.ref_available() else "port"
     global _REF_OCC
     _REF_OCC, _ = cfg3_map(side, seed=1)
@@ -236,7 +247,7 @@ def ours_arm(args):
 
     # ---- e2e: the call a user of the reference API makes, host buffers in pinned memory
     occ_pin = torch.from_numpy(occ).pin_memory()
-    cost_pin = torch.empty(F * n, dtype=torch.float64).pin_memory()
+    cost_pin = torch.empty(F * n, dtype=torch.float64, pin_memory=True)
     occ_h, cost_h = occ_pin.numpy(), cost_pin.numpy().reshape(F, side, side)
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
@@ -285,7 +296,7 @@ def ours_arm(args):
         "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg3", "map": f"{side}x{side} 8x8-block Bernoulli(0.30), seed 1+rank", "resolution": RES,
-                   "fields_per_step": F, "goals": "distinct cells of the cleared 5x5 goal patch",
+                   "fields_per_step": F, "goals": "the 25 cells of the cleared 5x5 goal patch, then seeded free cells of the central quarter",
                    "step": f"hpp_map_update_dev (K1) + hpp_heuristic_batch_dev (K3a, {F} fields in one launch)",
                    "per_rank": "own map",
                    "l2": "flushed between steps by a 256 MiB write outside the per-step event pair; one cost field "
@@ -296,7 +307,7 @@ def ours_arm(args):
                 "steps": e2e_steps, "api": "hpp_map_update + hpp_heuristic_batch (host buffers, pinned)",
                 "checksum": checksum},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"heur_persist_kernel (one persistent launch, {F} fields)",
+        "roofline": {"bound": "hbm", "kernel": f"heur_warp_kernel (one persistent cooperative launch, {F} fields, one warp per 32x32 tile)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes": HEUR_BYTES_PER_CELL * n * F,
                      "ms": heur_ms,
@@ -421,7 +432,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=4096)
-    ap.add_argument("--fields", type=int, default=16, help="goal fields (queries) per step, <= 25")
+    ap.add_argument("--fields", type=int, default=64, help="goal fields (queries) per step")
     ap.add_argument("--ref-cores", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

@@ -36,6 +36,10 @@
 
 #include "hpp_internal.cuh"
 
+#ifndef HPP_NB2_CTAS
+#define HPP_NB2_CTAS 4  // resident 64x64-tile CTAs per SM (register cap 65536 / (128 * HPP_NB2_CTAS))
+#endif
+
 namespace {
 
 constexpr int HB = 32;  // block side = one warp, lane = row
@@ -65,6 +69,7 @@ struct heur_args {
   uint32_t *dmask;                 // [n_fields][n_tiles][NB*NB*32]  deferred cells
   uint32_t *bar;                   // [n_groups][32]: count, generation
   uint32_t *stats;                 // [n_fields][4]: rounds, tile visits, windows, sweeps of CTA rank 0
+  uint32_t *lists;                 // warp-tile kernel: [grid][n_tiles] schedule of the round
   unsigned long long *prof;        // optional [grid][8] cycle counters (HPP_HEUR_DEBUG): schedule, stage, solve,
                                    // write-back, barrier wait, tiles, phases, longest single solve
   double delta;                    // width of the global cost window
@@ -231,12 +236,14 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
                                       blk_state &st, int blk, int bx, int by, int lane, double bound,
                                       const eval_w &wt) {
   constexpr int S = tile_cfg<NB>::S;
-  // border changes posted by the neighbouring warps
-  uint32_t inc = ((volatile uint32_t *)s_inc)[blk * 32 + lane];
-  if (__any_sync(FULL, inc != 0)) {
-    if (inc) inc = atomicExch(&s_inc[blk * 32 + lane], 0u);
-    __threadfence_block();
-    st.need |= inc & st.freem;
+  // border changes posted by the neighbouring warps (a one-block tile has no neighbours inside the CTA)
+  if (NB > 1) {
+    uint32_t inc = ((volatile uint32_t *)s_inc)[blk * 32 + lane];
+    if (__any_sync(FULL, inc != 0)) {
+      if (inc) inc = atomicExch(&s_inc[blk * 32 + lane], 0u);
+      __threadfence_block();
+      st.need |= inc & st.freem;
+    }
   }
   if (!__any_sync(FULL, st.need != 0)) return false;
   st.c_sweeps++;
@@ -341,7 +348,7 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
 
 // ---------------------------------------------------------------- the persistent kernel
 template <int NB, int VARIANT>
-__global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : 4) heur_persist_kernel(const __grid_constant__ heur_args a) {
+__global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : HPP_NB2_CTAS) heur_persist_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<NB>;
   constexpr int T = C::T, S = C::S, ROWS = C::ROWS, NBLK = C::NBLK, THREADS = C::THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -644,6 +651,286 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : 4) heur_p
   }
 }
 
+// ---------------------------------------------------------------- the warp-tile kernel (T = 32: one warp per tile)
+// Same scheduling protocol as heur_persist_kernel (cost windows, activity flags, deferred minima, one group barrier
+// per round), but a tile is a single 32x32 block solved by ONE warp with no block-level barrier at all: the 16 warps
+// of a CTA pull tiles of the round's schedule from a shared counter and never wait for each other inside a round.
+// This is the throughput configuration: with several fields in flight every warp of the GPU stays busy.
+constexpr int WT_WARPS = 16;
+
+template <int VARIANT>
+__global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __grid_constant__ heur_args a) {
+  using C = tile_cfg<1>;
+  constexpr int T = C::T, S = C::S, ROWS = C::ROWS, THREADS = WT_WARPS * 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *cs_all = (double *)smem_raw;                                  // WT_WARPS x ROWS*S
+  uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);          // WT_WARPS x ROWS*S (Dubins only)
+  __shared__ unsigned long long s_gmin;
+  __shared__ uint32_t s_count, s_mine, s_next, s_warp_cnt[32], s_outw[WT_WARPS];
+  __shared__ double s_db[20];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int group = blockIdx.x / a.group_size, grank = blockIdx.x % a.group_size;
+  if (group >= a.n_groups) return;
+  uint32_t *bar = a.bar + group * 32;
+  uint32_t *my_list = a.lists + (size_t)blockIdx.x * a.n_tiles;
+  const int W = a.W, H = a.H, n_tiles = a.n_tiles;
+  const size_t n = (size_t)W * H;
+  if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
+  eval_w wt;
+  wt.c0 = a.wt.rs[0][0];
+  wt.d0 = a.wt.rs[0][1];
+  wt.c1 = a.wt.rs[1][0];
+  wt.d1 = a.wt.rs[1][1];
+  wt.init = a.wt.init;
+  wt.db = s_db;
+  double *cs_nv = cs_all + wid * ROWS * S;
+  uint8_t *cl_nv = cl_all + wid * ROWS * S;
+  volatile double *cs = cs_nv;
+  const volatile uint8_t *cl = cl_nv;
+  __syncthreads();
+
+  for (int field = group; field < a.n_fields; field += a.n_groups) {
+    double *cost = a.cost_all + (size_t)field * n;
+    uint32_t *act = a.act + (size_t)field * 3 * n_tiles;
+    unsigned long long *pmin = a.pmin + (size_t)field * 2 * n_tiles;
+    uint32_t *dmask = a.dmask + (size_t)field * n_tiles * 32;
+    double bound = 0.0;
+    uint32_t rounds = 0, visits = 0, windows = 0;
+    unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tk = clock64();
+#define PF_MARK(i)                            \
+  if (a.prof) {                               \
+    const long long now_ = clock64();         \
+    pf[i] += (unsigned long long)(now_ - tk); \
+    tk = now_;                                \
+  }
+
+    for (uint32_t round = 0;; round++) {
+      uint32_t *act_cur = act + (round % 3) * n_tiles, *act_next = act + ((round + 1) % 3) * n_tiles,
+               *act_clr = act + ((round + 2) % 3) * n_tiles;
+      unsigned long long *pm_cur = pmin + (round & 1) * n_tiles, *pm_next = pmin + ((round + 1) & 1) * n_tiles;
+      // ---- pass 1: schedulable tiles under the current bound, global minimum of the deferred costs
+      uint32_t total;
+      for (;;) {
+        if (tid == 0) {
+          s_count = 0;
+          s_gmin = INF_BITS;
+        }
+        __syncthreads();
+        uint32_t cnt = 0;
+        unsigned long long mn = INF_BITS;
+        for (int t = tid; t < n_tiles; t += THREADS) {
+          const uint32_t af = __ldcg(act_cur + t);
+          const unsigned long long pm = __ldcg(pm_cur + t);
+          if (af != 0 || __longlong_as_double((long long)pm) < bound) cnt++;
+          mn = pm < mn ? pm : mn;
+        }
+        for (int d = 16; d; d >>= 1) {
+          cnt += __shfl_down_sync(FULL, cnt, d);
+          const unsigned long long o = __shfl_down_sync(FULL, mn, d);
+          mn = o < mn ? o : mn;
+        }
+        if (lane == 0) {
+          if (cnt) atomicAdd(&s_count, cnt);
+          if (mn != INF_BITS) atomicMin(&s_gmin, mn);
+        }
+        __syncthreads();
+        total = s_count;
+        const unsigned long long g = s_gmin;
+        __syncthreads();
+        if (total != 0 || g == INF_BITS) break;
+        bound = __longlong_as_double((long long)g) + a.delta;
+        windows++;
+      }
+      if (total == 0) break;
+      rounds++;
+      // ---- pass 2: my share of the schedule (ranks == grank mod group size, rotated per round) into my list;
+      // housekeeping for the tiles t == grank (mod group size) as in heur_persist_kernel
+      if (tid == 0) s_mine = 0;
+      uint32_t base_rank = 0;
+      for (int t0 = 0; t0 < n_tiles; t0 += THREADS) {
+        const int t = t0 + tid;
+        bool on = false;
+        if (t < n_tiles) {
+          const uint32_t af = __ldcg(act_cur + t);
+          const unsigned long long pm = __ldcg(pm_cur + t);
+          on = af != 0 || __longlong_as_double((long long)pm) < bound;
+          if (t % a.group_size == grank) {
+            if (!on) __stcg(pm_next + t, pm);
+            __stcg(act_clr + t, 0u);
+          }
+        }
+        const uint32_t b = __ballot_sync(FULL, on);
+        if (lane == 0) s_warp_cnt[wid] = __popc(b);
+        __syncthreads();
+        uint32_t pre = base_rank, chunk = 0;
+        for (int w = 0; w < WT_WARPS; w++) {
+          const uint32_t cw = s_warp_cnt[w];
+          if (w < wid) pre += cw;
+          chunk += cw;
+        }
+        if (on) {
+          const uint32_t rank = pre + __popc(b & ((1u << lane) - 1u));
+          if ((int)((rank + round) % (uint32_t)a.group_size) == grank) my_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
+        }
+        base_rank += chunk;
+        __syncthreads();
+      }
+      if (tid == 0) s_next = 0;
+      __syncthreads();
+      const uint32_t mine = s_mine;
+
+      // ---- drain: every warp pulls tiles until the list is empty
+      for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&s_next, 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= mine) break;
+        const int tile = (int)my_list[i];
+        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+        const int x0 = tx * T, y0 = ty * T;
+        visits++;
+        PF_MARK(0);
+        // stage the tile + one-cell halo: two coalesced loads per row
+        for (int r = 0; r < ROWS; r++) {
+          const int gy = y0 - 1 + r;
+          const bool rin = gy >= 0 && gy < H;
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const int c = lane + 32 * k;
+            if (c < T + 2) {
+              const int gx = x0 - 1 + c;
+              double v = wt.init;
+              uint8_t k8 = CLS_BLOCKED | 9;
+              if (rin && gx >= 0 && gx < W) {
+                v = __ldcg(cost + (size_t)gy * W + gx);
+                if (VARIANT == HPP_VARIANT_DUBINS) k8 = a.cls[(size_t)gy * W + gx];
+              }
+              cs_nv[r * S + c + 1] = v;
+              if (VARIANT == HPP_VARIANT_DUBINS) cl_nv[r * S + c + 1] = k8;
+            }
+          }
+        }
+        if (lane == 0) s_outw[wid] = 0;
+        blk_state st;
+        {
+          const int gy = y0 + lane, wx = x0 >> 5;
+          uint32_t ob = 0xffffffffu, nb = 0;
+          if (gy < H && wx < a.pitch) {
+            ob = a.occ_bits[(size_t)gy * a.pitch + wx];
+            nb = a.near_bits[(size_t)gy * a.pitch + wx];
+            const int rem = W - (wx << 5);
+            if (rem < 32) ob |= ~((1u << rem) - 1u);
+          }
+          st.freem = ~ob;
+          st.nearm = nb;
+          st.need = 0;
+          st.dirty = 0;
+          st.posted = 0;
+          st.c_heavy = st.c_sparse = st.c_on = st.c_imp = st.c_sweeps = 0;
+          st.defer = __ldcg(dmask + (size_t)tile * 32 + lane);
+        }
+        const uint32_t af = __ldcg(act_cur + tile);
+        __syncwarp();
+        PF_MARK(1);
+        if (af) {
+          if ((af & DIR_N) && lane == 0) st.need |= st.freem;
+          if ((af & DIR_S) && lane == 31) st.need |= st.freem;
+          if (af & DIR_W) st.need |= st.freem & 1u;
+          if (af & DIR_E) st.need |= st.freem & 0x80000000u;
+          if ((af & DIR_NW) && lane == 0) st.need |= st.freem & 1u;
+          if ((af & DIR_NE) && lane == 0) st.need |= st.freem & 0x80000000u;
+          if ((af & DIR_SW) && lane == 31) st.need |= st.freem & 1u;
+          if ((af & DIR_SE) && lane == 31) st.need |= st.freem & 0x80000000u;
+        }
+        // relax under the bound in sub-windows (see heur_persist_kernel); everything is warp-local
+        const int ebase = S + 2;
+        double lb = 0.0;
+        unsigned long long left = INF_BITS;
+        for (;;) {
+          while (sweep<1, VARIANT>(cs, cl, nullptr, &s_outw[wid], st, 0, 0, 0, lane, lb, wt)) {
+          }
+          unsigned long long mn = INF_BITS;
+          for (uint32_t m = st.defer; m; m &= m - 1) {
+            const int x = __ffs(m) - 1;
+            const unsigned long long v = (unsigned long long)__double_as_longlong(cs[ebase + lane * S + x]);
+            mn = v < mn ? v : mn;
+          }
+          for (int d = 16; d; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(FULL, mn, d);
+            mn = o < mn ? o : mn;
+          }
+          left = mn;
+          const double gm = __longlong_as_double((long long)mn);
+          if (mn == INF_BITS || !(gm < bound)) break;
+          lb = gm + a.delta_in;
+          if (lb > bound) lb = bound;
+          uint32_t rel = 0;
+          push3 ps = {0ull, 0ull, 0ull};
+          for (uint32_t m = st.defer; m; m &= m - 1) {
+            const int x = __ffs(m) - 1;
+            if (cs[ebase + lane * S + x] < lb) {
+              rel |= 1u << x;
+              add_push(ps, x, 0xffu);
+            }
+          }
+          st.defer &= ~rel;
+          __syncwarp();
+          if (__any_sync(FULL, rel != 0)) propagate<1>(ps, st, nullptr, &s_outw[wid], 0, 0, lane);
+        }
+        pf[5]++;
+        pf[6] += st.c_sweeps;
+        pf[7] += st.c_heavy + st.c_sparse;
+        PF_MARK(2);
+        // write back
+        __stcg(dmask + (size_t)tile * 32 + lane, st.defer);
+        uint32_t dr = __ballot_sync(FULL, st.dirty != 0);
+        const int gx = x0 + lane;
+        while (dr) {
+          const int r = __ffs(dr) - 1;
+          dr &= dr - 1;
+          const int gy = y0 + r;
+          if (gx < W && gy < H) __stcg(cost + (size_t)gy * W + gx, cs[ebase + r * S + lane]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __stcg(pm_next + tile, left);
+          const uint32_t o = ((volatile uint32_t *)s_outw)[wid];
+          if (o) {
+            __threadfence();
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+              constexpr int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+              constexpr int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+              constexpr uint32_t facing[8] = {DIR_S, DIR_N, DIR_E, DIR_W, DIR_SE, DIR_SW, DIR_NE, DIR_NW};
+              if (o & (1u << d)) {
+                const int nx = tx + ddx[d], ny = ty + ddy[d];
+                if (nx >= 0 && nx < a.tiles_x && ny >= 0 && ny < a.tiles_y)
+                  atomicOr(act_next + ny * a.tiles_x + nx, facing[d]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        PF_MARK(3);
+      }
+      PF_MARK(0);
+      group_barrier(bar, a.group_size);
+      PF_MARK(4);
+    }
+#undef PF_MARK
+    if (a.prof && tid == 0)
+      for (int i = 0; i < 8; i++) a.prof[blockIdx.x * 8 + i] = pf[i];
+    if (grank == 0 && tid == 0) {
+      uint32_t *sp = a.stats + field * 4;
+      sp[0] = rounds;
+      sp[2] = windows;
+    }
+    if (lane == 0 && visits) atomicAdd(a.stats + field * 4 + 1, visits);
+  }
+}
+
 // ---------------------------------------------------------------- init / seed / stats
 __global__ void __launch_bounds__(256) heur_init_kernel(double *__restrict__ cost, size_t total, double init,
                                                         unsigned long long *__restrict__ pmin, size_t n_pmin) {
@@ -732,20 +1019,29 @@ double env_double(const char *name, double dflt) {
 template <int NB, int VARIANT>
 hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   using C = tile_cfg<NB>;
-  const size_t smem = heur_smem_bytes<NB>(VARIANT);
-  auto kern = heur_persist_kernel<NB, VARIANT>;
+  constexpr int threads = NB == 1 ? WT_WARPS * 32 : C::THREADS;
+  size_t smem;
+  const void *kern;
+  if constexpr (NB == 1) {
+    smem = (size_t)WT_WARPS * C::ROWS * C::S * (sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? 1 : 0)) + 16;
+    kern = (const void *)heur_warp_kernel<VARIANT>;
+  } else {
+    smem = heur_smem_bytes<NB>(VARIANT);
+    kern = (const void *)heur_persist_kernel<NB, VARIANT>;
+  }
   HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem));
+  HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic kernel does not fit on an SM (%zu B shared)", smem);
-  const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", NB >= 4 ? 1 : 4);
+  const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", NB == 2 ? HPP_NB2_CTAS : 1);
   if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   const int G = per_sm * c->sm_count;  // co-resident CTAs
   // CTA groups: one field at a time per group, the groups never synchronise with each other.  A tile solve is a
   // latency chain on a few warps, so a single field cannot fill the GPU (its CTAs mostly wait for the slowest tile
   // of the round); with several fields the GPU is shared evenly, down to one CTA per field (no barrier at all).
   int gs = ctas_per_field_hint > 0 ? ctas_per_field_hint : G / a.n_fields;
-  if (gs > a.n_tiles) gs = a.n_tiles;  // never more CTAs than tiles
+  const int useful = NB == 1 ? (a.n_tiles + WT_WARPS - 1) / WT_WARPS : a.n_tiles;
+  if (gs > useful) gs = useful;  // never more CTAs than tiles (warp-tile kernel: than tiles / warps per CTA)
   if (gs > G) gs = G;
   if (gs < 1) gs = 1;
   int n_groups = G / gs;
@@ -753,8 +1049,14 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   a.group_size = gs;
   a.n_groups = n_groups;
   const int grid = gs * n_groups;
+  if constexpr (NB == 1) {
+    void *lp;
+    hpp_status s = hpp_scratch(c, 4, sizeof(uint32_t) * (size_t)grid * a.n_tiles, &lp);
+    if (s != HPP_OK) return s;
+    a.lists = (uint32_t *)lp;
+  }
   void *params[] = {&a};
-  HPP_CUDA(c, cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(C::THREADS), params, smem, c->stream));
+  HPP_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), params, smem, c->stream));
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
@@ -815,7 +1117,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   const size_t prof_n = (size_t)c->sm_count * 8 * 8 + 8;
   if (debug) {
     void *pp;
-    s = hpp_scratch(c, 1, prof_n * 8, &pp);
+    s = hpp_scratch(c, 5, prof_n * 8, &pp);
     if (s != HPP_OK) return s;
     a.prof = (unsigned long long *)pp;
     HPP_CUDA(c, cudaMemsetAsync(a.prof, 0, prof_n * 8, c->stream));
@@ -839,7 +1141,8 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
     std::vector<unsigned long long> hp((size_t)grid * 8 + 8);
     HPP_CUDA(c, cudaMemcpyAsync(hp.data(), a.prof, hp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     HPP_CUDA(c, cudaStreamSynchronize(c->stream));
-    const char *nm[8] = {"schedule", "stage", "solve", "writeback", "barrier", "tiles", "phases", "max_solve"};
+    const char *nm[8] = {"schedule", "stage", "solve", "writeback", "barrier", "tiles", NB == 1 ? "sweeps" : "phases",
+                         NB == 1 ? "iters" : "max_solve"};
     for (int i = 0; i < 8; i++) {
       unsigned long long sum = 0, mx = 0;
       for (int b = 0; b < grid; b++) {
@@ -902,10 +1205,14 @@ extern "C" hpp_status hpp_heuristic_batch_dev(hpp_map *m, int variant, const int
                f, W, H);
   if (n_fields > 65535) HPP_FAIL(c, HPP_ERR_ARG, "at most 65535 fields per call");
   HPP_CUDA(c, cudaSetDevice(c->device));
-  // tile side: 128 (16 warps, one CTA per SM) for big maps, 64 (4 warps, several CTAs per SM) for small ones
+  // Tile side.  Few fields on a big map: 128 (16 warps per tile, one CTA per SM) -- the fewest rounds, best latency.
+  // Small maps: 64.  Many fields in flight: 32, one warp per tile (heur_warp_kernel) -- no barrier inside a tile,
+  // every warp of the GPU busy: the throughput configuration.
   int nb = (W >= 1024 || H >= 1024) ? 4 : 2;
+  if (n_fields >= 8) nb = 1;
   const int env_nb = (int)env_double("HPP_HEUR_NB", 0);
-  if (env_nb == 2 || env_nb == 4) nb = env_nb;
+  if (env_nb == 1 || env_nb == 2 || env_nb == 4) nb = env_nb;
+  if (nb == 1) return run_batch<1>(m, variant, goal_xy, n_fields, cost_dev, reports);
   return nb == 4 ? run_batch<4>(m, variant, goal_xy, n_fields, cost_dev, reports)
                  : run_batch<2>(m, variant, goal_xy, n_fields, cost_dev, reports);
 }
