@@ -651,6 +651,33 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : HPP_NB2_C
   }
 }
 
+// ---------------------------------------------------------------- TMA (bulk async copy) + mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy (TMA engine; bytes and both addresses multiples of 16), completion on the mbarrier
+__device__ __forceinline__ void tma_load_row(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// orders this thread's generic-proxy accesses (shared and global) with async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---------------------------------------------------------------- the warp-tile kernel (T = 32: one warp per tile)
 // Same scheduling protocol as heur_persist_kernel (cost windows, activity flags, deferred minima, one group barrier
 // per round), but a tile is a single 32x32 block solved by ONE warp with no block-level barrier at all: the 16 warps
@@ -668,6 +695,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   __shared__ unsigned long long s_gmin;
   __shared__ uint32_t s_count, s_mine, s_next, s_warp_cnt[32], s_outw[WT_WARPS];
   __shared__ double s_db[20];
+  __shared__ __align__(8) unsigned long long s_mbar[WT_WARPS];  // one TMA completion barrier per warp
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int group = blockIdx.x / a.group_size, grank = blockIdx.x % a.group_size;
@@ -688,7 +716,13 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   uint8_t *cl_nv = cl_all + wid * ROWS * S;
   volatile double *cs = cs_nv;
   const volatile uint8_t *cl = cl_nv;
+  const uint32_t mbar = smem_u32(&s_mbar[wid]);
+  uint32_t mbar_parity = 0;
+  if (lane == 0) mbar_init(mbar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
+  // rows can be bulk-copied when every row start (x0 - 2 doubles) is 16-byte aligned: W even and an aligned base
+  const bool tma_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.cost_all) & 15) == 0);
 
   for (int field = group; field < a.n_fields; field += a.n_groups) {
     double *cost = a.cost_all + (size_t)field * n;
@@ -792,23 +826,59 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
         const int x0 = tx * T, y0 = ty * T;
         visits++;
         PF_MARK(0);
-        // stage the tile + one-cell halo: two coalesced loads per row
-        for (int r = 0; r < ROWS; r++) {
-          const int gy = y0 - 1 + r;
-          const bool rin = gy >= 0 && gy < H;
+        // ---- stage the tile + halo.  TMA path: one bulk copy per row (columns x0-2 .. x0+33, 16-byte aligned),
+        // all rows in flight at once, completion counted on the warp's mbarrier.  Cells outside the map keep the
+        // initial value: edge tiles are pre-filled before the copies land.
+        if (tma_ok) {
+          const int cx0 = x0 - 2 < 0 ? 0 : x0 - 2, cx1 = x0 + T + 2 > W ? W : x0 + T + 2;
+          const int ry0 = y0 - 1 < 0 ? 0 : y0 - 1, ry1 = y0 + T + 1 > H ? H : y0 + T + 1;  // valid global rows
+          const bool edge = x0 == 0 || x0 + T + 2 > W || y0 == 0 || y0 + T + 1 > H;
+          if (edge) {
+            for (int i = lane; i < ROWS * S; i += 32) cs_nv[i] = wt.init;
+            __syncwarp();
+          }
+          fence_proxy_async();  // my generic-proxy accesses to this buffer before the async-proxy writes
+          const uint32_t row_bytes = (uint32_t)(cx1 - cx0) * 8u;
+          if (lane == 0) mbar_expect_tx(mbar, row_bytes * (uint32_t)(ry1 - ry0));
+          __syncwarp();
+          for (int gy = ry0 + lane; gy < ry1; gy += 32) {
+            const int r = gy - (y0 - 1);
+            tma_load_row(smem_u32(cs_nv + r * S + (cx0 - (x0 - 2))), cost + (size_t)gy * W + cx0, row_bytes, mbar);
+          }
+          if (VARIANT == HPP_VARIANT_DUBINS) {
+            for (int r = 0; r < ROWS; r++) {
+              const int gy = y0 - 1 + r;
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const int c = lane + 32 * k;
-            if (c < T + 2) {
-              const int gx = x0 - 1 + c;
-              double v = wt.init;
-              uint8_t k8 = CLS_BLOCKED | 9;
-              if (rin && gx >= 0 && gx < W) {
-                v = __ldcg(cost + (size_t)gy * W + gx);
-                if (VARIANT == HPP_VARIANT_DUBINS) k8 = a.cls[(size_t)gy * W + gx];
+              for (int k = 0; k < 2; k++) {
+                const int c = lane + 32 * k, gx = x0 - 1 + c;
+                if (c < T + 2) {
+                  uint8_t k8 = CLS_BLOCKED | 9;
+                  if (gy >= 0 && gy < H && gx >= 0 && gx < W) k8 = a.cls[(size_t)gy * W + gx];
+                  cl_nv[r * S + c + 1] = k8;
+                }
               }
-              cs_nv[r * S + c + 1] = v;
-              if (VARIANT == HPP_VARIANT_DUBINS) cl_nv[r * S + c + 1] = k8;
+            }
+          }
+          mbar_wait(mbar, mbar_parity);
+          mbar_parity ^= 1u;
+        } else {
+          for (int r = 0; r < ROWS; r++) {
+            const int gy = y0 - 1 + r;
+            const bool rin = gy >= 0 && gy < H;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+              const int c = lane + 32 * k;
+              if (c < T + 2) {
+                const int gx = x0 - 1 + c;
+                double v = wt.init;
+                uint8_t k8 = CLS_BLOCKED | 9;
+                if (rin && gx >= 0 && gx < W) {
+                  v = __ldcg(cost + (size_t)gy * W + gx);
+                  if (VARIANT == HPP_VARIANT_DUBINS) k8 = a.cls[(size_t)gy * W + gx];
+                }
+                cs_nv[r * S + c + 1] = v;
+                if (VARIANT == HPP_VARIANT_DUBINS) cl_nv[r * S + c + 1] = k8;
+              }
             }
           }
         }
@@ -893,6 +963,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
           const int gy = y0 + r;
           if (gx < W && gy < H) __stcg(cost + (size_t)gy * W + gx, cs[ebase + r * S + lane]);
         }
+        fence_proxy_async();  // the rows just stored are read by other warps' bulk copies (async proxy) later
         __syncwarp();
         if (lane == 0) {
           __stcg(pm_next + tile, left);
