@@ -36,6 +36,13 @@
 
 #include "hpp_internal.cuh"
 
+// per-warp iteration / evaluation counters for the HPP_HEUR_DEBUG report (cost ~3 % of the instructions)
+#ifdef HPP_HEUR_COUNTERS
+#define HPP_COUNT(x) x
+#else
+#define HPP_COUNT(x)
+#endif
+
 #ifndef HPP_NB2_CTAS
 #define HPP_NB2_CTAS 4  // resident 64x64-tile CTAs per SM (register cap 65536 / (128 * HPP_NB2_CTAS))
 #endif
@@ -189,8 +196,9 @@ __device__ __forceinline__ void propagate(const push3 &ps, blk_state &st, uint32
 
 // weights held in registers (RS) / shared memory (Dubins table)
 struct eval_w {
-  double c0, d0, c1, d1;  // RS: cardinal / diagonal, plain and near-obstacle
+  double c0, d0;          // RS: cheapest cardinal / diagonal edge (the push filter's lower bound)
   double init;
+  const double2 *rs;      // RS: [near] -> (cardinal, diagonal) weights, in shared memory (one LDS.128)
   const double *db;       // Dubins: [2][10] in shared memory
 };
 
@@ -206,8 +214,8 @@ __device__ __forceinline__ double eval_cell(const volatile double *cs, const vol
   if (VARIANT == HPP_VARIANT_RS) {
     const double mc = dmin(dmin(n, s), dmin(w, ea));
     const double md = dmin(dmin(nw, ne), dmin(sw, se));
-    const double wc = near ? wt.c1 : wt.c0, wd = near ? wt.d1 : wt.d0;
-    best = dmin(mc + wc, md + wd);
+    const double2 wcd = wt.rs[near ? 1 : 0];
+    best = dmin(mc + wcd.x, md + wcd.y);
     t1 = best + wt.c0;
     t2 = best + wt.d0;
   } else {
@@ -246,25 +254,27 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     }
   }
   if (!__any_sync(FULL, st.need != 0)) return false;
-  st.c_sweeps++;
+  HPP_COUNT(st.c_sweeps++;)
   const int ebase = (by * HB + 1) * S + bx * HB + 2;  // shared index of cell (row 0, col 0) of my block
   push3 ps = {0ull, 0ull, 0ull};
   // Split the rows into "heavy" ones (evaluated one lane per column, one iteration per row) and "sparse" ones (one
   // cell per lane and iteration, as many iterations as the fullest sparse row): pick the threshold that minimises
   // the iteration count of this sweep.
   const int cnt = __popc(st.need);
-  int thr = 33, best_cost = __reduce_max_sync(FULL, cnt);  // everything sparse
+  int thr = 33, best_cost = (__reduce_max_sync(FULL, cnt) + 1) >> 1;  // everything sparse: two cells per iteration
+  if (best_cost > 1) {
 #pragma unroll
-  for (int k = 0; k < 7; k++) {
-    constexpr int cand[7] = {2, 3, 4, 6, 8, 12, 20};
-    const int t = cand[k];
-    const int c = __popc(__ballot_sync(FULL, cnt >= t)) + (t - 1);
-    if (t - 1 < best_cost && c < best_cost) {
-      best_cost = c;
-      thr = t;
+    for (int k = 0; k < 6; k++) {
+      constexpr int cand[6] = {3, 5, 7, 9, 13, 21};
+      const int t = cand[k];
+      const int c = __popc(__ballot_sync(FULL, cnt >= t)) + (t >> 1);  // heavy rows + ceil((t-1)/2) sparse iterations
+      if ((t >> 1) < best_cost && c < best_cost) {
+        best_cost = c;
+        thr = t;
+      }
     }
   }
-  uint32_t heavy = __ballot_sync(FULL, cnt >= thr);
+  uint32_t heavy = thr < 33 ? __ballot_sync(FULL, cnt >= thr) : 0u;
   while (heavy) {
     const int r = __ffs(heavy) - 1;
     heavy &= heavy - 1;
@@ -272,15 +282,14 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     const uint32_t nm = __shfl_sync(FULL, st.nearm, r);
     const int e = ebase + r * S + lane;
     const bool on = (m >> lane) & 1u;
-    st.c_heavy++;
-    st.c_on += on;
+    HPP_COUNT(st.c_heavy++; st.c_on += on;)
     const double c0 = cs[e];
     uint32_t nmask;
     const double best = eval_cell<VARIANT, S>(cs, cl, e, (nm >> lane) & 1u, wt, nmask);
     const bool imp = on && best < c0;
     if (imp) cs[e] = best;
     const bool low = imp && best < bound;
-    st.c_imp += imp;
+    HPP_COUNT(st.c_imp += imp;)
     if (!low) nmask = 0;
     const uint32_t bimp = __ballot_sync(FULL, imp);
     const uint32_t blow = __ballot_sync(FULL, low);
@@ -304,14 +313,14 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
   }
   // sparse rows: two cells per lane and iteration (independent evaluations overlap their latencies)
   while (__any_sync(FULL, st.need != 0)) {
-    st.c_sparse++;
+    HPP_COUNT(st.c_sparse++;)
     const bool on0 = st.need != 0;
     const int x0 = on0 ? __ffs(st.need) - 1 : 0;
     st.need &= st.need - 1;
     const bool on1 = st.need != 0;
     const int x1 = on1 ? __ffs(st.need) - 1 : 0;
     st.need &= st.need - 1;
-    st.c_on += (on0 ? 1 : 0) + (on1 ? 1 : 0);
+    HPP_COUNT(st.c_on += (on0 ? 1 : 0) + (on1 ? 1 : 0);)
     const int e0 = ebase + lane * S + x0, e1 = ebase + lane * S + x1;
     const double c0 = cs[e0], c1 = cs[e1];
     uint32_t nm0, nm1;
@@ -319,7 +328,7 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     const double b1 = eval_cell<VARIANT, S>(cs, cl, e1, (st.nearm >> x1) & 1u, wt, nm1);
     const bool imp0 = on0 && b0 < c0, imp1 = on1 && b1 < c1;
     if (imp0) {
-      st.c_imp++;
+      HPP_COUNT(st.c_imp++;)
       cs[e0] = b0;
       st.dirty = 1;
       if (b0 < bound) {
@@ -330,7 +339,7 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
       }
     }
     if (imp1) {
-      st.c_imp++;
+      HPP_COUNT(st.c_imp++;)
       cs[e1] = b1;
       st.dirty = 1;
       if (b1 < bound) {
@@ -370,12 +379,13 @@ __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : HPP_NB2_C
   const size_t n = (size_t)W * H;
   __shared__ double s_db[20];
   if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
+  __shared__ __align__(16) double2 s_rs[2];
+  if (tid < 2) s_rs[tid] = make_double2(a.wt.rs[tid][0], a.wt.rs[tid][1]);
   eval_w wt;
   wt.c0 = a.wt.rs[0][0];
   wt.d0 = a.wt.rs[0][1];
-  wt.c1 = a.wt.rs[1][0];
-  wt.d1 = a.wt.rs[1][1];
   wt.init = a.wt.init;
+  wt.rs = s_rs;
   wt.db = s_db;
   __syncthreads();
 
@@ -693,7 +703,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   double *cs_all = (double *)smem_raw;                                  // WT_WARPS x ROWS*S
   uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);          // WT_WARPS x ROWS*S (Dubins only)
   __shared__ unsigned long long s_gmin;
-  __shared__ uint32_t s_count, s_mine, s_next, s_warp_cnt[32], s_outw[WT_WARPS];
+  __shared__ uint32_t s_mine, s_next, s_warp_cnt[32], s_outw[WT_WARPS];
   __shared__ double s_db[20];
   __shared__ __align__(8) unsigned long long s_mbar[WT_WARPS];  // one TMA completion barrier per warp
 
@@ -705,12 +715,13 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   const int W = a.W, H = a.H, n_tiles = a.n_tiles;
   const size_t n = (size_t)W * H;
   if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
+  __shared__ __align__(16) double2 s_rs[2];
+  if (tid < 2) s_rs[tid] = make_double2(a.wt.rs[tid][0], a.wt.rs[tid][1]);
   eval_w wt;
   wt.c0 = a.wt.rs[0][0];
   wt.d0 = a.wt.rs[0][1];
-  wt.c1 = a.wt.rs[1][0];
-  wt.d1 = a.wt.rs[1][1];
   wt.init = a.wt.init;
+  wt.rs = s_rs;
   wt.db = s_db;
   double *cs_nv = cs_all + wid * ROWS * S;
   uint8_t *cl_nv = cl_all + wid * ROWS * S;
@@ -744,73 +755,70 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
       uint32_t *act_cur = act + (round % 3) * n_tiles, *act_next = act + ((round + 1) % 3) * n_tiles,
                *act_clr = act + ((round + 2) % 3) * n_tiles;
       unsigned long long *pm_cur = pmin + (round & 1) * n_tiles, *pm_next = pmin + ((round + 1) & 1) * n_tiles;
-      // ---- pass 1: schedulable tiles under the current bound, global minimum of the deferred costs
+      // ---- schedule: one scan of the tile table builds my list of the round (ranks == grank mod group size,
+      // rotated per round), counts the schedulable tiles and finds the global minimum of the deferred costs; when
+      // nothing is schedulable the bound moves to that minimum + delta and the scan is repeated.  Housekeeping for
+      // the tiles t == grank (mod group size), as in heur_persist_kernel: carry an unscheduled tile's minimum over
+      // to the next round's table, zero the activity buffer of the round after (both idempotent under a re-scan:
+      // a tile that becomes schedulable overwrites its minimum when it is processed).
+      const bool solo = a.group_size == 1;
       uint32_t total;
       for (;;) {
         if (tid == 0) {
-          s_count = 0;
           s_gmin = INF_BITS;
+          s_mine = 0;
         }
         __syncthreads();
-        uint32_t cnt = 0;
         unsigned long long mn = INF_BITS;
-        for (int t = tid; t < n_tiles; t += THREADS) {
-          const uint32_t af = __ldcg(act_cur + t);
-          const unsigned long long pm = __ldcg(pm_cur + t);
-          if (af != 0 || __longlong_as_double((long long)pm) < bound) cnt++;
-          mn = pm < mn ? pm : mn;
+        uint32_t base_rank = 0;
+        for (int t0 = 0; t0 < n_tiles; t0 += THREADS) {
+          const int t = t0 + tid;
+          bool on = false;
+          if (t < n_tiles) {
+            const uint32_t af = __ldcg(act_cur + t);
+            const unsigned long long pm = __ldcg(pm_cur + t);
+            on = af != 0 || __longlong_as_double((long long)pm) < bound;
+            mn = pm < mn ? pm : mn;
+            if (solo || t % a.group_size == grank) {
+              if (!on) __stcg(pm_next + t, pm);
+              __stcg(act_clr + t, 0u);
+            }
+          }
+          const uint32_t b = __ballot_sync(FULL, on);
+          if (lane == 0) s_warp_cnt[wid] = __popc(b);
+          __syncthreads();
+          // exclusive prefix of the 16 warp counts by shuffles (every warp computes the same scan)
+          uint32_t v = lane < WT_WARPS ? s_warp_cnt[lane] : 0u, inc = v;
+#pragma unroll
+          for (int d = 1; d < WT_WARPS; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
+          }
+          const uint32_t pre = base_rank + __shfl_sync(FULL, inc - v, wid);
+          const uint32_t chunk = __shfl_sync(FULL, inc, WT_WARPS - 1);
+          if (on) {
+            const uint32_t rank = pre + __popc(b & ((1u << lane) - 1u));
+            if (solo || (int)((rank + round) % (uint32_t)a.group_size) == grank)
+              my_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
+          }
+          base_rank += chunk;
+          __syncthreads();
         }
         for (int d = 16; d; d >>= 1) {
-          cnt += __shfl_down_sync(FULL, cnt, d);
           const unsigned long long o = __shfl_down_sync(FULL, mn, d);
           mn = o < mn ? o : mn;
         }
-        if (lane == 0) {
-          if (cnt) atomicAdd(&s_count, cnt);
-          if (mn != INF_BITS) atomicMin(&s_gmin, mn);
-        }
+        if (lane == 0 && mn != INF_BITS) atomicMin(&s_gmin, mn);
         __syncthreads();
-        total = s_count;
+        total = base_rank;
         const unsigned long long g = s_gmin;
         __syncthreads();
         if (total != 0 || g == INF_BITS) break;
-        bound = __longlong_as_double((long long)g) + a.delta;
+        bound = __longlong_as_double((long long)g) + a.delta;  // open the next cost window
         windows++;
       }
-      if (total == 0) break;
+      if (total == 0) break;  // nothing active, nothing deferred: fixed point reached
       rounds++;
-      // ---- pass 2: my share of the schedule (ranks == grank mod group size, rotated per round) into my list;
-      // housekeeping for the tiles t == grank (mod group size) as in heur_persist_kernel
-      if (tid == 0) s_mine = 0;
-      uint32_t base_rank = 0;
-      for (int t0 = 0; t0 < n_tiles; t0 += THREADS) {
-        const int t = t0 + tid;
-        bool on = false;
-        if (t < n_tiles) {
-          const uint32_t af = __ldcg(act_cur + t);
-          const unsigned long long pm = __ldcg(pm_cur + t);
-          on = af != 0 || __longlong_as_double((long long)pm) < bound;
-          if (t % a.group_size == grank) {
-            if (!on) __stcg(pm_next + t, pm);
-            __stcg(act_clr + t, 0u);
-          }
-        }
-        const uint32_t b = __ballot_sync(FULL, on);
-        if (lane == 0) s_warp_cnt[wid] = __popc(b);
-        __syncthreads();
-        uint32_t pre = base_rank, chunk = 0;
-        for (int w = 0; w < WT_WARPS; w++) {
-          const uint32_t cw = s_warp_cnt[w];
-          if (w < wid) pre += cw;
-          chunk += cw;
-        }
-        if (on) {
-          const uint32_t rank = pre + __popc(b & ((1u << lane) - 1u));
-          if ((int)((rank + round) % (uint32_t)a.group_size) == grank) my_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
-        }
-        base_rank += chunk;
-        __syncthreads();
-      }
       if (tid == 0) s_next = 0;
       __syncthreads();
       const uint32_t mine = s_mine;
