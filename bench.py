@@ -3,7 +3,7 @@
 
 Workload at N=1 (config.workload = "cfg3"): BASELINE.json configs[2], the configuration the north_star's target is
 quoted on -- "holonomic heuristic plus distance-layer EDT on a synthetic 4096x4096 random-obstacle grid".
-One step = one pass of the hot path over one map message and a batch of F queries on it (--fields, default 64; the
+One step = one pass of the hot path over one map message and a batch of F queries on it (--fields, default 128; the
 reference arm runs the same kind of batch, one field per host core):  K1 (per-cell tables + obstacle/distance layers of the
 occupancy, what the reference's Grid_map constructor does per map message) + K3a (the RS holonomic-with-obstacles
 heuristic field of each query's goal, what HybridAstar::run does first).  value = F x 4096^2 cells x steps / device
@@ -247,7 +247,10 @@ def ours_arm(args):
 
     # ---- e2e: the call a user of the reference API makes, host buffers in pinned memory
     occ_pin = torch.from_numpy(occ).pin_memory()
-    cost_pin = torch.empty(F * n, dtype=torch.float64, pin_memory=True)
+    try:
+        cost_pin = torch.empty(F * n, dtype=torch.float64, pin_memory=True)
+    except RuntimeError:                                       # not enough lockable host memory: pageable buffer
+        cost_pin = torch.empty(F * n, dtype=torch.float64)
     occ_h, cost_h = occ_pin.numpy(), cost_pin.numpy().reshape(F, side, side)
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
@@ -288,7 +291,8 @@ def ours_arm(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("heuristic_field_dram_bytes")
+            traffic = json.load(open(tpath)).get("heuristic_dram_bytes_per_field")
+            traffic = int(traffic * F) if traffic else None   # per launch, like `achieved` (ncu capture at 64 fields)
         except Exception:
             traffic = None
     line = {
@@ -432,7 +436,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=4096)
-    ap.add_argument("--fields", type=int, default=64, help="goal fields (queries) per step")
+    ap.add_argument("--fields", type=int, default=128, help="goal fields (queries) per step")
     ap.add_argument("--ref-cores", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

@@ -1190,7 +1190,8 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.tiles_y = tiles_y;
   a.n_tiles = n_tiles;
   a.n_fields = (int)n_fields;
-  a.delta = env_double("HPP_HEUR_DELTA", 2.0 * C::T);
+  // window width: wide windows = fewer rounds (latency of a lone field), narrow = fewer re-evaluations (throughput)
+  a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 256.0 : 128.0) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 16.0);
   const bool debug = getenv("HPP_HEUR_DEBUG") != nullptr;
   const size_t prof_n = (size_t)c->sm_count * 8 * 8 + 8;
@@ -1284,11 +1285,10 @@ extern "C" hpp_status hpp_heuristic_batch_dev(hpp_map *m, int variant, const int
                f, W, H);
   if (n_fields > 65535) HPP_FAIL(c, HPP_ERR_ARG, "at most 65535 fields per call");
   HPP_CUDA(c, cudaSetDevice(c->device));
-  // Tile side.  Few fields on a big map: 128 (16 warps per tile, one CTA per SM) -- the fewest rounds, best latency.
-  // Small maps: 64.  Many fields in flight: 32, one warp per tile (heur_warp_kernel) -- no barrier inside a tile,
-  // every warp of the GPU busy: the throughput configuration.
-  int nb = (W >= 1024 || H >= 1024) ? 4 : 2;
-  if (n_fields >= 8) nb = 1;
+  // Tile side.  Default: 32, one warp per tile (heur_warp_kernel): no barrier inside a tile, TMA-staged tiles, every
+  // warp of the GPU busy when several fields are in flight, and also the lowest single-field latency measured.
+  // HPP_HEUR_NB=2|4 selects the multi-warp tile kernel (64x64 / 128x128 tiles, heur_persist_kernel) instead.
+  int nb = 1;
   const int env_nb = (int)env_double("HPP_HEUR_NB", 0);
   if (env_nb == 1 || env_nb == 2 || env_nb == 4) nb = env_nb;
   if (nb == 1) return run_batch<1>(m, variant, goal_xy, n_fields, cost_dev, reports);
@@ -1297,29 +1297,40 @@ extern "C" hpp_status hpp_heuristic_batch_dev(hpp_map *m, int variant, const int
 }
 
 // host-buffer batch: n_fields goal cells on one map, fields returned in cost (n_fields x W*H doubles, pinned memory
-// recommended).  The fields are solved in chunks on the device and copied out chunk by chunk.
+// recommended).  Large batches are solved in two or more chunks so that the device-to-host copy of one chunk (a
+// field is 8 B/cell: the copy is PCIe-bound) overlaps the relaxation of the next.
 extern "C" hpp_status hpp_heuristic_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_fields, double *cost,
                                           hpp_quirk_report *reports) {
   if (!m || !goal_xy || !cost || n_fields == 0) return HPP_ERR_ARG;
   hpp_ctx *c = m->ctx;
   HPP_CUDA(c, cudaSetDevice(c->device));
+  if (!c->copy_stream) {
+    HPP_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    HPP_CUDA(c, cudaEventCreateWithFlags(&c->copy_done[0], cudaEventDisableTiming));
+    HPP_CUDA(c, cudaEventCreateWithFlags(&c->copy_done[1], cudaEventDisableTiming));
+  }
   size_t free_b = 0, total_b = 0;
   HPP_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   const size_t field_b = m->n * sizeof(double);
-  size_t chunk = n_fields;
+  size_t chunk = n_fields >= 64 ? (n_fields + 1) / 2 : n_fields;
   const size_t have = c->d_scratch_bytes[3] + free_b / 2;
-  if (chunk * field_b > have) chunk = have / field_b;
-  if (chunk < 1) HPP_FAIL(c, HPP_ERR_NOMEM, "not enough device memory for one heuristic field");
+  const int nbuf = chunk < n_fields ? 2 : 1;
+  if (nbuf * chunk * field_b > have) chunk = have / (2 * field_b);
+  if (chunk < 1) HPP_FAIL(c, HPP_ERR_NOMEM, "not enough device memory for two heuristic fields");
   void *d_cost;
-  hpp_status s = hpp_scratch(c, 3, chunk * field_b, &d_cost);
+  hpp_status s = hpp_scratch(c, 3, (chunk < n_fields ? 2 : 1) * chunk * field_b, &d_cost);
   if (s != HPP_OK) return s;
-  for (size_t f0 = 0; f0 < n_fields; f0 += chunk) {
+  size_t k = 0;
+  for (size_t f0 = 0; f0 < n_fields; f0 += chunk, k++) {
     const size_t nf = n_fields - f0 < chunk ? n_fields - f0 : chunk;
-    s = hpp_heuristic_batch_dev(m, variant, goal_xy + 2 * f0, nf, (double *)d_cost, reports ? reports + f0 : nullptr);
-    if (s != HPP_OK) return s;
-    HPP_CUDA(c, cudaMemcpyAsync(cost + f0 * m->n, d_cost, nf * field_b, cudaMemcpyDeviceToHost, c->stream));
-    HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+    double *buf = (double *)d_cost + (k & 1) * chunk * m->n;
+    if (k >= 2) HPP_CUDA(c, cudaEventSynchronize(c->copy_done[k & 1]));  // the copy that last read this buffer
+    s = hpp_heuristic_batch_dev(m, variant, goal_xy + 2 * f0, nf, buf, reports ? reports + f0 : nullptr);
+    if (s != HPP_OK) return s;  // (returns after the relaxation kernel completed)
+    HPP_CUDA(c, cudaMemcpyAsync(cost + f0 * m->n, buf, nf * field_b, cudaMemcpyDeviceToHost, c->copy_stream));
+    HPP_CUDA(c, cudaEventRecord(c->copy_done[k & 1], c->copy_stream));
   }
+  HPP_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   return HPP_OK;
 }
 

@@ -13,6 +13,8 @@ struct hpp_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
+  cudaStream_t copy_stream;   // D2H copies overlapped with compute (created on first use)
+  cudaEvent_t copy_done[2];
   uint64_t launches;
   char err[512];
   // pinned staging for small control words (convergence flags, counters)

@@ -39,6 +39,11 @@ extern "C" hpp_status hpp_ctx_destroy(hpp_ctx *c) {
     if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
   cudaFreeHost(c->h_flags);
   cudaFree(c->d_flags);
+  if (c->copy_stream) {
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->copy_done[0]);
+    cudaEventDestroy(c->copy_done[1]);
+  }
   cudaStreamDestroy(c->stream);
   free(c);
   return HPP_OK;

@@ -116,3 +116,46 @@ def test_heuristic_cfg3_full_size(ctx):
     assert rep.h1_progress_break == 0 and rep.h2_bucket_clamp == 0
     assert bits_equal(got, want), f"{(got != want).sum()} cells differ"
     m.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_heuristic_batch_host_chunks(ctx, variant):
+    """hpp_heuristic_batch: 70 goal cells in one call (>= 64 fields are solved in two overlapped chunks), every field
+    bit-identical to the oracle's fixed point; the reports carry the per-field reachable counts."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ = block_map(200, 150, 0.12, 3, seed=21)
+    rng = np.random.default_rng(5)
+    free = np.argwhere(occ == 0)
+    goals = np.array([free[i][::-1] for i in rng.choice(len(free), 70, replace=False)], np.int32)
+    goals[0] = (0, 0)
+    goals[1] = (199, 149)
+    m = hpp.Map(ctx, occ, 0.2)
+    got, reps = m.heuristic_batch(variant, goals, want_reports=True)
+    assert got.shape == (70, 150, 200)
+    for f in (0, 1, 2, 17, 34, 35, 36, 69):
+        g = tuple(int(v) for v in goals[f])
+        want = O.heuristic_rs(occ, g, (0, 0), quirks=False)[0] if variant == 0 else O.heuristic_dubins(occ, g)
+        assert bits_equal(got[f], want), f"field {f}: {(got[f] != want).sum()} cells differ"
+        fin = want < (np.inf if variant == 0 else 1000.0)
+        assert reps[f].reachable == int(fin.sum())
+    m.close()
+
+
+def test_heuristic_all_tile_kernels_agree(ctx, monkeypatch):
+    """the three tile configurations (32: warp-tile kernel with TMA staging; 64 / 128: multi-warp tile kernel) and both
+    window settings give the same bits on even- and odd-width maps (odd widths take the non-TMA staging path)"""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    for W, H in ((330, 257), (331, 120)):
+        occ = block_map(W, H, 0.25, 5, seed=W)
+        occ[H // 2, W // 2] = 0
+        want = O.heuristic_rs(occ, (W // 2, H // 2), (0, 0), quirks=False)[0]
+        m = hpp.Map(ctx, occ, 0.2)
+        for nb in ("1", "2", "4"):
+            for delta in ("24", "1000000"):
+                monkeypatch.setenv("HPP_HEUR_NB", nb)
+                monkeypatch.setenv("HPP_HEUR_DELTA", delta)
+                got, _ = m.heuristic_rs((W // 2, H // 2), (0, 0))
+                assert bits_equal(got, want), (W, H, nb, delta)
+        m.close()
