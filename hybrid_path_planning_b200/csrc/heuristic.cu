@@ -693,7 +693,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // per round), but a tile is a single 32x32 block solved by ONE warp with no block-level barrier at all: the 16 warps
 // of a CTA pull tiles of the round's schedule from a shared counter and never wait for each other inside a round.
 // This is the throughput configuration: with several fields in flight every warp of the GPU stays busy.
-constexpr int WT_WARPS = 16;
+#ifndef HPP_WT_WARPS
+#define HPP_WT_WARPS 16
+#endif
+constexpr int WT_WARPS = HPP_WT_WARPS;  // 20 also fits (96 registers, 207 KB shared)
 
 template <int VARIANT>
 __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __grid_constant__ heur_args a) {
