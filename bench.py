@@ -395,7 +395,8 @@ def extras(ctx, torch, hpp, stream):
         free = cand[O.collide_circles(om, cand) == 0][:2 * npairs]
         cx = hpp.Context(torch.cuda.current_device())
         jobs.append(dict(ctx=cx, map=hpp.Map(cx, pm, RES), om=om, starts=free[:npairs], goals=free[npairs:2 * npairs]))
-    jobs[0]["map"].plan_batch(hpp.VARIANT_RS, jobs[0]["starts"][:8], jobs[0]["goals"][:8])     # warm-up
+    for j in jobs:                                   # warm-up: every context grows its device scratch once
+        j["map"].plan_batch(hpp.VARIANT_RS, j["starts"], j["goals"])
 
     def work(j):
         j["plans"], _ = j["map"].plan_batch(hpp.VARIANT_RS, j["starts"], j["goals"])

@@ -1128,6 +1128,11 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   if (gs < 1) gs = 1;
   int n_groups = G / gs;
   if (n_groups > a.n_fields) n_groups = a.n_fields;
+  // One CTA per field never waits for another CTA, so it needs no co-residency guarantee: a plain launch with one CTA
+  // per field lets the hardware scheduler balance the fields and lets the kernel share the GPU with other streams
+  // (a cooperative launch would wait until every one of its CTAs fits at once).
+  const bool solo = gs == 1;
+  if (solo) n_groups = a.n_fields;
   a.group_size = gs;
   a.n_groups = n_groups;
   const int grid = gs * n_groups;
@@ -1138,7 +1143,10 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
     a.lists = (uint32_t *)lp;
   }
   void *params[] = {&a};
-  HPP_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), params, smem, c->stream));
+  if (solo)
+    HPP_CUDA(c, cudaLaunchKernel(kern, dim3(grid), dim3(threads), params, smem, c->stream));
+  else
+    HPP_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), params, smem, c->stream));
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
@@ -1155,7 +1163,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   const size_t act_b = al(sizeof(uint32_t) * 3 * n_tiles * n_fields);
   const size_t pmin_b = al(sizeof(unsigned long long) * 2 * n_tiles * n_fields);
   const size_t dmask_b = al(sizeof(uint32_t) * (size_t)n_tiles * C::NBLK * 32 * n_fields);
-  const size_t bar_b = al(sizeof(uint32_t) * 32 * (size_t)c->sm_count * 8);
+  const size_t bar_b = al(sizeof(uint32_t) * 32 * ((size_t)c->sm_count * 8 + n_fields));
   const size_t stats_b = al(sizeof(uint32_t) * 4 * n_fields);
   const size_t goals_b = al(n_fields * 8);
   const size_t fstats_b = al(n_fields * 16);
@@ -1197,7 +1205,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 256.0 : 128.0) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 16.0);
   const bool debug = getenv("HPP_HEUR_DEBUG") != nullptr;
-  const size_t prof_n = (size_t)c->sm_count * 8 * 8 + 8;
+  const size_t prof_n = ((size_t)c->sm_count * 8 + n_fields) * 8 + 8;
   if (debug) {
     void *pp;
     s = hpp_scratch(c, 5, prof_n * 8, &pp);

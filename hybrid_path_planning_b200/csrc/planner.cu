@@ -463,13 +463,12 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   char *d_pool = nullptr, *d_io = nullptr;
   double *d_fields = nullptr;
   const size_t io_bytes = n * 48 + n * 8 + n * sizeof(hpp_plan) + traj_cap * 40 + 64;
-  cudaError_t e = cudaMalloc((void **)&d_pool, n_warps * per_warp + 256);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_io, io_bytes);
-  hpp_status st = HPP_OK;
-  if (e != cudaSuccess) {
-    snprintf(c->err, sizeof c->err, "plan_batch allocation failed: %s", cudaGetErrorString(e));
-    st = HPP_ERR_NOMEM;
-  }
+  // buffers come from the context's grow-only scratch: a per-call cudaMalloc/cudaFree would synchronise the whole
+  // device and serialise plan_batch calls that other contexts (threads) run concurrently on the same GPU
+  cudaError_t e = cudaSuccess;
+  hpp_status st = hpp_scratch(c, 1, n_warps * per_warp + 256, (void **)&d_pool);
+  if (st == HPP_OK) st = hpp_scratch(c, 0, io_bytes, (void **)&d_io);
+  if (st != HPP_OK) st = HPP_ERR_NOMEM;
   double *d_starts = nullptr, *d_goals = nullptr, *d_traj = nullptr;
   int *d_qids = nullptr, *d_fq = nullptr;
   hpp_plan *d_plans = nullptr;
@@ -512,13 +511,7 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
       }
       const size_t nf = chunk_goals.size() / 2;
       if (nf > fields_alloc) {
-        if (d_fields) {
-          cudaStreamSynchronize(c->stream);
-          cudaFree(d_fields);
-        }
-        e = cudaMalloc((void **)&d_fields, nf * field_bytes);
-        if (e != cudaSuccess) {
-          snprintf(c->err, sizeof c->err, "heuristic fields allocation failed: %s", cudaGetErrorString(e));
+        if (hpp_scratch(c, 3, nf * field_bytes, (void **)&d_fields) != HPP_OK) {
           st = HPP_ERR_NOMEM;
           d_fields = nullptr;
           break;
@@ -569,8 +562,5 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
     }
   }
   cudaStreamSynchronize(c->stream);
-  if (d_fields) cudaFree(d_fields);
-  if (d_pool) cudaFree(d_pool);
-  if (d_io) cudaFree(d_io);
   return st;
 }
