@@ -12,7 +12,7 @@
  *
  * Pinning status (see DESIGN.md "Oracle"):
  *   - a1/a5/a6/a7 (RS) and a8/a9/a10/a11 (Dubins) are pinned against the reference's own
- *     translation units compiled into oracle/_ref (tests/test_oracle_vs_ref.py, and the
+ *     translation units compiled into oracle/_ref (tests/test_cpu_oracle_vs_ref.py, and the
  *     committed tests/golden/ vectors generated from them).
  *   - a3 (EDT layers) and a12 (inflate) are pinned against cv2 (IPP off) goldens.
  *   - a4 (grid_map::atPosition bilinear + isInside) restates grid_map_core from its
