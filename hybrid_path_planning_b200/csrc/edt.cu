@@ -3,12 +3,12 @@
 //
 // Separable exact Euclidean distance transform in integer arithmetic:
 //   pass 1 (rows, along x):  g(x,y) = distance along x to the nearest obstacle cell of row y (uint16,
-//                            0xFFFF = the row has none).  One CTA per row, row staged in shared memory,
-//                            block-wide max/min scans of the nearest obstacle index, 16-byte vector I/O.
+//                            0xFFFF = the row has none).  One warp per row, bit-parallel: ballot words of the
+//                            obstacle predicate, clz/ffs inside a word, per-word carries across words.
 //   pass 2 (columns, along y): d2(x,y) = min_y' g(x,y')^2 + (y-y')^2 by an outward search that stops as
-//                            soon as k^2 >= best.  64x64 output tiles with a +-32-row halo of g in shared
-//                            memory (adjacent threads = adjacent x => coalesced); rows beyond the halo are
-//                            read through L2.  Epilogue: sqrtf((float)d2) * (float)res (both correctly
+//                            soon as k^2 >= best.  64x128 output tiles with a +-32-row halo of g in shared
+//                            memory (adjacent threads = adjacent x => coalesced, 16-byte staging loads); rows
+//                            beyond the halo are read through L2.  Epilogue: sqrtf((float)d2) * (float)res (both correctly
 //                            rounded, no FMA) stored at the 180-degree-rotated index n-1-k (hazard H7).
 // The float32 lower-envelope pass of OpenCV returns exactly sqrtf(d2) whenever d2 < 2^24 (distances below
 // 4096 cells); beyond that its float rounding is not reproduced (documented in DESIGN.md).
@@ -26,141 +26,117 @@ __device__ __forceinline__ int lut_test(const pred_lut &l, int8_t v) {
   return (l.w[u >> 5] >> (u & 31)) & 1u;
 }
 
-// ---- block-wide inclusive scans over one int per thread (256 threads) ----
-__device__ __forceinline__ int block_excl_max_scan(int v, int *warp_tot /*8*/, int ident) {
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int o = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc = max(inc, o);
-  }
-  if (lane == 31) warp_tot[wid] = inc;
-  __syncthreads();
-  int carry = ident;
-  for (int w = 0; w < wid; w++) carry = max(carry, warp_tot[w]);
-  int exc = __shfl_up_sync(0xffffffffu, inc, 1);
-  if (lane == 0) exc = ident;
-  __syncthreads();
-  return max(carry, exc);
-}
-
-__device__ __forceinline__ int block_excl_min_suffix_scan(int v, int *warp_tot /*8*/, int ident) {
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int o = __shfl_down_sync(0xffffffffu, inc, d);
-    if (lane + d < 32) inc = min(inc, o);
-  }
-  if (lane == 0) warp_tot[wid] = inc;
-  __syncthreads();
-  int carry = ident;
-  for (int w = wid + 1; w < nw; w++) carry = min(carry, warp_tot[w]);
-  int exc = __shfl_down_sync(0xffffffffu, inc, 1);
-  if (lane == 31) exc = ident;
-  __syncthreads();
-  return min(carry, exc);
-}
-
-// pass 1.  smem: flag[W] bytes then (2-byte aligned) g[W] uint16.
+// pass 1.  One warp per row, bit-parallel: the obstacle predicate of 32 consecutive cells is one ballot word, the
+// nearest obstacle inside a word is a clz / ffs on the masked word, and across words it is a per-word carry (the
+// last set bit before / the first set bit after the word), found by a 32-lane chunked scan over the row's words.
+// Every global access is coalesced (lane = consecutive cell) and there is no sequential dependency along the row.
+// Shared memory per warp: mask[NW], prev[NW], next[NW] (NW = ceil(W/32) words).
 // obstacle may be null (inflate reuses this kernel).  lut_dev: predicate table in device memory.
-__global__ void __launch_bounds__(256) edt_row_kernel(const int8_t *__restrict__ occ, int W, int H,
-                                                      const pred_lut *__restrict__ lut_dev,
-                                                      uint16_t *__restrict__ g, float *__restrict__ obstacle,
-                                                      uint32_t *__restrict__ any_obstacle) {
+#define EDT_ROW_WARPS 8
+__global__ void __launch_bounds__(EDT_ROW_WARPS * 32) edt_row_kernel(const int8_t *__restrict__ occ, int W, int H,
+                                                                     const pred_lut *__restrict__ lut_dev,
+                                                                     uint16_t *__restrict__ g,
+                                                                     float *__restrict__ obstacle,
+                                                                     uint32_t *__restrict__ any_obstacle) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int warp_tot[8];
   __shared__ pred_lut lut;
-  const int Wpad = (W + 15) & ~15;
-  unsigned char *flag = smem;
-  uint16_t *gs = (uint16_t *)(smem + Wpad);
-  const int y = blockIdx.x;
-  const int8_t *row = occ + (size_t)y * W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int NW = (W + 31) >> 5;
+  uint32_t *mask = (uint32_t *)smem + (size_t)wid * 3 * NW;
+  int *prev = (int *)(mask + NW), *next = prev + NW;
   if (threadIdx.x < 8) lut.w[threadIdx.x] = lut_dev->w[threadIdx.x];
   __syncthreads();
-
-  // stage the row: predicate bytes
-  if ((W & 15) == 0) {
-    const int4 *row4 = (const int4 *)row;
-    for (int i = threadIdx.x; i < W / 16; i += blockDim.x) {
-      int4 v = __ldg(row4 + i);
-      int8_t b[16];
-      *(int4 *)b = v;
-      unsigned char f[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) f[k] = (unsigned char)lut_test(lut, b[k]);
-      *(int4 *)(flag + 16 * i) = *(int4 *)f;
+  const int FAR = 1 << 20;
+  for (int y = blockIdx.x * EDT_ROW_WARPS + wid; y < H; y += gridDim.x * EDT_ROW_WARPS) {
+    const int8_t *row = occ + (size_t)y * W;
+    float *orow = obstacle ? obstacle + (size_t)y * W : nullptr;
+    // predicate words (+ the obstacle layer: same linear index x + y*W as the occupancy, 1 = free)
+    uint32_t any = 0;
+    for (int j = 0; j < NW; j++) {
+      const int x = (j << 5) + lane;
+      const bool p = x < W && lut_test(lut, row[x]);
+      const uint32_t m = __ballot_sync(0xffffffffu, p);
+      if (lane == 0) mask[j] = m;
+      any |= m;
+      if (orow && x < W) orow[x] = p ? 0.f : 1.f;
     }
-  } else {
-    for (int i = threadIdx.x; i < W; i += blockDim.x) flag[i] = (unsigned char)lut_test(lut, row[i]);
-  }
-  __syncthreads();
-
-  // per-thread contiguous chunk
-  const int C = (W + blockDim.x - 1) / blockDim.x;
-  const int c0 = min(W, (int)threadIdx.x * C), c1 = min(W, c0 + C);
-  int last = -(1 << 20), first = (1 << 20);
-  for (int x = c0; x < c1; x++)
-    if (flag[x]) {
-      last = x;
-      if (first == (1 << 20)) first = x;
-    }
-  int carryL = block_excl_max_scan(last, warp_tot, -(1 << 20));
-  int carryR = block_excl_min_suffix_scan(first, warp_tot, (1 << 20));
-  int l = carryL;
-  for (int x = c0; x < c1; x++) {
-    if (flag[x]) l = x;
-    int d = x - l;
-    gs[x] = (uint16_t)(d >= (int)EDT_INF16 ? EDT_INF16 : d);
-  }
-  int r = carryR;
-  for (int x = c1 - 1; x >= c0; x--) {
-    if (flag[x]) r = x;
-    int d = r - x;
-    if (d < (int)gs[x]) gs[x] = (uint16_t)d;
-  }
-  if (threadIdx.x == 0 && (carryR < (1 << 20) || first < (1 << 20))) *any_obstacle = 1u;
-  __syncthreads();
-
-  // store g (and the obstacle layer: same linear index x + y*W as the occupancy)
-  uint16_t *grow = g + (size_t)y * W;
-  if ((W & 7) == 0) {
-    for (int i = threadIdx.x; i < W / 8; i += blockDim.x) ((uint4 *)grow)[i] = ((const uint4 *)gs)[i];
-  } else {
-    for (int i = threadIdx.x; i < W; i += blockDim.x) grow[i] = gs[i];
-  }
-  if (obstacle) {
-    float *orow = obstacle + (size_t)y * W;
-    if ((W & 3) == 0) {
-      for (int i = threadIdx.x; i < W / 4; i += blockDim.x) {
-        uchar4 f = ((const uchar4 *)flag)[i];
-        float4 o = make_float4(f.x ? 0.f : 1.f, f.y ? 0.f : 1.f, f.z ? 0.f : 1.f, f.w ? 0.f : 1.f);
-        ((float4 *)orow)[i] = o;
+    __syncwarp();
+    // carries: lane l scans the contiguous chunk of words [l*C, (l+1)*C)
+    const int C = (NW + 31) >> 5;
+    const int j0 = min(NW, lane * C), j1 = min(NW, j0 + C);
+    int last = -FAR, first = FAR;
+    for (int j = j0; j < j1; j++) {
+      const uint32_t m = mask[j];
+      if (m) {
+        last = (j << 5) + 31 - __clz(m);
+        if (first == FAR) first = (j << 5) + __ffs(m) - 1;
       }
-    } else {
-      for (int i = threadIdx.x; i < W; i += blockDim.x) orow[i] = flag[i] ? 0.f : 1.f;
     }
+    int inc_l = last, inc_f = first;  // inclusive max-scan of last (up), inclusive min-scan of first (down)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc_l, d);
+      if (lane >= d) inc_l = max(inc_l, o);
+      const int q = __shfl_down_sync(0xffffffffu, inc_f, d);
+      if (lane + d < 32) inc_f = min(inc_f, q);
+    }
+    int carry_l = __shfl_up_sync(0xffffffffu, inc_l, 1), carry_f = __shfl_down_sync(0xffffffffu, inc_f, 1);
+    if (lane == 0) carry_l = -FAR;
+    if (lane == 31) carry_f = FAR;
+    for (int j = j0; j < j1; j++) {  // prev[j]: last obstacle before word j
+      prev[j] = carry_l;
+      const uint32_t m = mask[j];
+      if (m) carry_l = (j << 5) + 31 - __clz(m);
+    }
+    for (int j = j1 - 1; j >= j0; j--) {  // next[j]: first obstacle after word j
+      next[j] = carry_f;
+      const uint32_t m = mask[j];
+      if (m) carry_f = (j << 5) + __ffs(m) - 1;
+    }
+    __syncwarp();
+    uint16_t *grow = g + (size_t)y * W;
+    for (int j = 0; j < NW; j++) {
+      const int x = (j << 5) + lane;
+      const uint32_t m = mask[j];
+      const uint32_t ml = m & (0xffffffffu >> (31 - lane)), mr = m & (0xffffffffu << lane);
+      const int li = ml ? (j << 5) + 31 - __clz(ml) : prev[j];
+      const int ri = mr ? (j << 5) + __ffs(mr) - 1 : next[j];
+      const int d = min(x - li, ri - x);
+      if (x < W) grow[x] = (uint16_t)(d >= (int)EDT_INF16 ? EDT_INF16 : d);
+    }
+    if (lane == 0 && any) *any_obstacle = 1u;
+    __syncwarp();
   }
 }
 
-// pass 2.
+// pass 2.  64 columns x 128 rows of output per CTA, +-32 rows of halo in shared memory (1.5x read amplification of g).
 #define EDT_TX 64
-#define EDT_TY 64
+#define EDT_TY 128
 #define EDT_R 32
 __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict__ g, int W, int H, float res_f,
                                                       float *__restrict__ distance,
                                                       const uint32_t *__restrict__ any_obstacle) {
-  __shared__ uint16_t gs[EDT_TY + 2 * EDT_R][EDT_TX];
+  __shared__ __align__(16) uint16_t gs[EDT_TY + 2 * EDT_R][EDT_TX];
   const int x0 = blockIdx.x * EDT_TX, y0 = blockIdx.y * EDT_TY;
   const int tx = threadIdx.x & (EDT_TX - 1), tyb = threadIdx.x / EDT_TX;  // 4 row groups
   const int x = x0 + tx;
   const size_t n = (size_t)W * H;
-  for (int r = tyb; r < EDT_TY + 2 * EDT_R; r += 256 / EDT_TX) {
-    int yy = y0 - EDT_R + r;
-    uint16_t v = EDT_INF16;
-    if (x < W && yy >= 0 && yy < H) v = g[(size_t)yy * W + x];
-    gs[r][tx] = v;
+  if ((W & 7) == 0 && x0 + EDT_TX <= W) {
+    // 16-byte loads: a tile row is 8 chunks of 8 uint16
+    for (int i = threadIdx.x; i < (EDT_TY + 2 * EDT_R) * (EDT_TX / 8); i += 256) {
+      const int r = i / (EDT_TX / 8), c8 = i % (EDT_TX / 8);
+      const int yy = y0 - EDT_R + r;
+      uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (yy >= 0 && yy < H) v = __ldg((const uint4 *)(g + (size_t)yy * W + x0) + c8);
+      *((uint4 *)&gs[r][0] + c8) = v;
+    }
+  } else {
+    for (int r = tyb; r < EDT_TY + 2 * EDT_R; r += 256 / EDT_TX) {
+      int yy = y0 - EDT_R + r;
+      uint16_t v = EDT_INF16;
+      if (x < W && yy >= 0 && yy < H) v = g[(size_t)yy * W + x];
+      gs[r][tx] = v;
+    }
   }
   __syncthreads();
   if (x >= W) return;
@@ -202,10 +178,13 @@ static const pred_lut *edt_lut_dev(hpp_ctx *c) { return (const pred_lut *)(c->d_
 // row pass launcher shared with inflate.cu (lut_dev: 8 words in device memory)
 hpp_status hpp_row_dist_launch(hpp_ctx *c, const int8_t *occ_dev, int W, int H, const void *lut_dev, uint16_t *g,
                                float *obstacle, uint32_t *any_obstacle) {
-  size_t smem = (size_t)((W + 15) & ~15) + (size_t)W * 2 + 16;
+  const size_t smem = (size_t)EDT_ROW_WARPS * 3 * ((W + 31) / 32) * sizeof(uint32_t);
   if (smem > 48 * 1024)
     HPP_CUDA(c, cudaFuncSetAttribute(edt_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edt_row_kernel<<<H, 256, smem, c->stream>>>(occ_dev, W, H, (const pred_lut *)lut_dev, g, obstacle, any_obstacle);
+  int grid = hpp_div_up(H, EDT_ROW_WARPS);
+  if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+  edt_row_kernel<<<grid, EDT_ROW_WARPS * 32, smem, c->stream>>>(occ_dev, W, H, (const pred_lut *)lut_dev, g, obstacle,
+                                                                any_obstacle);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }

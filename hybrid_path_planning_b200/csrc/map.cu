@@ -125,10 +125,92 @@ __global__ void __launch_bounds__(256) build_cls_kernel(const int8_t *__restrict
   }
 }
 
+// Same tables, four consecutive cells per thread (needs W % 4 == 0): three rows x (one aligned 32-bit word + the two
+// bytes beside it) instead of 13 bounds-checked byte loads per cell; the class bytes leave as one 32-bit store and
+// the bit rows are assembled from four ballots (lane l holds cells 4l..4l+3 of a 128-cell span = 4 words).
+__device__ __forceinline__ uint32_t spread8(uint32_t b) {  // bit i of the low byte -> bit 4i
+  b &= 0xffu;
+  b = (b | (b << 12)) & 0x000F000Fu;
+  b = (b | (b << 6)) & 0x03030303u;
+  b = (b | (b << 3)) & 0x11111111u;
+  return b;
+}
+
+__global__ void __launch_bounds__(256) build_cls4_kernel(const int8_t *__restrict__ occ, int W, int H,
+                                                         uint8_t *__restrict__ cls, uint32_t *__restrict__ bits,
+                                                         uint32_t *__restrict__ near_bits, int pitch) {
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y;
+  const bool in = x0 < W;
+  uint32_t blocked4 = 0, near4m = 0;
+  if (in) {
+    // per row: bit c (c = 0..5) <-> column x0 - 1 + c.  cb: isInCollision (out of bounds = 1), ib: in bounds and data > 0
+    uint32_t cb[3], ib[3];
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+      const int yy = y + dy;
+      uint32_t c = 0x3fu, i = 0;
+      if (yy >= 0 && yy < H) {
+        const int8_t *row = occ + (size_t)yy * W;
+        const uint32_t w = *(const uint32_t *)(row + x0);
+        i = ((int8_t)(w & 0xff) > 0 ? 2u : 0u) | ((int8_t)((w >> 8) & 0xff) > 0 ? 4u : 0u) |
+            ((int8_t)((w >> 16) & 0xff) > 0 ? 8u : 0u) | ((int8_t)(w >> 24) > 0 ? 16u : 0u);
+        c = i;
+        if (x0 > 0) {
+          if (row[x0 - 1] > 0) i |= 1u, c |= 1u;
+        } else {
+          c |= 1u;
+        }
+        if (x0 + 4 < W) {
+          if (row[x0 + 4] > 0) i |= 32u, c |= 32u;
+        } else {
+          c |= 32u;
+        }
+      }
+      cb[dy + 1] = c;
+      ib[dy + 1] = i;
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t cnt = __popc((cb[0] >> k) & 7u) + __popc((cb[1] >> k) & 7u) + __popc((cb[2] >> k) & 7u);
+      const uint32_t nr = ((ib[1] >> k) | (ib[1] >> (k + 2)) | (ib[0] >> (k + 1)) | (ib[2] >> (k + 1))) & 1u;
+      const uint32_t bl = (ib[1] >> (k + 1)) & 1u;
+      out |= ((bl ? CLS_BLOCKED : 0u) | (nr ? CLS_NEAR4 : 0u) | cnt) << (8 * k);
+      blocked4 |= bl << k;
+      near4m |= nr << k;
+    }
+    *(uint32_t *)(cls + (size_t)y * W + x0) = out;
+  }
+  uint32_t wb = 0, wn = 0;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t bb = __ballot_sync(0xffffffffu, (blocked4 >> k) & 1u);
+    const uint32_t bn = __ballot_sync(0xffffffffu, (near4m >> k) & 1u);
+    if (lane < 4) {
+      wb |= spread8(bb >> (8 * lane)) << k;
+      wn |= spread8(bn >> (8 * lane)) << k;
+    }
+  }
+  const int word = ((x0 - 4 * lane) >> 5) + lane;  // first word of the warp's 128-cell span + my word
+  if (lane < 4 && word < pitch) {
+    bits[(size_t)y * pitch + word] = wb;
+    near_bits[(size_t)y * pitch + word] = wn;
+  }
+}
+
 hpp_status hpp_build_cls(hpp_map *m) {
   hpp_ctx *c = m->ctx;
-  dim3 grid(hpp_div_up(m->g.W, 256), m->g.H);
-  build_cls_kernel<<<grid, 256, 0, c->stream>>>(m->d_occ, m->g.W, m->g.H, m->d_cls, m->d_occ_bits, m->d_near_bits, m->bits_pitch);
+  if ((m->g.W & 3) == 0) {
+    dim3 grid(hpp_div_up(m->g.W, 4 * 256), m->g.H);
+    build_cls4_kernel<<<grid, 256, 0, c->stream>>>(m->d_occ, m->g.W, m->g.H, m->d_cls, m->d_occ_bits, m->d_near_bits,
+                                                   m->bits_pitch);
+  } else {
+    dim3 grid(hpp_div_up(m->g.W, 256), m->g.H);
+    build_cls_kernel<<<grid, 256, 0, c->stream>>>(m->d_occ, m->g.W, m->g.H, m->d_cls, m->d_occ_bits, m->d_near_bits,
+                                                  m->bits_pitch);
+  }
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
