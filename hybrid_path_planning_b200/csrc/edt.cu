@@ -32,7 +32,7 @@ __device__ __forceinline__ int lut_test(const pred_lut &l, int8_t v) {
 // Every global access is coalesced (lane = consecutive cell) and there is no sequential dependency along the row.
 // Shared memory per warp: mask[NW], prev[NW], next[NW] (NW = ceil(W/32) words).
 // obstacle may be null (inflate reuses this kernel).  lut_dev: predicate table in device memory.
-#define EDT_ROW_WARPS 8
+#define EDT_ROW_WARPS 4
 __global__ void __launch_bounds__(EDT_ROW_WARPS * 32) edt_row_kernel(const int8_t *__restrict__ occ, int W, int H,
                                                                      const pred_lut *__restrict__ lut_dev,
                                                                      uint16_t *__restrict__ g,
@@ -52,7 +52,25 @@ __global__ void __launch_bounds__(EDT_ROW_WARPS * 32) edt_row_kernel(const int8_
     float *orow = obstacle ? obstacle + (size_t)y * W : nullptr;
     // predicate words (+ the obstacle layer: same linear index x + y*W as the occupancy, 1 = free)
     uint32_t any = 0;
-    for (int j = 0; j < NW; j++) {
+    int j = 0;
+    for (; j + 4 <= NW; j += 4) {  // four independent byte loads in flight per lane
+      int8_t v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int x = ((j + u) << 5) + lane;
+        v[u] = x < W ? row[x] : (int8_t)0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int x = ((j + u) << 5) + lane;
+        const bool p = x < W && lut_test(lut, v[u]);
+        const uint32_t m = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) mask[j + u] = m;
+        any |= m;
+        if (orow && x < W) orow[x] = p ? 0.f : 1.f;
+      }
+    }
+    for (; j < NW; j++) {
       const int x = (j << 5) + lane;
       const bool p = x < W && lut_test(lut, row[x]);
       const uint32_t m = __ballot_sync(0xffffffffu, p);
@@ -95,6 +113,7 @@ __global__ void __launch_bounds__(EDT_ROW_WARPS * 32) edt_row_kernel(const int8_
     }
     __syncwarp();
     uint16_t *grow = g + (size_t)y * W;
+#pragma unroll 4
     for (int j = 0; j < NW; j++) {
       const int x = (j << 5) + lane;
       const uint32_t m = mask[j];
