@@ -77,6 +77,7 @@ struct heur_args {
   uint32_t *bar;                   // [n_groups][32]: count, generation
   uint32_t *stats;                 // [n_fields][4]: rounds, tile visits, windows, sweeps of CTA rank 0
   uint32_t *lists;                 // warp-tile kernel: [grid][n_tiles] schedule of the round
+  uint32_t *sched;                 // warp-tile kernel: [n_groups][4 * group_size] slice counts + minima of a round
   unsigned long long *prof;        // optional [grid][8] cycle counters (HPP_HEUR_DEBUG): schedule, stage, solve,
                                    // write-back, barrier wait, tiles, phases, longest single solve
   double delta;                    // width of the global cost window
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   double *cs_all = (double *)smem_raw;                                  // WT_WARPS x ROWS*S
   uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);          // WT_WARPS x ROWS*S (Dubins only)
   __shared__ unsigned long long s_gmin;
-  __shared__ uint32_t s_mine, s_next, s_warp_cnt[32], s_outw[WT_WARPS];
+  __shared__ uint32_t s_mine, s_next, s_warp_cnt[32], s_outw[WT_WARPS], s_pref[WT_WARPS * 32];
   __shared__ double s_db[20];
   __shared__ __align__(8) unsigned long long s_mbar[WT_WARPS];  // one TMA completion barrier per warp
 
@@ -765,6 +766,16 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
       // to the next round's table, zero the activity buffer of the round after (both idempotent under a re-scan:
       // a tile that becomes schedulable overwrites its minimum when it is processed).
       const bool solo = a.group_size == 1;
+      // Scan of the tile table.  A lone CTA (one field per CTA) scans all of it.  In a group, CTA c scans only the
+      // slice [c, c+1) * n_tiles / group_size, publishes (count, minimum, compacted slice list) to global memory, the
+      // group meets at one extra barrier, and every CTA derives its share of the round from the group_size counts --
+      // instead of 148 CTAs each pulling the whole table through L2 every round.
+      const int s0 = solo ? 0 : (int)((long long)n_tiles * grank / a.group_size);
+      const int s1 = solo ? n_tiles : (int)((long long)n_tiles * (grank + 1) / a.group_size);
+      const int range = ((((s1 - s0) + WT_WARPS - 1) / WT_WARPS) + 31) & ~31;
+      const int r0 = s0 + wid * range, r1 = min(s1, r0 + range);
+      uint32_t *slice_cnt = a.sched + (size_t)group * 4 * a.group_size;        // [group_size] counts
+      unsigned long long *slice_min = (unsigned long long *)(slice_cnt + 2 * a.group_size);  // [group_size] minima
       uint32_t total;
       for (;;) {
         if (tid == 0) {
@@ -772,50 +783,90 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
           s_mine = 0;
         }
         __syncthreads();
+        // pass A: count my range, minimum of the deferred costs, housekeeping (whoever scans a tile owns it)
         unsigned long long mn = INF_BITS;
-        uint32_t base_rank = 0;
-        for (int t0 = 0; t0 < n_tiles; t0 += THREADS) {
-          const int t = t0 + tid;
+        uint32_t cnt = 0;
+        for (int t0 = r0; t0 < r1; t0 += 32) {
+          const int t = t0 + lane;
           bool on = false;
-          if (t < n_tiles) {
+          if (t < r1) {
             const uint32_t af = __ldcg(act_cur + t);
             const unsigned long long pm = __ldcg(pm_cur + t);
             on = af != 0 || __longlong_as_double((long long)pm) < bound;
             mn = pm < mn ? pm : mn;
-            if (solo || t % a.group_size == grank) {
-              if (!on) __stcg(pm_next + t, pm);
-              __stcg(act_clr + t, 0u);
-            }
+            if (!on) __stcg(pm_next + t, pm);
+            __stcg(act_clr + t, 0u);
           }
-          const uint32_t b = __ballot_sync(FULL, on);
-          if (lane == 0) s_warp_cnt[wid] = __popc(b);
-          __syncthreads();
-          // exclusive prefix of the 16 warp counts by shuffles (every warp computes the same scan)
-          uint32_t v = lane < WT_WARPS ? s_warp_cnt[lane] : 0u, inc = v;
-#pragma unroll
-          for (int d = 1; d < WT_WARPS; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if (lane >= d) inc += o;
-          }
-          const uint32_t pre = base_rank + __shfl_sync(FULL, inc - v, wid);
-          const uint32_t chunk = __shfl_sync(FULL, inc, WT_WARPS - 1);
-          if (on) {
-            const uint32_t rank = pre + __popc(b & ((1u << lane) - 1u));
-            if (solo || (int)((rank + round) % (uint32_t)a.group_size) == grank)
-              my_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
-          }
-          base_rank += chunk;
-          __syncthreads();
+          cnt += __popc(__ballot_sync(FULL, on));
         }
         for (int d = 16; d; d >>= 1) {
           const unsigned long long o = __shfl_down_sync(FULL, mn, d);
           mn = o < mn ? o : mn;
         }
-        if (lane == 0 && mn != INF_BITS) atomicMin(&s_gmin, mn);
+        if (lane == 0) {
+          s_warp_cnt[wid] = cnt;
+          if (mn != INF_BITS) atomicMin(&s_gmin, mn);
+        }
         __syncthreads();
-        total = base_rank;
-        const unsigned long long g = s_gmin;
-        __syncthreads();
+        // exclusive prefix of the warp counts by shuffles (every warp computes the same scan)
+        uint32_t v = lane < WT_WARPS ? s_warp_cnt[lane] : 0u, inc = v;
+#pragma unroll
+        for (int d = 1; d < WT_WARPS; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(FULL, inc, d);
+          if (lane >= d) inc += o;
+        }
+        uint32_t rank0 = __shfl_sync(FULL, inc - v, wid);
+        const uint32_t my_total = __shfl_sync(FULL, inc, WT_WARPS - 1);
+        unsigned long long g = s_gmin;
+        // pass B: compact the schedulable tiles of my range (in tile order) into my list
+        if (my_total != 0) {
+          for (int t0 = r0; t0 < r1; t0 += 32) {
+            const int t = t0 + lane;
+            bool on = false;
+            if (t < r1) {
+              const uint32_t af = __ldcg(act_cur + t);
+              const unsigned long long pm = __ldcg(pm_cur + t);
+              on = af != 0 || __longlong_as_double((long long)pm) < bound;
+            }
+            const uint32_t b = __ballot_sync(FULL, on);
+            if (on) my_list[rank0 + __popc(b & ((1u << lane) - 1u))] = (uint32_t)t;
+            rank0 += __popc(b);
+          }
+        }
+        total = my_total;
+        if (!solo) {
+          // publish my slice, meet, then read everybody's counts and minima
+          if (tid == 0) {
+            __stcg(slice_cnt + grank, my_total);
+            __stcg(slice_min + grank, g);
+          }
+          group_barrier(bar, a.group_size);
+          if (tid == 0) {
+            s_mine = 0;
+            s_gmin = INF_BITS;
+          }
+          uint32_t my_c = 0;
+          if (tid < a.group_size) {
+            my_c = __ldcg(slice_cnt + tid);
+            s_pref[tid] = my_c;
+          }
+          __syncthreads();
+          if (tid < a.group_size) {
+            const unsigned long long m2 = __ldcg(slice_min + tid);
+            if (m2 != INF_BITS) atomicMin(&s_gmin, m2);
+            uint32_t pre = 0;
+            for (int c = 0; c < tid; c++) pre += s_pref[c];
+            if (tid == a.group_size - 1) s_mine = pre + my_c;
+            my_c = pre;
+          }
+          __syncthreads();
+          if (tid < a.group_size) s_pref[tid] = my_c;  // exclusive prefix: first global rank of slice tid
+          __syncthreads();
+          total = s_mine;
+          g = s_gmin;
+          __syncthreads();
+          if (total == 0 && g != INF_BITS) group_barrier(bar, a.group_size);  // before the slices are rewritten
+        }
         if (total != 0 || g == INF_BITS) break;
         bound = __longlong_as_double((long long)g) + a.delta;  // open the next cost window
         windows++;
@@ -824,7 +875,10 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
       rounds++;
       if (tid == 0) s_next = 0;
       __syncthreads();
-      const uint32_t mine = s_mine;
+      // my share of the round: a lone CTA takes its whole list; in a group the schedulable tiles are ranked in slice
+      // order and I take the ranks == grank + round (mod group size): rank -> (slice, offset) through the counts
+      const uint32_t mine = solo ? total : (total + (uint32_t)a.group_size - 1u - (uint32_t)((grank + round) % a.group_size)) /
+                                               (uint32_t)a.group_size;
 
       // ---- drain: every warp pulls tiles until the list is empty
       for (;;) {
@@ -832,7 +886,24 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
         if (lane == 0) i = atomicAdd(&s_next, 1u);
         i = __shfl_sync(FULL, i, 0);
         if (i >= mine) break;
-        const int tile = (int)my_list[i];
+        int tile;
+        if (solo) {
+          tile = (int)my_list[i];
+        } else {
+          // global rank of my i-th tile, then the slice that holds it (the counts are few: a serial walk by lane 0)
+          const uint32_t rk = (uint32_t)((grank + round) % a.group_size) + i * (uint32_t)a.group_size;
+          int tl = 0;
+          if (lane == 0) {
+            int lo = 0, hi = a.group_size - 1;  // last slice whose first rank is <= rk
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (s_pref[mid] <= rk) lo = mid;
+              else hi = mid - 1;
+            }
+            tl = (int)__ldcg(a.lists + (size_t)(group * a.group_size + lo) * a.n_tiles + (rk - s_pref[lo]));
+          }
+          tile = __shfl_sync(FULL, tl, 0);
+        }
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
         const int x0 = tx * T, y0 = ty * T;
         visits++;
@@ -1125,6 +1196,7 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   const int useful = NB == 1 ? (a.n_tiles + WT_WARPS - 1) / WT_WARPS : a.n_tiles;
   if (gs > useful) gs = useful;  // never more CTAs than tiles (warp-tile kernel: than tiles / warps per CTA)
   if (gs > G) gs = G;
+  if (NB == 1 && gs > WT_WARPS * 32) gs = WT_WARPS * 32;  // the group's slice counts are scanned by one CTA
   if (gs < 1) gs = 1;
   int n_groups = G / gs;
   if (n_groups > a.n_fields) n_groups = a.n_fields;
@@ -1138,9 +1210,11 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   const int grid = gs * n_groups;
   if constexpr (NB == 1) {
     void *lp;
-    hpp_status s = hpp_scratch(c, 4, sizeof(uint32_t) * (size_t)grid * a.n_tiles, &lp);
+    const size_t lists_b = ((sizeof(uint32_t) * (size_t)grid * a.n_tiles) + 255) & ~(size_t)255;
+    hpp_status s = hpp_scratch(c, 4, lists_b + sizeof(uint32_t) * 4 * (size_t)grid + 256, &lp);
     if (s != HPP_OK) return s;
     a.lists = (uint32_t *)lp;
+    a.sched = (uint32_t *)((uint8_t *)lp + lists_b);
   }
   void *params[] = {&a};
   if (solo)
