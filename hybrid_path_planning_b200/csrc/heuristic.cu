@@ -312,9 +312,31 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     }
     __syncwarp();
   }
-  // sparse rows: two cells per lane and iteration (independent evaluations overlap their latencies)
+  // sparse rows: two cells per lane and iteration (independent evaluations overlap their latencies); a thin front
+  // (at most one needed cell per row) takes the single-cell form, which is the shorter dependency chain
   while (__any_sync(FULL, st.need != 0)) {
     HPP_COUNT(st.c_sparse++;)
+    if (!__any_sync(FULL, (st.need & (st.need - 1)) != 0)) {
+      const bool on = st.need != 0;
+      const int x = on ? __ffs(st.need) - 1 : 0;
+      st.need = 0;
+      const int e = ebase + lane * S + x;
+      const double c0 = cs[e];
+      uint32_t nm;
+      const double b = eval_cell<VARIANT, S>(cs, cl, e, (st.nearm >> x) & 1u, wt, nm);
+      if (on && b < c0) {
+        cs[e] = b;
+        st.dirty = 1;
+        if (b < bound) {
+          add_push(ps, x, nm);
+          st.defer &= ~(1u << x);
+        } else {
+          st.defer |= 1u << x;
+        }
+      }
+      __syncwarp();
+      break;
+    }
     const bool on0 = st.need != 0;
     const int x0 = on0 ? __ffs(st.need) - 1 : 0;
     st.need &= st.need - 1;
