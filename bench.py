@@ -3,7 +3,7 @@
 
 Workload at N=1 (config.workload = "cfg3"): BASELINE.json configs[2], the configuration the north_star's target is
 quoted on -- "holonomic heuristic plus distance-layer EDT on a synthetic 4096x4096 random-obstacle grid".
-One step = one pass of the hot path over one map message and a batch of F queries on it (--fields, default 128; the
+One step = one pass of the hot path over one map message and a batch of F queries on it (--fields, default 148 = one per SM; the
 reference arm runs the same kind of batch, one field per host core):  K1 (per-cell tables + obstacle/distance layers of the
 occupancy, what the reference's Grid_map constructor does per map message) + K3a (the RS holonomic-with-obstacles
 heuristic field of each query's goal, what HybridAstar::run does first).  value = F x 4096^2 cells x steps / device
@@ -456,7 +456,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=4096)
-    ap.add_argument("--fields", type=int, default=128, help="goal fields (queries) per step")
+    ap.add_argument("--fields", type=int, default=148, help="goal fields (queries) per step; default = one per SM of a B200")
     ap.add_argument("--ref-cores", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

@@ -716,12 +716,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // per round), but a tile is a single 32x32 block solved by ONE warp with no block-level barrier at all: the 16 warps
 // of a CTA pull tiles of the round's schedule from a shared counter and never wait for each other inside a round.
 // This is the throughput configuration: with several fields in flight every warp of the GPU stays busy.
-#ifndef HPP_WT_WARPS
-#define HPP_WT_WARPS 16
-#endif
-constexpr int WT_WARPS = HPP_WT_WARPS;  // 20 also fits (96 registers, 207 KB shared)
+// Warps (= tiles in flight) per CTA: 16 (123 registers) is the latency configuration; 20 (96 registers, 207 KB of
+// shared memory) gives +6 % throughput when every field has its own CTA -- RS only, the Dubins tiles also hold the
+// class bytes and do not fit 20 times.
 
-template <int VARIANT>
+template <int VARIANT, int WT_WARPS>
 __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<1>;
   constexpr int T = C::T, S = C::S, ROWS = C::ROWS, THREADS = WT_WARPS * 32;
@@ -1194,12 +1193,16 @@ double env_double(const char *name, double dflt) {
 template <int NB, int VARIANT>
 hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   using C = tile_cfg<NB>;
-  constexpr int threads = NB == 1 ? WT_WARPS * 32 : C::THREADS;
+  // warp-tile kernel: 20 warps per CTA when every field gets its own CTA (throughput), else 16 (latency)
+  const bool many = NB == 1 && VARIANT == HPP_VARIANT_RS && ctas_per_field_hint <= 1 && a.n_fields >= c->sm_count / 2;
+  const int WT_WARPS = many ? 20 : 16;
+  const int threads = NB == 1 ? WT_WARPS * 32 : C::THREADS;
   size_t smem;
   const void *kern;
   if constexpr (NB == 1) {
     smem = (size_t)WT_WARPS * C::ROWS * C::S * (sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? 1 : 0)) + 16;
-    kern = (const void *)heur_warp_kernel<VARIANT>;
+    kern = many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
+                : (const void *)heur_warp_kernel<VARIANT, 16>;
   } else {
     smem = heur_smem_bytes<NB>(VARIANT);
     kern = (const void *)heur_persist_kernel<NB, VARIANT>;
