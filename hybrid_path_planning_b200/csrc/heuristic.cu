@@ -78,6 +78,7 @@ struct heur_args {
   uint32_t *stats;                 // [n_fields][4]: rounds, tile visits, windows, sweeps of CTA rank 0
   uint32_t *lists;                 // warp-tile kernel: [grid][n_tiles] schedule of the round
   uint32_t *sched;                 // warp-tile kernel: [n_groups][4 * group_size] slice counts + minima of a round
+  uint32_t *aq;                    // async kernel: control words + tile states + ring queue (see heur_async_kernel)
   unsigned long long *prof;        // optional [grid][8] cycle counters (HPP_HEUR_DEBUG): schedule, stage, solve,
                                    // write-back, barrier wait, tiles, phases, longest single solve
   double delta;                    // width of the global cost window
@@ -711,6 +712,168 @@ __device__ __forceinline__ void tma_load_row(uint32_t dst, const void *src, uint
 // orders this thread's generic-proxy accesses (shared and global) with async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// ---------------------------------------------------------------- one tile visit by one warp
+// Stages tile `tile` (+ halo) of the field `cost` into the warp's shared-memory slot, relaxes it to its fixed point under
+// `bound` (sub-windows of delta_in), writes the changed rows and the deferred masks back.  af = ring sides to
+// re-evaluate (DIR_* flags posted by the neighbours).  Returns the cheapest cost left deferred (bit pattern, INF_BITS
+// if none); *wc.s_out holds the DIR_* flags of the neighbour tiles whose halo this visit changed.
+struct warp_ctx {
+  double *cs_nv;
+  uint8_t *cl_nv;
+  uint32_t *s_out;
+  uint32_t mbar, parity;
+  bool tma_ok;
+};
+
+template <int VARIANT>
+__device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a, double *__restrict__ cost,
+                                                              uint32_t *__restrict__ dmask, int tile, uint32_t af,
+                                                              double bound, const eval_w &wt, warp_ctx &wc, int lane) {
+  using C = tile_cfg<1>;
+  constexpr int T = C::T, S = C::S, ROWS = C::ROWS;
+  const int W = a.W, H = a.H;
+  double *cs_nv = wc.cs_nv;
+  uint8_t *cl_nv = wc.cl_nv;
+  volatile double *cs = cs_nv;
+  const volatile uint8_t *cl = cl_nv;
+  const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  const int x0 = tx * T, y0 = ty * T;
+    // ---- stage the tile + halo.  TMA path: one bulk copy per row (columns x0-2 .. x0+33, 16-byte aligned),
+    // all rows in flight at once, completion counted on the warp's mbarrier.  Cells outside the map keep the
+    // initial value: edge tiles are pre-filled before the copies land.
+    if (wc.tma_ok) {
+      const int cx0 = x0 - 2 < 0 ? 0 : x0 - 2, cx1 = x0 + T + 2 > W ? W : x0 + T + 2;
+      const int ry0 = y0 - 1 < 0 ? 0 : y0 - 1, ry1 = y0 + T + 1 > H ? H : y0 + T + 1;  // valid global rows
+      const bool edge = x0 == 0 || x0 + T + 2 > W || y0 == 0 || y0 + T + 1 > H;
+      if (edge) {
+        for (int i = lane; i < ROWS * S; i += 32) cs_nv[i] = wt.init;
+        __syncwarp();
+      }
+      fence_proxy_async();  // my generic-proxy accesses to this buffer before the async-proxy writes
+      const uint32_t row_bytes = (uint32_t)(cx1 - cx0) * 8u;
+      if (lane == 0) mbar_expect_tx(wc.mbar, row_bytes * (uint32_t)(ry1 - ry0));
+      __syncwarp();
+      for (int gy = ry0 + lane; gy < ry1; gy += 32) {
+        const int r = gy - (y0 - 1);
+        tma_load_row(smem_u32(cs_nv + r * S + (cx0 - (x0 - 2))), cost + (size_t)gy * W + cx0, row_bytes, wc.mbar);
+      }
+      if (VARIANT == HPP_VARIANT_DUBINS) {
+        for (int r = 0; r < ROWS; r++) {
+          const int gy = y0 - 1 + r;
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const int c = lane + 32 * k, gx = x0 - 1 + c;
+            if (c < T + 2) {
+              uint8_t k8 = CLS_BLOCKED | 9;
+              if (gy >= 0 && gy < H && gx >= 0 && gx < W) k8 = a.cls[(size_t)gy * W + gx];
+              cl_nv[r * S + c + 1] = k8;
+            }
+          }
+        }
+      }
+      mbar_wait(wc.mbar, wc.parity);
+      wc.parity ^= 1u;
+    } else {
+      for (int r = 0; r < ROWS; r++) {
+        const int gy = y0 - 1 + r;
+        const bool rin = gy >= 0 && gy < H;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int c = lane + 32 * k;
+          if (c < T + 2) {
+            const int gx = x0 - 1 + c;
+            double v = wt.init;
+            uint8_t k8 = CLS_BLOCKED | 9;
+            if (rin && gx >= 0 && gx < W) {
+              v = __ldcg(cost + (size_t)gy * W + gx);
+              if (VARIANT == HPP_VARIANT_DUBINS) k8 = a.cls[(size_t)gy * W + gx];
+            }
+            cs_nv[r * S + c + 1] = v;
+            if (VARIANT == HPP_VARIANT_DUBINS) cl_nv[r * S + c + 1] = k8;
+          }
+        }
+      }
+    }
+    if (lane == 0) (*wc.s_out) = 0;
+    blk_state st;
+    {
+      const int gy = y0 + lane, wx = x0 >> 5;
+      uint32_t ob = 0xffffffffu, nb = 0;
+      if (gy < H && wx < a.pitch) {
+        ob = a.occ_bits[(size_t)gy * a.pitch + wx];
+        nb = a.near_bits[(size_t)gy * a.pitch + wx];
+        const int rem = W - (wx << 5);
+        if (rem < 32) ob |= ~((1u << rem) - 1u);
+      }
+      st.freem = ~ob;
+      st.nearm = nb;
+      st.need = 0;
+      st.dirty = 0;
+      st.posted = 0;
+      st.c_heavy = st.c_sparse = st.c_on = st.c_imp = st.c_sweeps = 0;
+      st.defer = __ldcg(dmask + (size_t)tile * 32 + lane);
+    }
+    __syncwarp();
+    if (af) {
+      if ((af & DIR_N) && lane == 0) st.need |= st.freem;
+      if ((af & DIR_S) && lane == 31) st.need |= st.freem;
+      if (af & DIR_W) st.need |= st.freem & 1u;
+      if (af & DIR_E) st.need |= st.freem & 0x80000000u;
+      if ((af & DIR_NW) && lane == 0) st.need |= st.freem & 1u;
+      if ((af & DIR_NE) && lane == 0) st.need |= st.freem & 0x80000000u;
+      if ((af & DIR_SW) && lane == 31) st.need |= st.freem & 1u;
+      if ((af & DIR_SE) && lane == 31) st.need |= st.freem & 0x80000000u;
+    }
+    // relax under the bound in sub-windows (see heur_persist_kernel); everything is warp-local
+    const int ebase = S + 2;
+    double lb = 0.0;
+    unsigned long long left = INF_BITS;
+    for (;;) {
+      while (sweep<1, VARIANT>(cs, cl, nullptr, wc.s_out, st, 0, 0, 0, lane, lb, wt)) {
+      }
+      unsigned long long mn = INF_BITS;
+      for (uint32_t m = st.defer; m; m &= m - 1) {
+        const int x = __ffs(m) - 1;
+        const unsigned long long v = (unsigned long long)__double_as_longlong(cs[ebase + lane * S + x]);
+        mn = v < mn ? v : mn;
+      }
+      for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, mn, d);
+        mn = o < mn ? o : mn;
+      }
+      left = mn;
+      const double gm = __longlong_as_double((long long)mn);
+      if (mn == INF_BITS || !(gm < bound)) break;
+      lb = gm + a.delta_in;
+      if (lb > bound) lb = bound;
+      uint32_t rel = 0;
+      push3 ps = {0ull, 0ull, 0ull};
+      for (uint32_t m = st.defer; m; m &= m - 1) {
+        const int x = __ffs(m) - 1;
+        if (cs[ebase + lane * S + x] < lb) {
+          rel |= 1u << x;
+          add_push(ps, x, 0xffu);
+        }
+      }
+      st.defer &= ~rel;
+      __syncwarp();
+      if (__any_sync(FULL, rel != 0)) propagate<1>(ps, st, nullptr, wc.s_out, 0, 0, lane);
+    }
+    // write back
+    __stcg(dmask + (size_t)tile * 32 + lane, st.defer);
+    uint32_t dr = __ballot_sync(FULL, st.dirty != 0);
+    const int gx = x0 + lane;
+    while (dr) {
+      const int r = __ffs(dr) - 1;
+      dr &= dr - 1;
+      const int gy = y0 + r;
+      if (gx < W && gy < H) __stcg(cost + (size_t)gy * W + gx, cs[ebase + r * S + lane]);
+    }
+    fence_proxy_async();  // the rows just stored are read by other warps' bulk copies (async proxy) later
+    __syncwarp();
+    return left;
+}
+
 // ---------------------------------------------------------------- the warp-tile kernel (T = 32: one warp per tile)
 // Same scheduling protocol as heur_persist_kernel (cost windows, activity flags, deferred minima, one group barrier
 // per round), but a tile is a single 32x32 block solved by ONE warp with no block-level barrier at all: the 16 warps
@@ -723,7 +886,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int VARIANT, int WT_WARPS>
 __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<1>;
-  constexpr int T = C::T, S = C::S, ROWS = C::ROWS, THREADS = WT_WARPS * 32;
+  constexpr int S = C::S, ROWS = C::ROWS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *cs_all = (double *)smem_raw;                                  // WT_WARPS x ROWS*S
   uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);          // WT_WARPS x ROWS*S (Dubins only)
@@ -748,17 +911,17 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   wt.init = a.wt.init;
   wt.rs = s_rs;
   wt.db = s_db;
-  double *cs_nv = cs_all + wid * ROWS * S;
-  uint8_t *cl_nv = cl_all + wid * ROWS * S;
-  volatile double *cs = cs_nv;
-  const volatile uint8_t *cl = cl_nv;
-  const uint32_t mbar = smem_u32(&s_mbar[wid]);
-  uint32_t mbar_parity = 0;
-  if (lane == 0) mbar_init(mbar, 1);
+  warp_ctx wc;
+  wc.cs_nv = cs_all + wid * ROWS * S;
+  wc.cl_nv = cl_all + wid * ROWS * S;
+  wc.s_out = &s_outw[wid];
+  wc.mbar = smem_u32(&s_mbar[wid]);
+  wc.parity = 0;
+  if (lane == 0) mbar_init(wc.mbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   // rows can be bulk-copied when every row start (x0 - 2 doubles) is 16-byte aligned: W even and an aligned base
-  const bool tma_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.cost_all) & 15) == 0);
+  wc.tma_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.cost_all) & 15) == 0);
 
   for (int field = group; field < a.n_fields; field += a.n_groups) {
     double *cost = a.cost_all + (size_t)field * n;
@@ -926,148 +1089,12 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
           tile = __shfl_sync(FULL, tl, 0);
         }
         const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-        const int x0 = tx * T, y0 = ty * T;
         visits++;
         PF_MARK(0);
-        // ---- stage the tile + halo.  TMA path: one bulk copy per row (columns x0-2 .. x0+33, 16-byte aligned),
-        // all rows in flight at once, completion counted on the warp's mbarrier.  Cells outside the map keep the
-        // initial value: edge tiles are pre-filled before the copies land.
-        if (tma_ok) {
-          const int cx0 = x0 - 2 < 0 ? 0 : x0 - 2, cx1 = x0 + T + 2 > W ? W : x0 + T + 2;
-          const int ry0 = y0 - 1 < 0 ? 0 : y0 - 1, ry1 = y0 + T + 1 > H ? H : y0 + T + 1;  // valid global rows
-          const bool edge = x0 == 0 || x0 + T + 2 > W || y0 == 0 || y0 + T + 1 > H;
-          if (edge) {
-            for (int i = lane; i < ROWS * S; i += 32) cs_nv[i] = wt.init;
-            __syncwarp();
-          }
-          fence_proxy_async();  // my generic-proxy accesses to this buffer before the async-proxy writes
-          const uint32_t row_bytes = (uint32_t)(cx1 - cx0) * 8u;
-          if (lane == 0) mbar_expect_tx(mbar, row_bytes * (uint32_t)(ry1 - ry0));
-          __syncwarp();
-          for (int gy = ry0 + lane; gy < ry1; gy += 32) {
-            const int r = gy - (y0 - 1);
-            tma_load_row(smem_u32(cs_nv + r * S + (cx0 - (x0 - 2))), cost + (size_t)gy * W + cx0, row_bytes, mbar);
-          }
-          if (VARIANT == HPP_VARIANT_DUBINS) {
-            for (int r = 0; r < ROWS; r++) {
-              const int gy = y0 - 1 + r;
-#pragma unroll
-              for (int k = 0; k < 2; k++) {
-                const int c = lane + 32 * k, gx = x0 - 1 + c;
-                if (c < T + 2) {
-                  uint8_t k8 = CLS_BLOCKED | 9;
-                  if (gy >= 0 && gy < H && gx >= 0 && gx < W) k8 = a.cls[(size_t)gy * W + gx];
-                  cl_nv[r * S + c + 1] = k8;
-                }
-              }
-            }
-          }
-          mbar_wait(mbar, mbar_parity);
-          mbar_parity ^= 1u;
-        } else {
-          for (int r = 0; r < ROWS; r++) {
-            const int gy = y0 - 1 + r;
-            const bool rin = gy >= 0 && gy < H;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-              const int c = lane + 32 * k;
-              if (c < T + 2) {
-                const int gx = x0 - 1 + c;
-                double v = wt.init;
-                uint8_t k8 = CLS_BLOCKED | 9;
-                if (rin && gx >= 0 && gx < W) {
-                  v = __ldcg(cost + (size_t)gy * W + gx);
-                  if (VARIANT == HPP_VARIANT_DUBINS) k8 = a.cls[(size_t)gy * W + gx];
-                }
-                cs_nv[r * S + c + 1] = v;
-                if (VARIANT == HPP_VARIANT_DUBINS) cl_nv[r * S + c + 1] = k8;
-              }
-            }
-          }
-        }
-        if (lane == 0) s_outw[wid] = 0;
-        blk_state st;
-        {
-          const int gy = y0 + lane, wx = x0 >> 5;
-          uint32_t ob = 0xffffffffu, nb = 0;
-          if (gy < H && wx < a.pitch) {
-            ob = a.occ_bits[(size_t)gy * a.pitch + wx];
-            nb = a.near_bits[(size_t)gy * a.pitch + wx];
-            const int rem = W - (wx << 5);
-            if (rem < 32) ob |= ~((1u << rem) - 1u);
-          }
-          st.freem = ~ob;
-          st.nearm = nb;
-          st.need = 0;
-          st.dirty = 0;
-          st.posted = 0;
-          st.c_heavy = st.c_sparse = st.c_on = st.c_imp = st.c_sweeps = 0;
-          st.defer = __ldcg(dmask + (size_t)tile * 32 + lane);
-        }
         const uint32_t af = __ldcg(act_cur + tile);
-        __syncwarp();
-        PF_MARK(1);
-        if (af) {
-          if ((af & DIR_N) && lane == 0) st.need |= st.freem;
-          if ((af & DIR_S) && lane == 31) st.need |= st.freem;
-          if (af & DIR_W) st.need |= st.freem & 1u;
-          if (af & DIR_E) st.need |= st.freem & 0x80000000u;
-          if ((af & DIR_NW) && lane == 0) st.need |= st.freem & 1u;
-          if ((af & DIR_NE) && lane == 0) st.need |= st.freem & 0x80000000u;
-          if ((af & DIR_SW) && lane == 31) st.need |= st.freem & 1u;
-          if ((af & DIR_SE) && lane == 31) st.need |= st.freem & 0x80000000u;
-        }
-        // relax under the bound in sub-windows (see heur_persist_kernel); everything is warp-local
-        const int ebase = S + 2;
-        double lb = 0.0;
-        unsigned long long left = INF_BITS;
-        for (;;) {
-          while (sweep<1, VARIANT>(cs, cl, nullptr, &s_outw[wid], st, 0, 0, 0, lane, lb, wt)) {
-          }
-          unsigned long long mn = INF_BITS;
-          for (uint32_t m = st.defer; m; m &= m - 1) {
-            const int x = __ffs(m) - 1;
-            const unsigned long long v = (unsigned long long)__double_as_longlong(cs[ebase + lane * S + x]);
-            mn = v < mn ? v : mn;
-          }
-          for (int d = 16; d; d >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(FULL, mn, d);
-            mn = o < mn ? o : mn;
-          }
-          left = mn;
-          const double gm = __longlong_as_double((long long)mn);
-          if (mn == INF_BITS || !(gm < bound)) break;
-          lb = gm + a.delta_in;
-          if (lb > bound) lb = bound;
-          uint32_t rel = 0;
-          push3 ps = {0ull, 0ull, 0ull};
-          for (uint32_t m = st.defer; m; m &= m - 1) {
-            const int x = __ffs(m) - 1;
-            if (cs[ebase + lane * S + x] < lb) {
-              rel |= 1u << x;
-              add_push(ps, x, 0xffu);
-            }
-          }
-          st.defer &= ~rel;
-          __syncwarp();
-          if (__any_sync(FULL, rel != 0)) propagate<1>(ps, st, nullptr, &s_outw[wid], 0, 0, lane);
-        }
+        const unsigned long long left = warp_visit_tile<VARIANT>(a, cost, dmask, tile, af, bound, wt, wc, lane);
         pf[5]++;
-        pf[6] += st.c_sweeps;
-        pf[7] += st.c_heavy + st.c_sparse;
         PF_MARK(2);
-        // write back
-        __stcg(dmask + (size_t)tile * 32 + lane, st.defer);
-        uint32_t dr = __ballot_sync(FULL, st.dirty != 0);
-        const int gx = x0 + lane;
-        while (dr) {
-          const int r = __ffs(dr) - 1;
-          dr &= dr - 1;
-          const int gy = y0 + r;
-          if (gx < W && gy < H) __stcg(cost + (size_t)gy * W + gx, cs[ebase + r * S + lane]);
-        }
-        fence_proxy_async();  // the rows just stored are read by other warps' bulk copies (async proxy) later
-        __syncwarp();
         if (lane == 0) {
           __stcg(pm_next + tile, left);
           const uint32_t o = ((volatile uint32_t *)s_outw)[wid];
@@ -1105,6 +1132,226 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   }
 }
 
+// ---------------------------------------------------------------- the asynchronous kernel (one field, all SMs)
+// Latency configuration for a lone field.  Same tile visits as heur_warp_kernel, but no rounds: every warp of the GPU
+// pops tiles from one ring queue and pushes the neighbour tiles whose halo it changed, so nobody waits for the slowest
+// tile of a round.  Only the cost window still needs agreement: a counter of tiles that are queued or being visited
+// reaches zero exactly when the window is exhausted; the warp that brings it to zero scans the deferred minima, opens
+// the next window and queues the tiles that fall into it (or raises `done`).
+//   tile state word: DIR_* flags (ring sides to re-evaluate) | AQ_QUEUED | AQ_BUSY
+//     post(t, dir):  old = atomicOr(state[t], dir | QUEUED);  neither QUEUED nor BUSY before -> pending++, push(t)
+//     pop:           state[t] <- BUSY (one CAS: takes the flags, clears QUEUED)
+//     release:       old = atomicAnd(state[t], ~BUSY);  QUEUED set meanwhile -> push(t), else pending--
+// A tile is in the queue at most once, so a ring of >= n_tiles slots cannot overflow.  Launched cooperatively (all
+// warps resident: a popper may wait for the pusher of its slot).
+constexpr uint32_t AQ_QUEUED = 256u, AQ_BUSY = 512u, AQ_EMPTY = 0xffffffffu;
+enum { AQ_HEAD = 0, AQ_TAIL = 1, AQ_PENDING = 2, AQ_DONE = 3, AQ_WINDOWS = 4, AQ_VISITS = 5, AQ_BOUND = 6 /* 2 words */,
+       AQ_HDR = 32 };
+
+__device__ __forceinline__ void aq_push(uint32_t *ctl, uint32_t *ring, uint32_t mask, uint32_t tile) {
+  const uint32_t slot = atomicAdd(ctl + AQ_TAIL, 1u) & mask;
+  __stcg(ring + slot, tile);
+}
+
+template <int VARIANT, int WT_WARPS>
+__global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_async_kernel(const __grid_constant__ heur_args a) {
+  using C = tile_cfg<1>;
+  constexpr int S = C::S, ROWS = C::ROWS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *cs_all = (double *)smem_raw;
+  uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);
+  __shared__ uint32_t s_outw[WT_WARPS];
+  __shared__ double s_db[20];
+  __shared__ __align__(16) double2 s_rs[2];
+  __shared__ __align__(8) unsigned long long s_mbar[WT_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int W = a.W, n_tiles = a.n_tiles;
+  if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
+  if (tid < 2) s_rs[tid] = make_double2(a.wt.rs[tid][0], a.wt.rs[tid][1]);
+  eval_w wt;
+  wt.c0 = a.wt.rs[0][0];
+  wt.d0 = a.wt.rs[0][1];
+  wt.init = a.wt.init;
+  wt.rs = s_rs;
+  wt.db = s_db;
+  warp_ctx wc;
+  wc.cs_nv = cs_all + wid * ROWS * S;
+  wc.cl_nv = cl_all + wid * ROWS * S;
+  wc.s_out = &s_outw[wid];
+  wc.mbar = smem_u32(&s_mbar[wid]);
+  wc.parity = 0;
+  if (lane == 0) mbar_init(wc.mbar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  wc.tma_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.cost_all) & 15) == 0);
+
+  uint32_t *ctl = a.aq;                     // control words
+  uint32_t *state = a.aq + AQ_HDR;          // [n_tiles]
+  uint32_t ring_size = 2;
+  while (ring_size < 2u * (uint32_t)n_tiles) ring_size <<= 1;  // twice the tiles: a slot is never reused while claimed
+  const uint32_t mask = ring_size - 1;
+  uint32_t *ring = state + n_tiles;         // [ring_size], AQ_EMPTY when free
+  unsigned long long *pmin = a.pmin;        // [n_tiles] (buffer 0 of the BSP layout)
+  double *cost = a.cost_all;
+  uint32_t *dmask = a.dmask;
+  volatile uint32_t *vctl = ctl;
+  uint32_t visits = 0;
+  unsigned idle = 0;
+
+  // CTA-local staging of popped tiles: only one warp per CTA at a time talks to the global queue (a storm of idle
+  // warps polling one cache line would slow every L2 access of the working warps); it claims up to AQ_FETCH tiles,
+  // keeps one and leaves the rest in a small shared-memory queue for the other idle warps of the CTA.
+  constexpr uint32_t AQ_FETCH = 4, LQ = 32;
+  __shared__ uint32_t s_lq[LQ];
+  __shared__ uint32_t s_lq_head, s_lq_tail, s_fetch_lock, s_done;
+  if (tid == 0) {
+    s_lq_head = 0;
+    s_lq_tail = 0;
+    s_fetch_lock = 0;
+    s_done = 0;
+  }
+  __syncthreads();
+  for (;;) {
+    // ---- pop
+    int tile = -1;
+    if (lane == 0) {
+      const uint32_t lh = *(volatile uint32_t *)&s_lq_head;
+      if (lh != *(volatile uint32_t *)&s_lq_tail) {
+        if (atomicCAS(&s_lq_head, lh, lh + 1u) == lh) tile = (int)((volatile uint32_t *)s_lq)[lh % LQ];
+      } else if (atomicCAS(&s_fetch_lock, 0u, 1u) == 0u) {
+        const uint32_t h = vctl[AQ_HEAD], t = vctl[AQ_TAIL];
+        uint32_t k = t - h;
+        if (k > AQ_FETCH) k = AQ_FETCH;
+        if (k != 0 && atomicCAS(ctl + AQ_HEAD, h, h + k) == h) {
+          for (uint32_t i = 0; i < k; i++) {
+            volatile uint32_t *slot = ring + ((h + i) & mask);
+            uint32_t v;
+            while ((v = *slot) == AQ_EMPTY) __nanosleep(20);  // the pusher took this slot and is about to write it
+            *slot = AQ_EMPTY;
+            if (i == 0) {
+              tile = (int)v;
+            } else {
+              const uint32_t lt = *(volatile uint32_t *)&s_lq_tail;
+              ((volatile uint32_t *)s_lq)[lt % LQ] = v;
+              __threadfence_block();
+              *(volatile uint32_t *)&s_lq_tail = lt + 1u;
+            }
+          }
+        } else if (k == 0 && vctl[AQ_DONE]) {
+          *(volatile uint32_t *)&s_done = 1u;
+        }
+        __threadfence_block();
+        atomicExch(&s_fetch_lock, 0u);
+      }
+    }
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile < 0) {
+      if (*(volatile uint32_t *)&s_done) break;
+      __nanosleep(idle < 8 ? 100 : 400);
+      idle++;
+      continue;
+    }
+    idle = 0;
+    // ---- take the tile: flags -> af, state <- BUSY
+    uint32_t af = 0;
+    if (lane == 0) {
+      uint32_t old = *(volatile uint32_t *)(state + tile);
+      for (;;) {
+        const uint32_t seen = atomicCAS(state + tile, old, AQ_BUSY);
+        if (seen == old) break;
+        old = seen;
+      }
+      af = old & 0xffu;
+      __threadfence();  // acquire: the poster's cost rows are visible before my staging reads
+    }
+    af = __shfl_sync(FULL, af, 0);
+    double bound;
+    {
+      const unsigned long long bb = *(volatile unsigned long long *)(ctl + AQ_BOUND);
+      bound = __longlong_as_double((long long)bb);
+    }
+    const unsigned long long left = warp_visit_tile<VARIANT>(a, cost, dmask, tile, af, bound, wt, wc, lane);
+    visits++;
+    // ---- publish: deferred minimum, neighbour posts, release
+    uint32_t ctrl = 0;
+    if (lane == 0) {
+      __stcg(pmin + tile, left);
+      const uint32_t o = ((volatile uint32_t *)s_outw)[wid];
+      __threadfence();  // release: my cost rows and pmin before the posts / the release below
+      if (o) {
+        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+          constexpr int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+          constexpr int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+          constexpr uint32_t facing[8] = {DIR_S, DIR_N, DIR_E, DIR_W, DIR_SE, DIR_SW, DIR_NE, DIR_NW};
+          if (o & (1u << d)) {
+            const int nx = tx + ddx[d], ny = ty + ddy[d];
+            if (nx >= 0 && nx < a.tiles_x && ny >= 0 && ny < a.tiles_y) {
+              const int nb = ny * a.tiles_x + nx;
+              const uint32_t old = atomicOr(state + nb, facing[d] | AQ_QUEUED);
+              if (!(old & (AQ_QUEUED | AQ_BUSY))) {
+                atomicAdd(ctl + AQ_PENDING, 1u);
+                aq_push(ctl, ring, mask, (uint32_t)nb);
+              }
+            }
+          }
+        }
+      }
+      const uint32_t old = atomicAnd(state + tile, ~AQ_BUSY);
+      if (old & AQ_QUEUED) aq_push(ctl, ring, mask, (uint32_t)tile);  // posted to while busy: still pending
+      else if (atomicSub(ctl + AQ_PENDING, 1u) == 1u) ctrl = 1;
+    }
+    ctrl = __shfl_sync(FULL, ctrl, 0);
+    // ---- the window is exhausted and my warp is the only one doing anything: open the next window.
+    // (a guard count keeps `pending` above zero until every tile of the new window is queued)
+    while (ctrl) {
+      if (lane == 0) atomicAdd(ctl + AQ_PENDING, 1u);
+      unsigned long long g = INF_BITS;
+#pragma unroll 4
+      for (int t = lane; t < n_tiles; t += 32) {
+        const unsigned long long pm = __ldcg(pmin + t);
+        g = pm < g ? pm : g;
+      }
+      for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, g, d);
+        g = o < g ? o : g;
+      }
+      if (g == INF_BITS) {
+        if (lane == 0) {
+          __threadfence();
+          vctl[AQ_DONE] = 1u;
+        }
+        break;
+      }
+      const double nbound = __longlong_as_double((long long)g) + a.delta;
+      if (lane == 0) {
+        *(volatile unsigned long long *)(ctl + AQ_BOUND) = (unsigned long long)__double_as_longlong(nbound);
+        __threadfence();
+        atomicAdd(ctl + AQ_WINDOWS, 1u);
+      }
+      __syncwarp();
+#pragma unroll 4
+      for (int t = lane; t < n_tiles; t += 32) {
+        const unsigned long long pm = __ldcg(pmin + t);
+        if (__longlong_as_double((long long)pm) < nbound) {
+          const uint32_t o2 = atomicOr(state + t, AQ_QUEUED);
+          if (!(o2 & (AQ_QUEUED | AQ_BUSY))) {
+            atomicAdd(ctl + AQ_PENDING, 1u);
+            aq_push(ctl, ring, mask, (uint32_t)t);
+          }
+        }
+      }
+      __syncwarp();
+      uint32_t again = 0;
+      if (lane == 0) again = atomicSub(ctl + AQ_PENDING, 1u) == 1u;  // everything queued was already finished
+      ctrl = __shfl_sync(FULL, again, 0);
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && visits) atomicAdd(ctl + AQ_VISITS, visits);
+}
+
 // ---------------------------------------------------------------- init / seed / stats
 __global__ void __launch_bounds__(256) heur_init_kernel(double *__restrict__ cost, size_t total, double init,
                                                         unsigned long long *__restrict__ pmin, size_t n_pmin) {
@@ -1129,6 +1376,22 @@ __global__ void heur_seed_kernel(double *__restrict__ cost, size_t n, size_t n_f
   const int blk = (ly / HB) * NB + lx / HB;
   dmask[((f * n_tiles + tile) * NBLK + blk) * 32 + (ly % HB)] = 1u << (lx % HB);
   pmin[f * 2 * n_tiles + tile] = 0ull;
+}
+
+// async kernel: control words, the goal tile queued, the first window open (state and ring are memset by the host)
+template <int NB>
+__global__ void heur_async_seed_kernel(uint32_t *__restrict__ aq, const int32_t *__restrict__ goal_xy, int tiles_x,
+                                       int n_tiles, double delta) {
+  constexpr int T = tile_cfg<NB>::T;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int tile = (goal_xy[1] / T) * tiles_x + goal_xy[0] / T;
+  for (int i = 0; i < AQ_HDR; i++) aq[i] = 0;
+  aq[AQ_TAIL] = 1;
+  aq[AQ_PENDING] = 1;
+  aq[AQ_WINDOWS] = 1;
+  *(unsigned long long *)(aq + AQ_BOUND) = (unsigned long long)__double_as_longlong(delta);
+  aq[AQ_HDR + tile] = AQ_QUEUED;
+  aq[AQ_HDR + n_tiles] = (uint32_t)tile;  // ring[0]
 }
 
 // reachable count / max finite cost per field
@@ -1322,11 +1585,51 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
                                                                                    a.pmin, a.dmask, tiles_x, n_tiles);
   HPP_LAUNCHED(c);
   const int hint = (int)env_double("HPP_HEUR_GROUP", 0);
-  s = (variant == HPP_VARIANT_RS) ? launch_persist<NB, HPP_VARIANT_RS>(c, a, hint)
-                                  : launch_persist<NB, HPP_VARIANT_DUBINS>(c, a, hint);
-  if (s != HPP_OK) return s;
+  // HPP_HEUR_ASYNC=1: a lone field through the asynchronous queue kernel (no rounds).  Off by default: it removes
+  // the wait for the slowest tile of a round, but visits tiles eagerly (1.7x the visits: a tile is re-visited after
+  // every neighbour instead of once per round) and ends up level with the round-based kernel (19.6 vs 18.3 ms at
+  // 4096^2, 3.9 vs 4.1 ms at 1024^2): both are bound by the chain of dependent sweeps.
+  bool use_async = false;
+  if constexpr (NB == 1)
+    use_async = n_fields == 1 && hint == 0 && n_tiles >= 4 * c->sm_count && env_double("HPP_HEUR_ASYNC", 0) != 0;
+  if (use_async) {
+    if constexpr (NB == 1) {
+      uint32_t ring = 2;
+      while (ring < 2u * (uint32_t)n_tiles) ring <<= 1;
+      const size_t aq_b = sizeof(uint32_t) * ((size_t)AQ_HDR + n_tiles + ring);
+      void *qp;
+      s = hpp_scratch(c, 4, aq_b, &qp);
+      if (s != HPP_OK) return s;
+      a.aq = (uint32_t *)qp;
+      HPP_CUDA(c, cudaMemsetAsync(a.aq, 0, sizeof(uint32_t) * ((size_t)AQ_HDR + n_tiles), c->stream));
+      HPP_CUDA(c, cudaMemsetAsync(a.aq + AQ_HDR + n_tiles, 0xff, sizeof(uint32_t) * ring, c->stream));
+      heur_async_seed_kernel<NB><<<1, 32, 0, c->stream>>>(a.aq, d_goals, tiles_x, n_tiles, a.delta);
+      HPP_LAUNCHED(c);
+      const size_t smem = (size_t)16 * C::ROWS * C::S * (sizeof(double) + (variant == HPP_VARIANT_DUBINS ? 1 : 0)) + 16;
+      const void *kern = variant == HPP_VARIANT_RS ? (const void *)heur_async_kernel<HPP_VARIANT_RS, 16>
+                                                   : (const void *)heur_async_kernel<HPP_VARIANT_DUBINS, 16>;
+      HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 16 * 32, smem));
+      if (per_sm < 1) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic kernel does not fit on an SM (%zu B shared)", smem);
+      int grid_a = c->sm_count;
+      if (grid_a * 16 > n_tiles) grid_a = (n_tiles + 15) / 16;
+      a.group_size = grid_a;
+      a.n_groups = 1;
+      void *params[] = {&a};
+      HPP_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid_a), dim3(16 * 32), params, smem, c->stream));
+      HPP_LAUNCHED(c);
+      // stats words of field 0: [0] rounds (none), [1] visits, [2] windows
+      HPP_CUDA(c, cudaMemcpyAsync(a.stats + 1, a.aq + AQ_VISITS, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+      HPP_CUDA(c, cudaMemcpyAsync(a.stats + 2, a.aq + AQ_WINDOWS, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
+  } else {
+    s = (variant == HPP_VARIANT_RS) ? launch_persist<NB, HPP_VARIANT_RS>(c, a, hint)
+                                    : launch_persist<NB, HPP_VARIANT_DUBINS>(c, a, hint);
+    if (s != HPP_OK) return s;
+  }
 
-  if (debug) {
+  if (debug && !use_async) {
     const int grid = a.group_size * a.n_groups;
     std::vector<unsigned long long> hp((size_t)grid * 8 + 8);
     HPP_CUDA(c, cudaMemcpyAsync(hp.data(), a.prof, hp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1346,12 +1649,15 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
       fprintf(stderr, "[hpp heur prof] warp totals: sweeps=%llu heavy_iter=%llu sparse_iter=%llu evals=%llu improved=%llu\n", pw[4],
               pw[0], pw[1], pw[2], pw[3]);
     }
+  }
+  if (debug) {
     uint32_t *h_stats = (uint32_t *)((uint8_t *)h_stage + goals_b);
     HPP_CUDA(c, cudaMemcpyAsync(h_stats, a.stats, n_fields * 16, cudaMemcpyDeviceToHost, c->stream));
     HPP_CUDA(c, cudaStreamSynchronize(c->stream));
     for (size_t f = 0; f < n_fields && f < 4; f++)
-      fprintf(stderr, "[hpp heur] NB=%d delta=%g groups=%d x %d CTAs, field %zu: rounds=%u visits=%u windows=%u sweeps(cta0,warp0)=%u\n",
-              NB, a.delta, a.n_groups, a.group_size, f, h_stats[4 * f], h_stats[4 * f + 1], h_stats[4 * f + 2], h_stats[4 * f + 3]);
+      fprintf(stderr, "[hpp heur] NB=%d%s delta=%g groups=%d x %d CTAs, field %zu: rounds=%u visits=%u windows=%u\n", NB,
+              use_async ? " async" : "", a.delta, a.n_groups, a.group_size, f, h_stats[4 * f], h_stats[4 * f + 1],
+              h_stats[4 * f + 2]);
   }
   if (reports) {
     uint32_t *h_stats = (uint32_t *)((uint8_t *)h_stage + goals_b);

@@ -159,3 +159,24 @@ def test_heuristic_all_tile_kernels_agree(ctx, monkeypatch):
                 got, _ = m.heuristic_rs((W // 2, H // 2), (0, 0))
                 assert bits_equal(got, want), (W, H, nb, delta)
         m.close()
+
+
+def test_heuristic_async_queue_kernel(ctx, monkeypatch):
+    """HPP_HEUR_ASYNC=1: the asynchronous tile-queue kernel (one field, no rounds) gives the same bits as the oracle"""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ, goal = cfg3_map(1024, seed=3)
+    want = O.heuristic_rs(occ, goal, (0, 0), quirks=False)[0]
+    m = hpp.Map(ctx, occ, 0.2)
+    monkeypatch.setenv("HPP_HEUR_ASYNC", "1")
+    for delta in ("256", "48"):
+        monkeypatch.setenv("HPP_HEUR_DELTA", delta)
+        got, rep = m.heuristic_rs(goal, (0, 0))
+        assert bits_equal(got, want), delta
+        assert rep.reachable == int(np.isfinite(want).sum())
+    wantd = O.heuristic_dubins(occ[:700, :900], (450, 350))
+    m2 = hpp.Map(ctx, occ[:700, :900], 0.2)
+    gotd, _ = m2.heuristic_dubins((450, 350))
+    assert bits_equal(gotd, wantd)
+    m.close()
+    m2.close()
