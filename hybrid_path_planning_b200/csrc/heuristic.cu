@@ -127,7 +127,9 @@ struct blk_state {
   uint32_t nearm;  // RS: near-obstacle cells of my row
   uint32_t dirty;  // my row changed (needs write-back)
   uint32_t posted; // I posted a border change to another warp of this CTA in this phase
-  uint32_t c_heavy, c_sparse, c_on, c_imp, c_sweeps;  // profiling counters (warp-uniform except c_on/c_imp: lane sums)
+  // counters of a visit (HPP_HEUR_COUNTERS builds): dense-row / sparse iterations, needed cells summed over the
+  // sweeps, ceil(needed / 64) summed over the sweeps (= iterations of a perfectly balanced evaluation), sweeps
+  uint32_t c_heavy, c_sparse, c_on, c_imp, c_sweeps;
 };
 
 template <int NB>
@@ -256,7 +258,7 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     }
   }
   if (!__any_sync(FULL, st.need != 0)) return false;
-  HPP_COUNT(st.c_sweeps++;)
+  HPP_COUNT(st.c_sweeps++; { const int n_ = __reduce_add_sync(FULL, __popc(st.need)); st.c_imp += (n_ + 63) >> 6; st.c_on += n_; })
   const int ebase = (by * HB + 1) * S + bx * HB + 2;  // shared index of cell (row 0, col 0) of my block
   push3 ps = {0ull, 0ull, 0ull};
   // Split the rows into "heavy" ones (evaluated one lane per column, one iteration per row) and "sparse" ones (one
@@ -284,14 +286,13 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     const uint32_t nm = __shfl_sync(FULL, st.nearm, r);
     const int e = ebase + r * S + lane;
     const bool on = (m >> lane) & 1u;
-    HPP_COUNT(st.c_heavy++; st.c_on += on;)
+    HPP_COUNT(st.c_heavy++;)
     const double c0 = cs[e];
     uint32_t nmask;
     const double best = eval_cell<VARIANT, S>(cs, cl, e, (nm >> lane) & 1u, wt, nmask);
     const bool imp = on && best < c0;
     if (imp) cs[e] = best;
     const bool low = imp && best < bound;
-    HPP_COUNT(st.c_imp += imp;)
     if (!low) nmask = 0;
     const uint32_t bimp = __ballot_sync(FULL, imp);
     const uint32_t blow = __ballot_sync(FULL, low);
@@ -344,7 +345,6 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     const bool on1 = st.need != 0;
     const int x1 = on1 ? __ffs(st.need) - 1 : 0;
     st.need &= st.need - 1;
-    HPP_COUNT(st.c_on += (on0 ? 1 : 0) + (on1 ? 1 : 0);)
     const int e0 = ebase + lane * S + x0, e1 = ebase + lane * S + x1;
     const double c0 = cs[e0], c1 = cs[e1];
     uint32_t nm0, nm1;
@@ -352,7 +352,6 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
     const double b1 = eval_cell<VARIANT, S>(cs, cl, e1, (st.nearm >> x1) & 1u, wt, nm1);
     const bool imp0 = on0 && b0 < c0, imp1 = on1 && b1 < c1;
     if (imp0) {
-      HPP_COUNT(st.c_imp++;)
       cs[e0] = b0;
       st.dirty = 1;
       if (b0 < bound) {
@@ -363,7 +362,6 @@ __device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_
       }
     }
     if (imp1) {
-      HPP_COUNT(st.c_imp++;)
       cs[e1] = b1;
       st.dirty = 1;
       if (b1 < bound) {
@@ -871,6 +869,16 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
     }
     fence_proxy_async();  // the rows just stored are read by other warps' bulk copies (async proxy) later
     __syncwarp();
+#ifdef HPP_HEUR_COUNTERS
+    if (a.prof && lane == 0) {  // warp-uniform counters of this visit (debug builds only)
+      unsigned long long *pw = a.prof + (size_t)gridDim.x * 8;
+      atomicAdd(pw + 0, (unsigned long long)st.c_heavy);
+      atomicAdd(pw + 1, (unsigned long long)st.c_sparse);
+      atomicAdd(pw + 2, (unsigned long long)st.c_on);   // needed cells summed over the sweeps
+      atomicAdd(pw + 3, (unsigned long long)st.c_imp);  // ceil(needed / 64) summed over the sweeps: ideal iterations
+      atomicAdd(pw + 4, (unsigned long long)st.c_sweeps);
+    }
+#endif
     return left;
 }
 
@@ -1646,7 +1654,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
     }
     {
       const unsigned long long *pw = hp.data() + (size_t)grid * 8;
-      fprintf(stderr, "[hpp heur prof] warp totals: sweeps=%llu heavy_iter=%llu sparse_iter=%llu evals=%llu improved=%llu\n", pw[4],
+      fprintf(stderr, "[hpp heur prof] warp totals: sweeps=%llu heavy_iter=%llu sparse_iter=%llu needed_cells=%llu ideal_iter=%llu\n", pw[4],
               pw[0], pw[1], pw[2], pw[3]);
     }
   }
