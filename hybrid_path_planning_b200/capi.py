@@ -324,6 +324,10 @@ class Map:
         self.ctx.check(self.L.hpp_expand(self.h, variant, parents.ctypes.data, len(parents), kids.ctypes.data))
         return kids
 
+    def expand_dev(self, variant, parents_dev, n, children_dev):
+        """device pointers: parents n x hpp_node, children n x n_cmd x hpp_child; enqueue only"""
+        self.ctx.check(self.L.hpp_expand_dev(self.h, variant, _ptr(parents_dev), n, _ptr(children_dev)))
+
     def _shot(self, fn, starts, goals, samples_cap):
         starts = np.ascontiguousarray(starts, NODE_DTYPE)
         goals = np.ascontiguousarray(goals, np.float64).reshape(-1, 3)
