@@ -977,8 +977,9 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
         __syncthreads();
         // pass A: count my range, minimum of the deferred costs, housekeeping (whoever scans a tile owns it)
         unsigned long long mn = INF_BITS;
-        uint32_t cnt = 0;
-        for (int t0 = r0; t0 < r1; t0 += 32) {
+        uint32_t cnt = 0, onbits = 0;  // onbits: my tiles' verdicts, kept for pass B when the range has <= 32 steps
+        const bool cached = range <= 32 * 32;
+        for (int t0 = r0, k = 0; t0 < r1; t0 += 32, k++) {
           const int t = t0 + lane;
           bool on = false;
           if (t < r1) {
@@ -989,6 +990,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
             if (!on) __stcg(pm_next + t, pm);
             __stcg(act_clr + t, 0u);
           }
+          if (cached && on) onbits |= 1u << k;
           cnt += __popc(__ballot_sync(FULL, on));
         }
         for (int d = 16; d; d >>= 1) {
@@ -1012,10 +1014,12 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
         unsigned long long g = s_gmin;
         // pass B: compact the schedulable tiles of my range (in tile order) into my list
         if (my_total != 0) {
-          for (int t0 = r0; t0 < r1; t0 += 32) {
+          for (int t0 = r0, k = 0; t0 < r1; t0 += 32, k++) {
             const int t = t0 + lane;
             bool on = false;
-            if (t < r1) {
+            if (cached) {
+              on = (onbits >> k) & 1u;
+            } else if (t < r1) {
               const uint32_t af = __ldcg(act_cur + t);
               const unsigned long long pm = __ldcg(pm_cur + t);
               on = af != 0 || __longlong_as_double((long long)pm) < bound;
