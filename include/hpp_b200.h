@@ -131,8 +131,8 @@ typedef struct {
   double max_cost;       /* largest finite cost */
   int32_t h1_progress_break; /* 0 = cannot fire, 1 = fires for certain, 2 = may fire (start reachable) */
   int32_t h2_bucket_clamp;   /* 1 = some cost >= max(5000, W+H) - 1: reference's last bucket is FIFO */
-  uint32_t rounds;       /* relaxation rounds the device ran */
-  uint32_t tile_visits;  /* tile activations summed over rounds */
+  uint32_t rounds;       /* scheduling rounds of the persistent kernel (0 for the asynchronous kernel) */
+  uint32_t tile_visits;  /* tile visits (a 32x32 tile staged, relaxed under the cost window, written back) */
 } hpp_quirk_report;
 
 hpp_status hpp_heuristic_rs(hpp_map *map, int32_t goal_x, int32_t goal_y, int32_t start_x, int32_t start_y,
@@ -140,8 +140,9 @@ hpp_status hpp_heuristic_rs(hpp_map *map, int32_t goal_x, int32_t goal_y, int32_
 hpp_status hpp_heuristic_dubins(hpp_map *map, int32_t goal_x, int32_t goal_y, double *cost,
                                 hpp_quirk_report *report /* may be NULL */);
 /* batched, device-resident: n_fields goal cells (goal_xy: n_fields x 2 int32, HOST memory), one W*H field
- * each written to cost_dev + f*W*H.  Work is enqueued and completed before return (the relaxation needs
- * host-visible convergence flags). */
+ * each written to cost_dev + f*W*H.  All fields are relaxed by ONE persistent launch (cost-window tile scheduling
+ * on the device, no host polling); the call returns after that launch has completed, so a device fault is
+ * reported here.  Many fields per call is the efficient form: every field gets its own group of CTAs. */
 hpp_status hpp_heuristic_batch_dev(hpp_map *map, int variant, const int32_t *goal_xy, size_t n_fields,
                                    double *cost_dev, hpp_quirk_report *reports /* n_fields or NULL */);
 
