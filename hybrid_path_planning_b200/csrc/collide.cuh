@@ -18,8 +18,8 @@ struct circ_consts {
 
 // grid_map::getIndexFromPosition: ((p - 0.5*len) - pos) / res, truncated after negation
 __device__ __forceinline__ void gm_index(const hpp_geom &g, double px, double py, int &i, int &j) {
-  double vx = ((px - 0.5 * g.lenx) - g.posx) / g.res;
-  double vy = ((py - 0.5 * g.leny) - g.posy) / g.res;
+  double vx = hpp_div_res(g, (px - 0.5 * g.lenx) - g.posx);
+  double vy = hpp_div_res(g, (py - 0.5 * g.leny) - g.posy);
   i = (int)(-vx);
   j = (int)(-vy);
 }
@@ -58,7 +58,7 @@ __device__ __forceinline__ int circle_hits(const hpp_geom &g, const float *__res
     const float f0 = __ldg(dist + l0), f1 = __ldg(dist + l1), f2 = __ldg(dist + l2), f3 = __ldg(dist + l3);
     double bx = cx, by = cy;
     gm_position(g, ia, ja, bx, by);
-    const double rx = (px - bx) / g.res, ry = (py - by) / g.res;
+    const double rx = hpp_div_res(g, px - bx), ry = hpp_div_res(g, py - by);
     const double fx = 1.0 - rx, fy = 1.0 - ry;
     value = (float)((double)f0 * fx * fy + (double)f1 * rx * fy + (double)f2 * fx * ry + (double)f3 * rx * ry);
   }
@@ -172,8 +172,8 @@ __device__ __forceinline__ int sat_collide_warp(const hpp_geom &g, const float *
   const double offset = 5.0;
   const double min_x = fmax(g.ox, x - offset), max_x = fmin(g.ox + g.W * g.res, x + offset);
   const double min_y = fmax(g.oy, y - offset), max_y = fmin(g.oy + g.H * g.res, y + offset);
-  const int min_i = max(0, (int)((min_y - g.oy) / g.res)), max_i = min(g.H - 1, (int)((max_y - g.oy) / g.res));
-  const int min_j = max(0, (int)((min_x - g.ox) / g.res)), max_j = min(g.W - 1, (int)((max_x - g.ox) / g.res));
+  const int min_i = max(0, (int)(hpp_div_res(g, min_y - g.oy))), max_i = min(g.H - 1, (int)(hpp_div_res(g, max_y - g.oy)));
+  const int min_j = max(0, (int)(hpp_div_res(g, min_x - g.ox))), max_j = min(g.W - 1, (int)(hpp_div_res(g, max_x - g.ox)));
   int hit = 0;
   if (max_j >= min_j) {
     const int w0 = min_j >> 5, w1 = max_j >> 5;
@@ -194,7 +194,7 @@ __device__ __forceinline__ int sat_collide_warp(const hpp_geom &g, const float *
     }
   }
   hit = __any_sync(0xffffffffu, hit);
-  const int gx = (int)((x - g.ox) / g.res), gy = (int)((y - g.oy) / g.res);
+  const int gx = (int)(hpp_div_res(g, x - g.ox)), gy = (int)(hpp_div_res(g, y - g.oy));
   const int inb = gx >= 0 && gx < g.W && gy >= 0 && gy < g.H;
   return hit || !inb;
 }

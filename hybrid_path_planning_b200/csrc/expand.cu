@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(256) expand_rs_kernel(hpp_geom g, expand_const
       ch->traj[i][0] = x;
       ch->traj[i][1] = y;
       ch->traj[i][2] = h;
-      ch->traj[i][3] = (double)(int)((x - g.ox) / g.res);  // toCellID (RS/src/HybridAstar.cpp:38-40)
-      ch->traj[i][4] = (double)(int)((y - g.oy) / g.res);
+      ch->traj[i][3] = (double)(int)(hpp_div_res(g, x - g.ox));  // toCellID (RS/src/HybridAstar.cpp:38-40)
+      ch->traj[i][4] = (double)(int)(hpp_div_res(g, y - g.oy));
       if (!hit) hit = circles_collide(g, cc, dist, x, y, h);
     }
     ch->cost = path_cost(ec, lane, nd.cost, nd.steer, nd.direction);
@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(256) expand_db_kernel(hpp_geom g, expand_const
         ch->traj[i][0] = x;
         ch->traj[i][1] = y;
         ch->traj[i][2] = h;
-        ch->traj[i][3] = (double)(int)((x - g.ox) / g.res);
-        ch->traj[i][4] = (double)(int)((y - g.oy) / g.res);
+        ch->traj[i][3] = (double)(int)(hpp_div_res(g, x - g.ox));
+        ch->traj[i][4] = (double)(int)(hpp_div_res(g, y - g.oy));
       }
       if (!hit) hit = sat_collide_warp(g, rc.rx, rc.ry, bits, pitch, x, y, h);
     }

@@ -269,6 +269,7 @@ static hpp_status map_alloc(hpp_ctx *c, uint32_t W, uint32_t H, float resolution
   m->g.H = (int)H;
   m->g.res_f = resolution;
   m->g.res = (double)resolution;
+  m->g.rcp_res = 1.0 / m->g.res;
   m->g.ox = ox;
   m->g.oy = oy;
   {  // RS/src/Grid_map.cpp:15-25 + grid_map_core setGeometry (size = round(length/res), length = size*res)
@@ -396,8 +397,8 @@ __global__ void __launch_bounds__(256) cells_kernel(const double *__restrict__ x
                                                     uint8_t *__restrict__ flags) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int cx = (int)((xy[2 * i] - g.ox) / g.res);
-  int cy = (int)((xy[2 * i + 1] - g.oy) / g.res);
+  int cx = (int)hpp_div_res(g, xy[2 * i] - g.ox);
+  int cy = (int)hpp_div_res(g, xy[2 * i + 1] - g.oy);
   bool inb = cx >= 0 && cx < g.W && cy >= 0 && cy < g.H;
   bool col = !inb || occ[(size_t)cy * g.W + cx] > 0;
   cell[2 * i] = cx;

@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
     const double *hmap = fields + (size_t)field_of_query[qi] * map_size;
     const double sx = starts[3 * q], sy = starts[3 * q + 1], sh = starts[3 * q + 2];
     const double gx = goals[3 * q], gy = goals[3 * q + 1], gh = goals[3 * q + 2];
-    const int s_cx = (int)((sx - g.ox) / g.res), s_cy = (int)((sy - g.oy) / g.res);
-    const int g_cx = (int)((gx - g.ox) / g.res), g_cy = (int)((gy - g.oy) / g.res);
+    const int s_cx = (int)(hpp_div_res(g, sx - g.ox)), s_cy = (int)(hpp_div_res(g, sy - g.oy));
+    const int g_cx = (int)(hpp_div_res(g, gx - g.ox)), g_cy = (int)(hpp_div_res(g, gy - g.oy));
     for (int i = lane; i <= pc.table_mask; i += 32) table[i] = -1;
     __syncwarp();
     int n_nodes = 0, hn = 0, iterations = 0;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
       {
         double hd = fabs(cn.h - gh);
         if (hd > PI_ASTAR) hd = fabs(hd - 2 * PI_ASTAR);
-        const int c_cx = (int)((cn.x - g.ox) / g.res), c_cy = (int)((cn.y - g.oy) / g.res);
+        const int c_cx = (int)(hpp_div_res(g, cn.x - g.ox)), c_cy = (int)(hpp_div_res(g, cn.y - g.oy));
         if (c_cx == g_cx && c_cy == g_cy && hd <= 0.05) {
           goal_node = cur;
           break;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
         const int v = table_find(table, nodes, pc.table_mask, cxs, cys, chs, sl);
         if (v >= 0 && (v & 1)) valid = 0;  // in the closed set
         else {
-          const int ccx = (int)((cxs - g.ox) / g.res), ccy = (int)((cys - g.oy) / g.res);
+          const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
           const long nidx = (long)ccy * W + ccx;
           if (VARIANT == HPP_VARIANT_RS && (nidx < 0 || nidx >= map_size)) valid = 0;  // :674-677
           else {
@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
               pos -= 1;
               double *r = out + (size_t)pos * 5;
               r[0] = nd.x; r[1] = nd.y; r[2] = nd.h;
-              r[3] = (double)(int)((nd.x - g.ox) / g.res);
-              r[4] = (double)(int)((nd.y - g.oy) / g.res);
+              r[3] = (double)(int)(hpp_div_res(g, nd.x - g.ox));
+              r[4] = (double)(int)(hpp_div_res(g, nd.y - g.oy));
             } else {
               pos -= pc.ec.sim;
               const pnode pr = nodes[nd.parent];
@@ -375,8 +375,8 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
                 vehicle_step(x, y, h, pc.ec.dir[nd.cmd], pc.ec.step, pc.ec.dtheta[nd.cmd]);
                 double *r = out + (size_t)(pos + i) * 5;
                 r[0] = x; r[1] = y; r[2] = h;
-                r[3] = (double)(int)((x - g.ox) / g.res);
-                r[4] = (double)(int)((y - g.oy) / g.res);
+                r[3] = (double)(int)(hpp_div_res(g, x - g.ox));
+                r[4] = (double)(int)(hpp_div_res(g, y - g.oy));
               }
             }
           }
