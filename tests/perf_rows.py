@@ -1,10 +1,10 @@
 """Throughput of the remaining hot-path entry points (K2 inflate, K5 SAT footprint, K6 expansion, K7/K8 shots) on the
 device, one line per kernel, next to a bounded single-core CPU sample of the oracle port.  Not the bench (bench.py
-measures the headline); this fills the per-row numbers of DESIGN.md / profiles.  usage: python tools/kernels_probe.py"""
+measures the headline); this fills the per-row numbers of DESIGN.md / profiles.  usage: python tests/perf_rows.py"""
 import os, sys, time, json
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import hybrid_path_planning_b200 as hpp
 from hybrid_path_planning_b200.capi import make_nodes
 from oracle import pyorc as O

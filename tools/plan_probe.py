@@ -4,19 +4,17 @@ import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hybrid_path_planning_b200 as hpp
-from oracle import pyorc as O
 from tests.common import parking_map, random_poses
 
 npairs = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 ctx = hpp.Context(0)
 pm = parking_map(256, seed=0)
-om = O.Map(pm, 0.2)
 cand = random_poses(20000, 256, 256, margin=3.0, seed=100)
-free = cand[:6000][O.collide_circles(om, cand[:6000]) == 0]
+m = hpp.Map(ctx, pm, 0.2)
+free = cand[:6000][m.collide_circles(cand[:6000]) == 0]      # device verdicts
 reps = (2 * npairs + len(free) - 1) // len(free)
 free = np.concatenate([free] * max(1, reps))[:2 * npairs]
 starts, goals = free[:npairs], free[npairs:2 * npairs]
-m = hpp.Map(ctx, pm, 0.2)
 m.plan_batch(hpp.VARIANT_RS, starts[:8], goals[:8])
 for rep in range(2):
     t0 = time.perf_counter(); plans, _ = m.plan_batch(hpp.VARIANT_RS, starts, goals); t1 = time.perf_counter()
