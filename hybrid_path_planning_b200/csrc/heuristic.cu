@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   double *cs_all = (double *)smem_raw;                                  // WT_WARPS x ROWS*S
   uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);          // WT_WARPS x ROWS*S (Dubins only)
   __shared__ unsigned long long s_gmin;
-  __shared__ uint32_t s_mine, s_next, s_warp_cnt[32], s_outw[WT_WARPS], s_pref[WT_WARPS * 32];
+  __shared__ uint32_t s_mine, s_next, s_lnext, s_warp_cnt[32], s_outw[WT_WARPS], s_pref[WT_WARPS * 32];
   __shared__ double s_db[20];
   __shared__ __align__(8) unsigned long long s_mbar[WT_WARPS];  // one TMA completion barrier per warp
 
@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   const int group = blockIdx.x / a.group_size, grank = blockIdx.x % a.group_size;
   if (group >= a.n_groups) return;
   uint32_t *bar = a.bar + group * 32;
-  uint32_t *my_list = a.lists + (size_t)blockIdx.x * a.n_tiles;
+  uint32_t *my_list = a.lists + (size_t)blockIdx.x * 2 * a.n_tiles;  // two lists (current / next round) per CTA
   const int W = a.W, H = a.H, n_tiles = a.n_tiles;
   const size_t n = (size_t)W * H;
   if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
@@ -947,6 +947,95 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
     tk = now_;                                \
   }
 
+    if (a.group_size == 1) {
+      // ---- one CTA owns the whole field: nobody else reads its tables, so the schedule of a round is simply the list
+      // of tiles that were posted to during the previous round (a post appends the tile when it sets the first
+      // flag), and the tile table is only scanned when that list runs empty and the cost window has to move.
+      uint32_t *lcur = my_list, *lnext = my_list + n_tiles;
+      uint32_t *acur = act, *anext = act + n_tiles;
+      if (tid == 0) s_mine = 0;
+      __syncthreads();
+      for (;;) {
+        uint32_t ncur = s_mine;
+        __syncthreads();
+        if (ncur == 0) {
+          if (tid == 0) s_gmin = INF_BITS;
+          __syncthreads();
+          unsigned long long mn = INF_BITS;
+          for (int t = tid; t < n_tiles; t += WT_WARPS * 32) {
+            const unsigned long long pm = __ldcg(pmin + t);
+            mn = pm < mn ? pm : mn;
+          }
+          for (int d = 16; d; d >>= 1) {
+            const unsigned long long o = __shfl_down_sync(FULL, mn, d);
+            mn = o < mn ? o : mn;
+          }
+          if (lane == 0 && mn != INF_BITS) atomicMin(&s_gmin, mn);
+          __syncthreads();
+          const unsigned long long g = s_gmin;
+          if (g == INF_BITS) break;  // nothing posted, nothing deferred: fixed point reached
+          bound = __longlong_as_double((long long)g) + a.delta;
+          windows++;
+          for (int t = tid; t < n_tiles; t += WT_WARPS * 32)
+            if (__longlong_as_double((long long)__ldcg(pmin + t)) < bound) lcur[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
+          __syncthreads();
+          ncur = s_mine;
+          __syncthreads();
+        }
+        rounds++;
+        if (tid == 0) {
+          s_next = 0;
+          s_lnext = 0;
+        }
+        __syncthreads();
+        PF_MARK(0);
+        for (;;) {
+          uint32_t i = 0;
+          if (lane == 0) i = atomicAdd(&s_next, 1u);
+          i = __shfl_sync(FULL, i, 0);
+          if (i >= ncur) break;
+          const int tile = (int)__ldcg(lcur + i);
+          const uint32_t af = __ldcg(acur + tile) & 0xffu;
+          visits++;
+          const unsigned long long left = warp_visit_tile<VARIANT>(a, cost, dmask, tile, af, bound, wt, wc, lane);
+          pf[5]++;
+          if (lane == 0) {
+            __stcg(acur + tile, 0u);  // this buffer receives the posts of the next round
+            __stcg(pmin + tile, left);
+            const uint32_t o = ((volatile uint32_t *)s_outw)[wid];
+            if (o) {
+              const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+#pragma unroll
+              for (int d = 0; d < 8; d++) {
+                constexpr int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
+                constexpr int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+                constexpr uint32_t facing[8] = {DIR_S, DIR_N, DIR_E, DIR_W, DIR_SE, DIR_SW, DIR_NE, DIR_NW};
+                if (o & (1u << d)) {
+                  const int nx = tx + ddx[d], ny = ty + ddy[d];
+                  if (nx >= 0 && nx < a.tiles_x && ny >= 0 && ny < a.tiles_y) {
+                    const int nb = ny * a.tiles_x + nx;
+                    if (atomicOr(anext + nb, facing[d]) == 0u) __stcg(lnext + atomicAdd(&s_lnext, 1u), (uint32_t)nb);
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+          PF_MARK(2);
+        }
+        PF_MARK(3);
+        __syncthreads();  // round end: every visit of the round is written back
+        PF_MARK(4);
+        uint32_t *tl = lcur;
+        lcur = lnext;
+        lnext = tl;
+        uint32_t *ta = acur;
+        acur = anext;
+        anext = ta;
+        if (tid == 0) s_mine = s_lnext;
+        __syncthreads();
+      }
+    } else
     for (uint32_t round = 0;; round++) {
       uint32_t *act_cur = act + (round % 3) * n_tiles, *act_next = act + ((round + 1) % 3) * n_tiles,
                *act_clr = act + ((round + 2) % 3) * n_tiles;
@@ -1096,7 +1185,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
               if (s_pref[mid] <= rk) lo = mid;
               else hi = mid - 1;
             }
-            tl = (int)__ldcg(a.lists + (size_t)(group * a.group_size + lo) * a.n_tiles + (rk - s_pref[lo]));
+            tl = (int)__ldcg(a.lists + (size_t)(group * a.group_size + lo) * 2 * a.n_tiles + (rk - s_pref[lo]));
           }
           tile = __shfl_sync(FULL, tl, 0);
         }
@@ -1510,7 +1599,7 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   const int grid = gs * n_groups;
   if constexpr (NB == 1) {
     void *lp;
-    const size_t lists_b = ((sizeof(uint32_t) * (size_t)grid * a.n_tiles) + 255) & ~(size_t)255;
+    const size_t lists_b = ((sizeof(uint32_t) * (size_t)grid * 2 * a.n_tiles) + 255) & ~(size_t)255;
     hpp_status s = hpp_scratch(c, 4, lists_b + sizeof(uint32_t) * 4 * (size_t)grid + 256, &lp);
     if (s != HPP_OK) return s;
     a.lists = (uint32_t *)lp;
