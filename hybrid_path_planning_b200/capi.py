@@ -85,6 +85,8 @@ def lib():
             "hpp_map_cells": [vp, vp, sz, vp, vp],
             "hpp_inflate": [vp, vp, u32, u32, dbl, dbl, vp],
             "hpp_inflate_dev": [vp, vp, u32, u32, dbl, dbl, vp],
+            "hpp_image_to_occupancy": [vp, vp, u32, u32, vp],
+            "hpp_image_to_occupancy_dev": [vp, vp, u32, u32, vp],
             "hpp_collide_circles": [vp, vp, sz, vp],
             "hpp_collide_circles_dev": [vp, vp, sz, vp],
             "hpp_collide_sat": [vp, vp, sz, vp],
@@ -162,6 +164,14 @@ class Context:
         out = np.empty_like(occ)
         self.check(self.L.hpp_inflate(self.h, occ.ctypes.data, W, H, float(resolution), float(radius), out.ctypes.data))
         return out
+
+    def image_to_occupancy(self, img):
+        """8-bit gray image [rows, cols] -> occupancy [H = cols, W = rows] (grid_map_publisher's conversion)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        rows, cols = img.shape
+        occ = np.empty((cols, rows), np.int8)
+        self.check(self.L.hpp_image_to_occupancy(self.h, img.ctypes.data, rows, cols, occ.ctypes.data))
+        return occ
 
     def inflate_dev(self, occ_dev, W, H, resolution, radius, out_dev):
         self.check(self.L.hpp_inflate_dev(self.h, _ptr(occ_dev), W, H, float(resolution), float(radius), _ptr(out_dev)))

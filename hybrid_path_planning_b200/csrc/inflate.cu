@@ -182,3 +182,53 @@ extern "C" hpp_status hpp_inflate(hpp_ctx *c, const int8_t *occ, uint32_t W, uin
   HPP_CUDA(c, cudaStreamSynchronize(c->stream));
   return HPP_OK;
 }
+
+// ------------------------------------------------------------------ image -> OccupancyGrid
+// grid_map_cv addLayerFromImage<unsigned char,1>(image, layer, map, lowerValue = 255, upperValue = 0, alpha 1):
+//   mapValue = lowerValue + (upperValue - lowerValue) * ((float)imageValue / 255.f), grid_map index (i, j) = pixel (i, j);
+// grid_map_ros toOccupancyGrid(map, layer, dataMin = 0, dataMax = 255): value = (mapValue - 0) / 255, clamped to [0,1],
+//   * 100, stored (float -> int8, truncation) at data[nCells - 1 - (j*rows + i)], info.width = rows, info.height = cols.
+// (GP/src/grid_publisher.cpp:32-50,78-86; the arithmetic is grid_map's, an un-vendored dependency: restated as recalled.)
+__global__ void __launch_bounds__(256) image_to_occ_kernel(const uint8_t *__restrict__ img, int rows, int cols,
+                                                           int8_t *__restrict__ occ) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    // k = y * rows + x  (coalesced writes); pixel (i, j) = (rows-1-x, cols-1-y)
+    const int x = (int)(k % rows), y = (int)(k / rows);
+    const int i = rows - 1 - x, j = cols - 1 - y;
+    const float v = (float)img[(size_t)i * cols + j];
+    const float map_value = __fadd_rn(255.0f, __fmul_rn(-255.0f, __fdiv_rn(v, 255.0f)));
+    float val = __fdiv_rn(__fsub_rn(map_value, 0.0f), 255.0f);
+    val = fminf(fmaxf(0.0f, val), 1.0f);
+    occ[k] = (int8_t)__fadd_rn(0.0f, __fmul_rn(val, 100.0f));
+  }
+}
+
+extern "C" hpp_status hpp_image_to_occupancy_dev(hpp_ctx *c, const uint8_t *img_dev, uint32_t rows, uint32_t cols,
+                                                 int8_t *occ_dev) {
+  if (!c || !img_dev || !occ_dev || rows == 0 || cols == 0) return HPP_ERR_ARG;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)rows * cols;
+  const long long want = hpp_div_up((long long)n, 256);
+  const int grid = (int)(want < (long long)c->sm_count * 16 ? want : (long long)c->sm_count * 16);
+  image_to_occ_kernel<<<grid, 256, 0, c->stream>>>(img_dev, (int)rows, (int)cols, occ_dev);
+  HPP_LAUNCHED(c);
+  return HPP_OK;
+}
+
+extern "C" hpp_status hpp_image_to_occupancy(hpp_ctx *c, const uint8_t *img, uint32_t rows, uint32_t cols, int8_t *occ) {
+  if (!c || !img || !occ || rows == 0 || cols == 0) return HPP_ERR_ARG;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)rows * cols;
+  void *d_in, *d_out;
+  hpp_status s = hpp_scratch(c, 0, n, &d_in);
+  if (s != HPP_OK) return s;
+  s = hpp_scratch(c, 1, n, &d_out);
+  if (s != HPP_OK) return s;
+  HPP_CUDA(c, cudaMemcpyAsync(d_in, img, n, cudaMemcpyHostToDevice, c->stream));
+  s = hpp_image_to_occupancy_dev(c, (const uint8_t *)d_in, rows, cols, (int8_t *)d_out);
+  if (s != HPP_OK) return s;
+  HPP_CUDA(c, cudaMemcpyAsync(occ, d_out, n, cudaMemcpyDeviceToHost, c->stream));
+  HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HPP_OK;
+}

@@ -57,3 +57,7 @@ using HybridAstarDubins = HybridAstarT<HPP_VARIANT_DUBINS>;
 // occupancy in, inflated occupancy out (same geometry), through hpp_inflate.
 std::vector<int8_t> InflateOccupancy(const std::vector<int8_t> &occ, uint32_t width, uint32_t height, double resolution,
                                      double inflation_radius);
+
+// drop-in for grid_map_publisher's image -> OccupancyGrid conversion (GP/src/grid_publisher.cpp:32-50,78-86): 8-bit gray
+// image (rows x cols, row-major) in, occupancy data out; the grid has width = rows and height = cols.
+std::vector<int8_t> OccupancyFromImage(const std::vector<uint8_t> &img, uint32_t rows, uint32_t cols);

@@ -249,3 +249,11 @@ std::vector<int8_t> InflateOccupancy(const std::vector<int8_t> &occ, uint32_t wi
   check(ctx, hpp_inflate(ctx, occ.data(), width, height, resolution, inflation_radius, out.data()), "hpp_inflate");
   return out;
 }
+
+std::vector<int8_t> OccupancyFromImage(const std::vector<uint8_t> &img, uint32_t rows, uint32_t cols) {
+  if (img.size() != (std::size_t)rows * cols) throw std::runtime_error("OccupancyFromImage: size mismatch");
+  std::vector<int8_t> out(img.size());
+  hpp_ctx *ctx = hpp_host::thread_ctx();
+  check(ctx, hpp_image_to_occupancy(ctx, img.data(), rows, cols, out.data()), "hpp_image_to_occupancy");
+  return out;
+}

@@ -107,6 +107,17 @@ hpp_status hpp_inflate(hpp_ctx *ctx, const int8_t *occ, uint32_t W, uint32_t H, 
 hpp_status hpp_inflate_dev(hpp_ctx *ctx, const int8_t *occ_dev, uint32_t W, uint32_t H, double resolution,
                            double inflation_radius, int8_t *out_dev);
 
+/* ---------------------------------------------------------------- image -> OccupancyGrid
+ * Replaces the map source of the demo stack: grid_map_publisher's image -> grid_map "obstacle" layer ->
+ * nav_msgs/OccupancyGrid conversion (GP/src/grid_publisher.cpp:32-50,78-86: GridMapCvConverter::addLayerFromImage
+ * <unsigned char,1>(img, "obstacle", map, 255, 0, 1) then GridMapRosConverter::toOccupancyGrid(map, "obstacle", 0, 255)).
+ * img: rows x cols 8-bit gray, row-major.  The grid gets width = rows, height = cols, and cell (x, y) comes from pixel
+ * (rows-1-x, cols-1-y); value = (int8)(clamp(((255 - 255 * (v / 255.f)) - 0) / 255, 0, 1) * 100) in float32:
+ * black -> 100, white -> 0.  occ: cols x rows int8, row-major [y*rows + x]. */
+hpp_status hpp_image_to_occupancy(hpp_ctx *ctx, const uint8_t *img, uint32_t rows, uint32_t cols, int8_t *occ);
+hpp_status hpp_image_to_occupancy_dev(hpp_ctx *ctx, const uint8_t *img_dev, uint32_t rows, uint32_t cols,
+                                      int8_t *occ_dev);
+
 /* ---------------------------------------------------------------- footprint collision
  * hpp_collide_circles replaces Grid_map::isSingleStateCollisionFree (RS/include/Grid_map.h:102,
  * RS/src/Grid_map.cpp:239-284) with CarData::getCircles (RS/src/CarData.cpp:100-110).

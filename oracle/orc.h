@@ -58,6 +58,9 @@ void orc_edt_sq_exact(const int8_t *occ, int W, int H, int64_t *d2);
 
 /* ---- a12: map_inflate (MI/src/map_inflate_node.cpp:65-161) ---- */
 void orc_inflate(const int8_t *occ, int W, int H, double resolution, double inflation_radius, int8_t *out);
+/* f1: image -> OccupancyGrid as grid_map_publisher does it (GP/src/grid_publisher.cpp:32-50,78-86; grid_map_cv /
+ * grid_map_ros arithmetic restated as recalled: parity unpinned).  img rows x cols, occ [y*rows + x], W = rows, H = cols */
+void orc_image_to_occ(const uint8_t *img, int rows, int cols, int8_t *occ);
 int orc_otsu_threshold(const uint8_t *gray, size_t n);
 void orc_ellipse_halfwidths(int r, int *dx /* 2r+1 entries, -1 = empty row */);
 

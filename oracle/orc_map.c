@@ -469,3 +469,21 @@ int orc_collide_sat(const orc_map *m, const orc_car *car, double x, double y, do
   gy = orc_cell_y(m, y);
   return !orc_in_bounds(m, gx, gy);
 }
+
+/* ------------------------------------------------------------------ f1 */
+/* GP/src/grid_publisher.cpp:46-50: GridMapCvConverter::addLayerFromImage<unsigned char, 1>(img_src, "obstacle", map,
+ * OCCUPY = 255, FREE = 0, 1):  mapValue = lower + (upper - lower) * ((float)pixel / 255), index (i, j) = pixel (i, j).
+ * :78-86: GridMapRosConverter::toOccupancyGrid(map, "obstacle", 0, 255, grid): value = (mapValue - dataMin) /
+ * (dataMax - dataMin), clamped to [0, 1], * 100, float -> int8; data[nCells - 1 - (j * rows + i)]; width = rows. */
+void orc_image_to_occ(const uint8_t *img, int rows, int cols, int8_t *occ) {
+  const size_t n = (size_t)rows * cols;
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) {
+      const float lower = 255.0f, upper = 0.0f;
+      const float map_value = lower + (upper - lower) * ((float)img[(size_t)i * cols + j] / 255.0f);
+      float value = (map_value - 0.0f) / (255.0f - 0.0f);
+      value = fminf(fmaxf(0.0f, value), 1.0f);
+      value = 0.0f + value * 100.0f;
+      occ[n - 1 - ((size_t)j * rows + i)] = (int8_t)value;
+    }
+}

@@ -151,6 +151,17 @@ def inflate(occ, resolution, radius):
     return out
 
 
+def image_to_occ(img):
+    """f1: 8-bit gray image [rows, cols] -> occupancy [H = cols, W = rows] (grid_map_publisher's convention)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = img.shape
+    occ = np.empty((cols, rows), np.int8)
+    L = lib()
+    L.orc_image_to_occ.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.orc_image_to_occ(img.ctypes.data, rows, cols, occ.ctypes.data)
+    return occ
+
+
 def heuristic_rs(occ, goal, start=(0, 0), quirks=True):
     occ = _i8(occ)
     H, W = occ.shape

@@ -130,3 +130,25 @@ def test_exact_edt_property():
     _, dist = O.edt_layers(occ, np.float32(0.2))
     want = (np.sqrt(d2.astype(np.float32)) * np.float32(0.2)).astype(np.float32).reshape(-1)[::-1]
     assert bits_equal(dist, np.ascontiguousarray(want))
+
+
+def test_image_to_occupancy_convention():
+    """f1 (GP/src/grid_publisher.cpp:32-50,78-86): the oracle's image -> OccupancyGrid conversion reproduces the committed
+    fixture maps from their (binary) images -- width = image rows, both axes reversed, black = 100 -- and maps gray
+    levels through grid_map's float arithmetic with truncation."""
+    maps = np.load(os.path.join(G, "maps.npz"))
+    for k in maps.files:
+        occ = maps[k]
+        img = np.where(occ.T[::-1, ::-1] > 0, 0, 255).astype(np.uint8)      # pixel (i, j) <- cell (rows-1-i, cols-1-j)
+        got = O.image_to_occ(img)
+        assert got.shape == occ.shape and bits_equal(got, occ)
+    ramp = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    got = O.image_to_occ(ramp)
+    want = np.empty(256, np.int8)
+    for v in range(256):
+        mv = np.float32(255.0) + np.float32(-255.0) * (np.float32(v) / np.float32(255.0))
+        val = min(max(np.float32(0.0), mv / np.float32(255.0)), np.float32(1.0)) * np.float32(100.0)
+        i, j = divmod(v, 16)
+        want[255 - (j * 16 + i)] = np.int8(int(val))
+    assert bits_equal(got.reshape(-1), want)
+    assert got.reshape(-1)[255] == 100 and got.reshape(-1)[0] == 0

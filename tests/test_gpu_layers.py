@@ -103,3 +103,16 @@ def test_inflate_multivalued_otsu(ctx):
     for vals in ([0, 30, 60, 100, -1], [0, 100, -1], [0, 10, 20, 30, 40, 50, 60, 70, 80, 90, 100]):
         occ = rng.choice(np.array(vals, np.int8), size=(90, 130))
         assert bits_equal(ctx.inflate(occ, res, 0.6), O.inflate(occ, res, 0.6))
+
+
+@pytest.mark.parametrize("rows,cols,seed", [(16, 16, 1), (37, 91, 2), (300, 257, 3), (1, 5, 4)])
+def test_image_to_occupancy_bit_exact(ctx, rows, cols, seed):
+    """f1: device image -> OccupancyGrid conversion == the oracle's restatement of grid_map_publisher's, all gray levels"""
+    from oracle import pyorc as O
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (rows, cols)).astype(np.uint8)
+    if rows * cols >= 256:
+        img.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)
+    got = ctx.image_to_occupancy(img)
+    assert got.shape == (cols, rows)
+    assert bits_equal(got, O.image_to_occ(img))
