@@ -180,3 +180,40 @@ def test_heuristic_async_queue_kernel(ctx, monkeypatch):
     assert bits_equal(gotd, wantd)
     m.close()
     m2.close()
+
+
+def test_heuristic_one_cta_per_field_list_schedule(ctx, monkeypatch):
+    """HPP_HEUR_GROUP=1 forces the one-CTA-per-field mode (plain launch, list-based schedule of the rounds) that large
+    batches use; checked here on single fields of several shapes and on a 150-field batch (RS and Dubins)."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    monkeypatch.setenv("HPP_HEUR_GROUP", "1")
+    for W, H, p, blk, seed in ((64, 64, 0.1, 2, 1), (301, 203, 0.25, 4, 2), (512, 384, 0.3, 8, 3)):
+        occ = block_map(W, H, p, blk, seed)
+        occ[H // 2, W // 2] = 0
+        m = hpp.Map(ctx, occ, 0.2)
+        got, _ = m.heuristic_rs((W // 2, H // 2), (0, 0))
+        assert bits_equal(got, O.heuristic_rs(occ, (W // 2, H // 2), (0, 0), quirks=False)[0]), (W, H)
+        gotd, _ = m.heuristic_dubins((W // 2, H // 2))
+        assert bits_equal(gotd, O.heuristic_dubins(occ, (W // 2, H // 2))), (W, H)
+        m.close()
+    monkeypatch.delenv("HPP_HEUR_GROUP")
+    occ = block_map(160, 128, 0.15, 3, seed=9)
+    free = np.argwhere(occ == 0)
+    rng = np.random.default_rng(2)
+    goals = np.array([free[i][::-1] for i in rng.choice(len(free), 150, replace=False)], np.int32)
+    m = hpp.Map(ctx, occ, 0.2)
+    for variant in (0, 1):
+        got = m.heuristic_batch(variant, goals)          # 150 fields: chunks of 38 -> groups; force the solo path below
+        for f in (0, 37, 38, 149):
+            g = tuple(int(v) for v in goals[f])
+            want = O.heuristic_rs(occ, g, (0, 0), quirks=False)[0] if variant == 0 else O.heuristic_dubins(occ, g)
+            assert bits_equal(got[f], want), (variant, f)
+    import torch
+    cost = torch.empty((150, 128, 160), dtype=torch.float64, device="cuda:0")
+    m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost)    # 150 fields in one launch: one CTA per field
+    ctx.sync()
+    for f in (0, 75, 149):
+        g = tuple(int(v) for v in goals[f])
+        assert bits_equal(cost[f].cpu().numpy(), O.heuristic_rs(occ, g, (0, 0), quirks=False)[0]), f
+    m.close()
