@@ -31,13 +31,22 @@ __device__ __forceinline__ void gm_position(const hpp_geom &g, int i, int j, dou
   y = (g.posy + (0.5 * g.leny - 0.5 * g.res)) + g.res * (double)(-j);
 }
 
-// one footprint circle at world position (px,py): 1 = outside the map or clearance < r
-__device__ __forceinline__ int circle_hits(const hpp_geom &g, const float *__restrict__ dist, double px, double py,
-                                           double r) {
+// one footprint circle at world position (px,py), in two halves so that the taps of several circles can be in
+// flight together: circle_prep resolves the taps, circle_finish interpolates and compares
+struct circle_taps {
+  int mode;           // 0 = outside the map (collision), 1 = INTER_NEAREST fallback (tap l[0]), 2 = bilinear
+  long l[4];
+  double rx, ry;
+};
+
+__device__ __forceinline__ void circle_prep(const hpp_geom &g, double px, double py, circle_taps &t) {
   // isInside -> checkIfPositionWithinMap
   double tx = -((px - g.posx) - 0.5 * g.lenx);
   double ty = -((py - g.posy) - 0.5 * g.leny);
-  if (!(tx >= 0.0 && ty >= 0.0 && tx < g.lenx && ty < g.leny)) return 1;
+  t.mode = 0;
+  t.l[0] = t.l[1] = t.l[2] = t.l[3] = 0;
+  t.rx = t.ry = 0.0;
+  if (!(tx >= 0.0 && ty >= 0.0 && tx < g.lenx && ty < g.leny)) return;
   // atPositionLinearInterpolated
   int i0, j0;
   gm_index(g, px, py, i0, j0);
@@ -51,20 +60,46 @@ __device__ __forceinline__ int circle_hits(const hpp_geom &g, const float *__res
   const int ja = diry ? j0 : j2, jb = diry ? j2 : j0;
   const long W = g.W, nn = (long)g.W * g.H;
   const long l0 = ja * W + ia, l1 = ja * W + ib, l2 = jb * W + ia, l3 = jb * W + ib;
-  float value;
   if (l0 < 0 || l0 >= nn || l1 < 0 || l1 >= nn || l2 < 0 || l2 >= nn || l3 < 0 || l3 >= nn) {
-    value = __ldg(dist + (size_t)j0 * W + i0);  // INTER_NEAREST fallback
+    t.mode = 1;  // INTER_NEAREST fallback
+    t.l[0] = t.l[1] = t.l[2] = t.l[3] = (long)j0 * W + i0;
   } else {
-    const float f0 = __ldg(dist + l0), f1 = __ldg(dist + l1), f2 = __ldg(dist + l2), f3 = __ldg(dist + l3);
+    t.mode = 2;
+    t.l[0] = l0; t.l[1] = l1; t.l[2] = l2; t.l[3] = l3;
     double bx = cx, by = cy;
     gm_position(g, ia, ja, bx, by);
-    const double rx = hpp_div_res(g, px - bx), ry = hpp_div_res(g, py - by);
-    const double fx = 1.0 - rx, fy = 1.0 - ry;
-    value = (float)((double)f0 * fx * fy + (double)f1 * rx * fy + (double)f2 * fx * ry + (double)f3 * rx * ry);
+    t.rx = hpp_div_res(g, px - bx);
+    t.ry = hpp_div_res(g, py - by);
+  }
+}
+
+__device__ __forceinline__ int circle_finish(const circle_taps &t, float f0, float f1, float f2, float f3, double r) {
+  if (t.mode == 0) return 1;
+  float value = f0;
+  if (t.mode == 2) {
+    const double fx = 1.0 - t.rx, fy = 1.0 - t.ry;
+    value = (float)((double)f0 * fx * fy + (double)f1 * t.rx * fy + (double)f2 * fx * t.ry + (double)f3 * t.rx * t.ry);
   }
   return (double)value < r;
 }
 
+// 1 = outside the map or clearance < r
+__device__ __forceinline__ int circle_hits(const hpp_geom &g, const float *__restrict__ dist, double px, double py,
+                                           double r) {
+  circle_taps t;
+  circle_prep(g, px, py, t);
+  if (t.mode == 0) return 1;
+  const float f0 = __ldg(dist + t.l[0]);
+  float f1 = f0, f2 = f0, f3 = f0;
+  if (t.mode == 2) {
+    f1 = __ldg(dist + t.l[1]);
+    f2 = __ldg(dist + t.l[2]);
+    f3 = __ldg(dist + t.l[3]);
+  }
+  return circle_finish(t, f0, f1, f2, f3, r);
+}
+
+// throughput form: the four circles in the reference's order, later circles are skipped after a hit
 __device__ __forceinline__ int circles_collide(const hpp_geom &g, const circ_consts &cc,
                                                const float *__restrict__ dist, double x, double y, double h) {
   double s, c;
@@ -76,6 +111,30 @@ __device__ __forceinline__ int circles_collide(const hpp_geom &g, const circ_con
     if (circle_hits(g, dist, px, py, cc.cr)) return 1;
   }
   return 0;
+}
+
+// latency form (the planner's per-query chains): the taps of all four circles are loaded together; same verdict.
+// Not inlined: the planner kernels are instruction-fetch bound, one shared copy keeps their code small.
+static __device__ __noinline__ int circles_collide_ilp(const hpp_geom &g, const circ_consts &cc,
+                                                   const float *__restrict__ dist, double x, double y, double h) {
+  double s, c;
+  sincos(h, &s, &c);
+  circle_taps t[4];
+  float f[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    double px = cc.cx[k] * c - cc.cy[k] * s + x;
+    double py = cc.cx[k] * s + cc.cy[k] * c + y;
+    circle_prep(g, px, py, t[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) f[k][q] = t[k].mode ? __ldg(dist + t[k].l[q]) : 0.f;
+  int hit = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) hit |= circle_finish(t[k], f[k][0], f[k][1], f[k][2], f[k][3], cc.cr);
+  return hit;
 }
 
 // ---------------------------------------------------------------------------------------- SAT

@@ -116,9 +116,10 @@ static inline int hpp_div_up(long long a, long long b) { return (int)((a + b - 1
 // double (24 significant bits), so it always holds here; checked against a/d on 3.2e9 random operands over 22 resolutions
 // and exponents +-930.  Zeros, subnormal-range and huge operands take the plain division.
 #ifdef __CUDACC__
+static __device__ __noinline__ double hpp_div_slow(double a, double d) { return a / d; }  // cold: one copy per kernel
 __device__ __forceinline__ double hpp_div_res(const hpp_geom &g, double a) {
   const double m = fabs(a);
-  if (!(m > 1e-280 && m < 1e280)) return a / g.res;
+  if (!(m > 1e-280 && m < 1e280)) return hpp_div_slow(a, g.res);
   const double q0 = a * g.rcp_res;
   const double r = __fma_rn(-q0, g.res, a);
   return __fma_rn(r, g.rcp_res, q0);

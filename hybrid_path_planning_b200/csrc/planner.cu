@@ -1,8 +1,12 @@
 // planner.cu -- whole Hybrid A* queries on the device: HybridAstar::run (RS/src/HybridAstar.cpp:553-729,
 // DB/src/HybridAstar.cpp:315-496) for a batch of independent start/goal pairs on one map.
 //
-// One warp owns one query from start to finish (and then takes the next one): no host round trip per A*
-// iteration.  Per query the warp keeps, in its own slice of global memory,
+// One CTA of PLAN_WARPS warps owns one query from start to finish (and then takes the next one from a counter): no
+// host round trip per A* iteration.  The iterations of a query are a sequential chain, so the CTA's job is to make
+// one iteration short: the 46 Reeds-Shepp closed forms are spread over the warps family by family, the candidate
+// paths are sampled and footprint-checked one per warp, and the expansion's rollouts run one thread per
+// (command, state); pop, de-duplication and the heap pushes stay on one warp / one thread.
+// Per query the CTA keeps, in its own slice of global memory,
 //   * a node pool (state, Cost_path, steering angle, direction, parent, command index),
 //   * the open list as a binary heap of (f, node) that replays libstdc++'s std::push_heap / std::pop_heap for
 //     the reference's cost-only comparator, so equal-f nodes pop in the reference's order,
@@ -21,6 +25,7 @@
 #include "shots.cuh"
 
 #define PLAN_WARPS 4
+#define PLAN_THREADS (PLAN_WARPS * 32)
 #define PLAN_ITER_CAP 3500
 #define PI_ASTAR 3.14159 /* RS/include/HybridAstar.h:24 */
 
@@ -122,41 +127,91 @@ __device__ __forceinline__ int gheap_pop(double *key, int *idx, int &n) {
   return top;
 }
 
+// what the threads of a query's CTA tell each other (two copies, alternating per iteration, so that one barrier per
+// hand-over is enough)
+struct plan_mail {
+  int hn, tv, slot;         // after the pop
+  int n_new, status;        // after the insertions (hn is rewritten too)
+  int found, samples;       // Dubins shot (evaluated by warp 0)
+  double cost;
+};
+
+struct plan_smem {
+  rs_warp_smem S;
+  plan_mail mail[2];
+  int query;
+  int verdict[2][PLAN_WARPS];           // kept sample count (or -1) of the path each warp checked
+  unsigned hit;                         // expansion: commands with a colliding state
+  double child[HPP_MAX_COMMANDS][3];    // expansion: last state of every command's rollout
+};
+
+// formula evaluated by (warp, lane): the closed forms of one family share their code path, so each warp gets at most
+// three families (RS/src/reeds_shepp_path.cpp:795-817 issue order: SLS 0-1, LSL 2-5, LSR 6-9, LRL 10-17, LRLRn 18-21,
+// LRLRp 22-25, LRSL 26-29 and 34-37, LRSR 30-33 and 38-41, LRSLR 42-45)
+__device__ __forceinline__ int plan_formula_of(int wid, int lane) {
+#if PLAN_WARPS == 4
+  switch (wid) {
+    case 0: return lane < 10 ? lane : -1;
+    case 1: return lane < 12 ? 10 + lane : -1;
+    case 2: return lane < 8 ? 22 + lane : (lane < 12 ? 26 + lane : -1);
+    default: return lane < 4 ? 30 + lane : (lane < 12 ? 34 + lane : -1);
+  }
+#else
+  const int t = wid * 32 + lane;
+  return t < RS_NCAND ? t : -1;
+#endif
+}
+
 template <int VARIANT>
-__global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, const float *__restrict__ dist,
-                                                               const uint32_t *__restrict__ bits, int pitch,
-                                                               const double *__restrict__ starts,
-                                                               const double *__restrict__ goals,
-                                                               const int *__restrict__ query_ids, int n_queries,
-                                                               const int *__restrict__ field_of_query,
-                                                               const double *__restrict__ fields,
-                                                               pnode *__restrict__ node_pool, double *__restrict__ key_pool,
-                                                               int *__restrict__ idx_pool, int *__restrict__ table_pool,
-                                                               hpp_plan *__restrict__ plans, double *__restrict__ traj,
-                                                               unsigned long long traj_cap,
-                                                               unsigned long long *__restrict__ cursor) {
-  __shared__ rs_warp_smem S_all[PLAN_WARPS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  rs_warp_smem &S = S_all[wid];
-  const int gwarp = blockIdx.x * PLAN_WARPS + wid, nwarps = gridDim.x * PLAN_WARPS;
+__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, const float *__restrict__ dist,
+                                                            const uint32_t *__restrict__ bits, int pitch,
+                                                            const double *__restrict__ starts,
+                                                            const double *__restrict__ goals,
+                                                            const int *__restrict__ query_ids, int n_queries,
+                                                            const int *__restrict__ field_of_query,
+                                                            const double *__restrict__ fields,
+                                                            pnode *__restrict__ node_pool, double *__restrict__ key_pool,
+                                                            int *__restrict__ idx_pool, int *__restrict__ table_pool,
+                                                            hpp_plan *__restrict__ plans, double *__restrict__ traj,
+                                                            unsigned long long traj_cap,
+                                                            unsigned long long *__restrict__ cursor,
+                                                            unsigned long long *__restrict__ prof) {
+  __shared__ plan_smem sm;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  rs_warp_smem &S = sm.S;
   const hpp_geom &g = pc.g;
   const int W = g.W, H = g.H;
   const long map_size = (long)W * H;
-  pnode *nodes = node_pool + (size_t)gwarp * pc.max_nodes;
-  double *hkey = key_pool + (size_t)gwarp * pc.max_nodes;
-  int *hidx = idx_pool + (size_t)gwarp * pc.max_nodes;
-  int *table = table_pool + (size_t)gwarp * (pc.table_mask + 1);
-  const int ncmd = pc.ec.n_cmd;
+  pnode *nodes = node_pool + (size_t)blockIdx.x * pc.max_nodes;
+  double *hkey = key_pool + (size_t)blockIdx.x * pc.max_nodes;
+  int *hidx = idx_pool + (size_t)blockIdx.x * pc.max_nodes;
+  int *table = table_pool + (size_t)blockIdx.x * (pc.table_mask + 1);
+  const int ncmd = pc.ec.n_cmd, n_poses = pc.ec.n_cmd * pc.ec.sim;
 
-  for (int qi = gwarp; qi < n_queries; qi += nwarps) {
+#ifdef HPP_PLAN_PROF
+  unsigned long long pf[6] = {0, 0, 0, 0, 0, 0};
+  long long tk = 0;
+#define PLAN_MARK(i) { const long long now_ = clock64(); pf[i] += (unsigned long long)(now_ - tk); tk = now_; }
+#else
+#define PLAN_MARK(i)
+#endif
+  // queries are handed out one at a time (cursor[1]): the few long ones (the 3500-iteration failures) then start
+  // early on whichever CTA is free instead of queueing behind a fixed share of the batch
+  int *next_query = (int *)(cursor + 1);
+  for (;;) {
+    __syncthreads();  // the previous query is finished by every warp
+    if (tid == 0) sm.query = atomicAdd(next_query, 1);
+    __syncthreads();
+    const int qi = sm.query;
+    if (qi >= n_queries) break;
     const int q = query_ids[qi];
     const double *hmap = fields + (size_t)field_of_query[qi] * map_size;
     const double sx = starts[3 * q], sy = starts[3 * q + 1], sh = starts[3 * q + 2];
     const double gx = goals[3 * q], gy = goals[3 * q + 1], gh = goals[3 * q + 2];
     const int s_cx = (int)(hpp_div_res(g, sx - g.ox)), s_cy = (int)(hpp_div_res(g, sy - g.oy));
     const int g_cx = (int)(hpp_div_res(g, gx - g.ox)), g_cy = (int)(hpp_div_res(g, gy - g.oy));
-    for (int i = lane; i <= pc.table_mask; i += 32) table[i] = -1;
-    __syncwarp();
+    for (int i = tid; i <= pc.table_mask; i += PLAN_THREADS) table[i] = -1;
+    __syncthreads();
     int n_nodes = 0, hn = 0, iterations = 0;
     int goal_node = -1, via_shot = 0, status = 0;
     rs_shot_result SR;
@@ -170,7 +225,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
     if (start_index < 0 || start_index >= map_size) {
       status = 2;  // the reference indexes goal_map_ out of range here (undefined behaviour)
     } else {
-      if (lane == 0) {
+      if (tid == 0) {
         pnode nd;
         nd.x = sx; nd.y = sy; nd.h = sh; nd.cost = 0.0; nd.steer = 0.0; nd.parent = -1; nd.dir = 1; nd.cmd = -1; nd.pad = 0;
         nodes[0] = nd;
@@ -180,53 +235,111 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
         gheap_push(hkey, hidx, hn, 0.0 + 30.0 * hmap[start_index], 0);
       }
       n_nodes = 1;
-      hn = __shfl_sync(0xffffffffu, hn, 0);
-      __syncwarp();
+      hn = 1;
     }
 
     while (status == 0 && hn > 0) {
       iterations++;
       if (iterations > PLAN_ITER_CAP) break;
-      // ---- pop
-      int cur = -1, slot = 0, tv = -1;
-      if (lane == 0) {
+      plan_mail &mail = sm.mail[iterations & 1];
+#ifdef HPP_PLAN_PROF
+      tk = clock64();
+#endif
+      // ---- pop (one thread)
+      if (tid == 0) {
+        int slot = 0;
         const int top = gheap_pop(hkey, hidx, hn);
         const pnode &tn = nodes[top];
-        tv = table_find(table, nodes, pc.table_mask, tn.x, tn.y, tn.h, slot);
+        const int tv = table_find(table, nodes, pc.table_mask, tn.x, tn.y, tn.h, slot);
+        if (tv >= 0 && !(tv & 1)) table[slot] = tv | 1;  // openSet.erase + closedSet[currentState] = currentNode
+        mail.hn = hn;
+        mail.tv = tv;
+        sm.hit = 0u;
       }
-      hn = __shfl_sync(0xffffffffu, hn, 0);
-      tv = __shfl_sync(0xffffffffu, tv, 0);
-      slot = __shfl_sync(0xffffffffu, slot, 0);
+      __syncthreads();
+      hn = mail.hn;
+      const int tv = mail.tv;
       if (tv < 0 || (tv & 1)) continue;  // already in the closed set
-      cur = tv >> 1;                     // openSet[currentState] (may be a cheaper replacement of the popped node)
-      if (lane == 0) table[slot] = tv | 1;  // openSet.erase + closedSet[currentState] = currentNode
-      __syncwarp();
+      const int cur = tv >> 1;           // openSet[currentState] (may be a cheaper replacement of the popped node)
       const pnode cn = nodes[cur];
+      PLAN_MARK(0)
 
-      // ---- analytic shot
+      // ---- analytic shot (+ for Dubins, the expansion's footprint checks on the other warps meanwhile)
       if (VARIANT == HPP_VARIANT_RS) {
-        rs_generate(S, cn.x, cn.y, cn.h, gx, gy, gh, pc.maxc);
-        SR = rs_select(S, g, pc.cc, dist, cn.x, cn.y, cn.h, cn.cost, pc.maxc, pc.max_steer);
+        const rs_frame f = rs_make_frame(cn.x, cn.y, cn.h, gx, gy, gh, pc.maxc);
+        const int idx = plan_formula_of(wid, lane);
+        if (idx >= 0) rs_eval_formula(idx, f.x, f.y, f.dth, f.xb, f.yb, S);
+        __syncthreads();
+        if (wid == 0) {
+          rs_dedup(S);
+          if (S.n_acc) rs_order_paths(S, cn.cost, pc.maxc, pc.max_steer);
+        }
+        __syncthreads();
+        PLAN_MARK(1)
+        const int n_acc = S.n_acc;
+        SR.found = 0; SR.chosen = -1; SR.n_samples = 0; SR.cand = -1; SR.cost = 0.0; SR.n_paths = n_acc;
+        double best = INFINITY;
+        bool done = false;
+        for (int o0 = 0, round = 0; o0 < n_acc && !done; o0 += PLAN_WARPS, round++) {
+          // PLAN_WARPS paths at a time, one per warp, folded in evaluation order afterwards
+          const int o = o0 + wid;
+          int verdict = -1;
+          if (o < n_acc) verdict = rs_check_path(S, o, g, pc.cc, dist, cn.x, cn.y, cn.h, pc.maxc);
+          if (lane == 0) sm.verdict[round & 1][wid] = verdict;
+          __syncthreads();
+          for (int w = 0; w < PLAN_WARPS && o0 + w < n_acc; w++)
+            if (rs_fold_path(S, o0 + w, sm.verdict[round & 1][w], SR, best)) {
+              done = true;
+              break;
+            }
+        }
         if (SR.found) {
           shot_samples = SR.n_samples;
           shot_cost = SR.cost;
         }
       } else {
-        DB = db_plan(cn.x, cn.y, cn.h, gx, gy, gh, pc.maxc);
-        sat_visitor vis;
-        vis.g = &g; vis.rx = pc.rx; vis.ry = pc.ry; vis.bits = bits; vis.pitch = pitch; vis.hit_zero_idx = 0x7fffffff;
-        const int n_keep = warp_sample_path<true>(DB.len, DB.typ, DB.nmode, pc.maxc, 0.1, cn.x, cn.y, cn.h, vis);
-        const bool collides = (n_keep < 0) || (vis.hit_zero_idx < n_keep);
-        SR.found = (n_keep > 0 && !collides);
-        if (SR.found) {
+        if (wid == 0) {
+          DB = db_plan(cn.x, cn.y, cn.h, gx, gy, gh, pc.maxc);
+          sat_visitor vis;
+          vis.g = &g; vis.rx = pc.rx; vis.ry = pc.ry; vis.bits = bits; vis.pitch = pitch; vis.hit_zero_idx = 0x7fffffff;
+          const int n_keep = warp_sample_path<true>(DB.len, DB.typ, DB.nmode, pc.maxc, 0.1, cn.x, cn.y, cn.h, vis);
+          const bool collides = (n_keep < 0) || (vis.hit_zero_idx < n_keep);
+          const int found = (n_keep > 0 && !collides);
           double cost = cn.cost;
           cost += fabs(DB.best_cost);
           for (int i = 0; i < 3; i++)
             if (DB.typ[i] != 'S') cost += pc.max_steer * 15.0;
-          shot_samples = n_keep;
-          shot_cost = cost;
+          if (lane == 0) {
+            mail.found = found;
+            mail.samples = n_keep;
+            mail.cost = cost;
+          }
+        }
+        if (wid != 0 || PLAN_WARPS == 1) {
+          // GetnextNeighbours' SAT checks (DB/src/HybridAstar.cpp:23-79), one pose per warp at a time
+          const int w0 = PLAN_WARPS == 1 ? 0 : wid - 1, ws = PLAN_WARPS == 1 ? 1 : PLAN_WARPS - 1;
+          for (int p = w0; p < n_poses; p += ws) {
+            const int c = p / pc.ec.sim, i = p % pc.ec.sim;
+            if ((sm.hit >> c) & 1u) continue;  // an earlier state of this command already collides
+            double x = cn.x, y = cn.y, h = cn.h;
+            for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
+            const int hit = sat_collide_warp(g, pc.rx, pc.ry, bits, pitch, x, y, h);
+            if (lane == 0) {
+              if (hit) atomicOr(&sm.hit, 1u << c);
+              if (i == pc.ec.sim - 1) {
+                sm.child[c][0] = x; sm.child[c][1] = y; sm.child[c][2] = h;
+              }
+            }
+          }
+        }
+        __syncthreads();
+        SR.found = mail.found;
+        if (SR.found) {
+          shot_samples = mail.samples;
+          shot_cost = mail.cost;
         }
       }
+      PLAN_MARK(2)
       if (SR.found) {
         goal_node = cur;  // the shot node hangs off `cur`
         via_shot = 1;
@@ -244,87 +357,101 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
         }
       }
 
-      // ---- expansion: lane = command
-      double cxs = 0, cys = 0, chs = 0, ccost = 0;
-      int valid = 0;
+      // ---- expansion (RS): one thread per (command, state of its rollout)
       if (VARIANT == HPP_VARIANT_RS) {
+        for (int p = tid; p < n_poses; p += PLAN_THREADS) {
+          const int c = p / pc.ec.sim, i = p % pc.ec.sim;
+          double x = cn.x, y = cn.y, h = cn.h;
+          for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
+          if (circles_collide_ilp(g, pc.cc, dist, x, y, h)) atomicOr(&sm.hit, 1u << c);
+          if (i == pc.ec.sim - 1) {
+            sm.child[c][0] = x; sm.child[c][1] = y; sm.child[c][2] = h;
+          }
+        }
+        __syncthreads();
+      }
+      PLAN_MARK(3)
+
+      // ---- insert / replace in command order (warp 0: lane = command)
+      if (wid == 0) {
+        double cxs = 0, cys = 0, chs = 0, ccost = 0;
+        int valid = 0;
         if (lane < ncmd) {
-          double x = cn.x, y = cn.y, h = cn.h;
-          int hit = 0;
-          for (int i = 0; i < pc.ec.sim; i++) {
-            vehicle_step(x, y, h, pc.ec.dir[lane], pc.ec.step, pc.ec.dtheta[lane]);
-            if (!hit) hit = circles_collide(g, pc.cc, dist, x, y, h);
-          }
-          valid = !hit;
-          cxs = x; cys = y; chs = h;
+          valid = !((sm.hit >> lane) & 1u);
+          cxs = sm.child[lane][0]; cys = sm.child[lane][1]; chs = sm.child[lane][2];
         }
-      } else {
-        for (int c = 0; c < ncmd; c++) {
-          double x = cn.x, y = cn.y, h = cn.h;
-          int hit = 0;
-          for (int i = 0; i < pc.ec.sim; i++) {
-            vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
-            if (!hit) hit = sat_collide_warp(g, pc.rx, pc.ry, bits, pitch, x, y, h);
-          }
-          if (lane == c) {
-            valid = !hit;
-            cxs = x; cys = y; chs = h;
-          }
-        }
-      }
-      double fkey = 0.0;
-      int ins_slot = -1, replace = 0;
-      if (valid) {
-        ccost = path_cost(pc.ec, lane, cn.cost, cn.steer, cn.dir);
-        int sl;
-        const int v = table_find(table, nodes, pc.table_mask, cxs, cys, chs, sl);
-        if (v >= 0 && (v & 1)) valid = 0;  // in the closed set
-        else {
-          const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
-          const long nidx = (long)ccy * W + ccx;
-          if (VARIANT == HPP_VARIANT_RS && (nidx < 0 || nidx >= map_size)) valid = 0;  // :674-677
+        double fkey = 0.0;
+        int ins_slot = -1, replace = 0;
+        if (valid) {
+          ccost = path_cost(pc.ec, lane, cn.cost, cn.steer, cn.dir);
+          int sl;
+          const int v = table_find(table, nodes, pc.table_mask, cxs, cys, chs, sl);
+          if (v >= 0 && (v & 1)) valid = 0;  // in the closed set
           else {
-            fkey = ccost + 30.0 * hmap[nidx];
-            if (v >= 0) {
-              if (ccost < nodes[v >> 1].cost) replace = 1;  // strictly cheaper than the open node
-              else valid = 0;
+            const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
+            const long nidx = (long)ccy * W + ccx;
+            if (VARIANT == HPP_VARIANT_RS && (nidx < 0 || nidx >= map_size)) valid = 0;  // :674-677
+            else {
+              fkey = ccost + 30.0 * hmap[nidx];
+              if (v >= 0) {
+                if (ccost < nodes[v >> 1].cost) replace = 1;  // strictly cheaper than the open node
+                else valid = 0;
+              }
+              ins_slot = sl;
             }
-            ins_slot = sl;
           }
         }
-      }
-      const unsigned vm = __ballot_sync(0xffffffffu, valid);
-      const int n_new = __popc(vm);
-      if (n_nodes + n_new > pc.max_nodes) {
-        status = 1;
-        break;
-      }
-      if (valid) {
-        const int my = n_nodes + __popc(vm & ((1u << lane) - 1u));
-        pnode nd;
-        nd.x = cxs; nd.y = cys; nd.h = chs; nd.cost = ccost; nd.steer = pc.ec.steer[lane]; nd.parent = cur;
-        nd.dir = (signed char)(int)pc.ec.dir[lane]; nd.cmd = (signed char)lane; nd.pad = 0;
-        nodes[my] = nd;
-        __threadfence_block();
-        if (replace) table[ins_slot] = my << 1;
-        else {
-          int sl = ins_slot;
-          while (atomicCAS(&table[sl], -1, my << 1) != -1) sl = (sl + 1) & pc.table_mask;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        const int n_new = __popc(vm);
+        int st = 0;
+        if (n_nodes + n_new > pc.max_nodes) {
+          st = 1;
+        } else {
+          if (valid) {
+            const int my = n_nodes + __popc(vm & ((1u << lane) - 1u));
+            pnode nd;
+            nd.x = cxs; nd.y = cys; nd.h = chs; nd.cost = ccost; nd.steer = pc.ec.steer[lane]; nd.parent = cur;
+            nd.dir = (signed char)(int)pc.ec.dir[lane]; nd.cmd = (signed char)lane; nd.pad = 0;
+            nodes[my] = nd;
+            __threadfence_block();
+            if (replace) table[ins_slot] = my << 1;
+            else {
+              int sl = ins_slot;
+              while (atomicCAS(&table[sl], -1, my << 1) != -1) sl = (sl + 1) & pc.table_mask;
+            }
+          }
+          __syncwarp();
+          PLAN_MARK(4)
+          // heap pushes in command order (one lane; keys fetched with shuffles)
+          for (unsigned mset = vm; mset;) {
+            const int b = __ffs(mset) - 1;
+            mset &= mset - 1;
+            const double k = __shfl_sync(0xffffffffu, fkey, b);
+            const int my = n_nodes + __popc(vm & ((1u << b) - 1u));
+            if (lane == 0) gheap_push(hkey, hidx, hn, k, my);
+          }
+        }
+        if (lane == 0) {
+          mail.hn = hn;
+          mail.n_new = n_new;
+          mail.status = st;
         }
       }
-      __syncwarp();
-      // heap pushes in command order (one lane; keys fetched with shuffles)
-      for (unsigned mset = vm; mset;) {
-        const int b = __ffs(mset) - 1;
-        mset &= mset - 1;
-        const double k = __shfl_sync(0xffffffffu, fkey, b);
-        const int my = n_nodes + __popc(vm & ((1u << b) - 1u));
-        if (lane == 0) gheap_push(hkey, hidx, hn, k, my);
-      }
-      hn = __shfl_sync(0xffffffffu, hn, 0);
-      n_nodes += n_new;
-      __syncwarp();
+      __syncthreads();
+      hn = mail.hn;
+      n_nodes += mail.n_new;
+      status = mail.status;
+      PLAN_MARK(5)
     }
+#ifdef HPP_PLAN_PROF
+    if (prof && tid == 0 && iterations > 3000) {
+      for (int i = 0; i < 6; i++) atomicAdd(prof + i, pf[i]);
+      atomicAdd(prof + 6, (unsigned long long)iterations);
+      atomicAdd(prof + 7, 1ull);
+    }
+    for (int i = 0; i < 6; i++) pf[i] = 0;
+#endif
+    if (wid != 0) continue;  // the back-track is warp 0's
 
     // ---- back-track (RS/src/HybridAstar.cpp:690-710)
     int total = 1;  // failure: the goal state alone (hazard H10)
@@ -449,7 +576,7 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   else
     HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, plan_kernel<HPP_VARIANT_DUBINS>, PLAN_WARPS * 32, 0));
   if (occ_blocks < 1) occ_blocks = 1;
-  size_t max_warps = (size_t)c->sm_count * occ_blocks * PLAN_WARPS;  // one resident wave of persistent warps
+  size_t max_warps = (size_t)c->sm_count * occ_blocks;  // CTAs (= queries in flight): one resident wave, persistent
   if (max_warps > n) max_warps = n;
   const size_t field_bytes = m->n * sizeof(double);
   const size_t budget = free_b > ((size_t)2 << 30) ? free_b - ((size_t)1 << 30) : free_b / 2;
@@ -457,8 +584,8 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   size_t fields_cap = (budget - max_warps * per_warp - n * 64 - traj_cap * 40) / field_bytes;
   if (fields_cap < 1) HPP_FAIL(c, HPP_ERR_NOMEM, "not enough device memory for one heuristic field");
   if (fields_cap > 4096) fields_cap = 4096;
-  const int grid = (int)((max_warps + PLAN_WARPS - 1) / PLAN_WARPS);
-  const size_t n_warps = (size_t)grid * PLAN_WARPS;
+  const int grid = (int)max_warps;
+  const size_t n_warps = (size_t)grid;  // one node pool / heap / table per CTA
 
   char *d_pool = nullptr, *d_io = nullptr;
   double *d_fields = nullptr;
@@ -492,6 +619,10 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
     cudaMemcpyAsync(d_goals, goals, n * 24, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(d_qids, order.data(), n * 4, cudaMemcpyHostToDevice, c->stream);
     cudaMemsetAsync(d_cursor, 0, 16, c->stream);
+    unsigned long long *d_prof = nullptr;
+#ifdef HPP_PLAN_PROF
+    if (hpp_scratch(c, 5, 64, (void **)&d_prof) == HPP_OK) cudaMemsetAsync(d_prof, 0, 64, c->stream);
+#endif
     // chunks of distinct goal cells
     size_t q0 = 0;
     while (q0 < n && st == HPP_OK) {
@@ -521,14 +652,15 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
       st = hpp_heuristic_batch_dev(m, variant, chunk_goals.data(), nf, d_fields, nullptr);
       if (st != HPP_OK) break;
       cudaMemcpyAsync(d_fq + q0, fq.data() + q0, (q1 - q0) * 4, cudaMemcpyHostToDevice, c->stream);
+      cudaMemsetAsync(d_cursor + 1, 0, 8, c->stream);  // the kernel's query counter
       if (variant == HPP_VARIANT_RS)
         plan_kernel<HPP_VARIANT_RS><<<grid, PLAN_WARPS * 32, 0, c->stream>>>(
             pc, m->d_distance, m->d_occ_bits, m->bits_pitch, d_starts, d_goals, d_qids + q0, (int)(q1 - q0), d_fq + q0,
-            d_fields, d_nodes, d_keys, d_idx, d_table, d_plans, d_traj, traj_cap, d_cursor);
+            d_fields, d_nodes, d_keys, d_idx, d_table, d_plans, d_traj, traj_cap, d_cursor, d_prof);
       else
         plan_kernel<HPP_VARIANT_DUBINS><<<grid, PLAN_WARPS * 32, 0, c->stream>>>(
             pc, m->d_distance, m->d_occ_bits, m->bits_pitch, d_starts, d_goals, d_qids + q0, (int)(q1 - q0), d_fq + q0,
-            d_fields, d_nodes, d_keys, d_idx, d_table, d_plans, d_traj, traj_cap, d_cursor);
+            d_fields, d_nodes, d_keys, d_idx, d_table, d_plans, d_traj, traj_cap, d_cursor, d_prof);
       c->launches++;
       e = cudaGetLastError();
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // fq / chunk_goals are reused by the next chunk
@@ -539,6 +671,16 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
       q0 = q1;
     }
   }
+#ifdef HPP_PLAN_PROF
+  if (st == HPP_OK) {
+    unsigned long long hp[8];
+    void *dp = nullptr;
+    if (hpp_scratch(c, 5, 64, &dp) == HPP_OK && cudaMemcpy(hp, dp, 64, cudaMemcpyDeviceToHost) == cudaSuccess && hp[7])
+      fprintf(stderr, "[plan prof] %llu long queries, %llu iterations; cycles/iteration: pop %.0f generate %.0f select %.0f "
+              "expand %.0f insert %.0f push %.0f\n", hp[7], hp[6], (double)hp[0] / hp[6], (double)hp[1] / hp[6],
+              (double)hp[2] / hp[6], (double)hp[3] / hp[6], (double)hp[4] / hp[6], (double)hp[5] / hp[6]);
+  }
+#endif
   if (st == HPP_OK) {
     unsigned long long used = 0;
     cudaMemcpyAsync(plans, d_plans, n * sizeof(hpp_plan), cudaMemcpyDeviceToHost, c->stream);

@@ -24,6 +24,7 @@
 struct rs_warp_smem {
   double len[RS_NCAND][5];  // normalised, signed segment lengths
   double L[RS_NCAND];       // normalised total length
+  unsigned long long word[RS_NCAND];  // segment count and types packed into one integer (one compare in set_path)
   double cost[RS_NCAND];
   unsigned char typ[RS_NCAND][5];
   unsigned char nseg[RS_NCAND];
@@ -34,13 +35,16 @@ struct rs_warp_smem {
 };
 
 // ------------------------------------------------------------------------------------ scalar helpers
-__device__ __forceinline__ double rs_M(double theta) {  // :846-860
+// (rs_M, rs_R and the sampler's sincos are deliberately NOT inlined: the planner kernel walks through its code once
+// per A* iteration with a handful of warps, so its speed is set by instruction fetch -- B200's L1.5 instruction cache
+// holds 32 KB -- and one shared copy of each libm expansion keeps the footprint down.  Same instructions, same bits.)
+static __device__ __noinline__ double rs_M(double theta) {  // :846-860
   double phi = fmod(theta, 2.0 * RS_PI);
   if (phi < -RS_PI) phi += 2.0 * RS_PI;
   if (phi > RS_PI) phi -= 2.0 * RS_PI;
   return phi;
 }
-__device__ __forceinline__ void rs_R(double x, double y, double &r, double &theta) {  // :837-843
+static __device__ __noinline__ void rs_R(double x, double y, double &r, double &theta) {  // :837-843
   r = hypot(x, y);
   theta = atan2(y, x);
 }
@@ -247,64 +251,80 @@ __device__ __forceinline__ void rs_eval_formula(int idx, double x, double y, dou
     default: ns = 5; ty = "LRSLR"; l[0] = t; l[1] = hp; l[2] = u; l[3] = hp; l[4] = v; break;
   }
   S.nseg[idx] = (unsigned char)ns;
+  unsigned long long word = (unsigned long long)ns;
+  double L = 0.0;
   for (int i = 0; i < 5; i++) {
-    S.len[idx][i] = (i < ns) ? l[i] * sg : 0.0;
+    const double li = (i < ns) ? l[i] * sg : 0.0;
+    S.len[idx][i] = li;
+    if (i < ns) L = L + fabs(li);  // set_path :123-127, same order
     char c = (i < ns) ? ty[i] : 0;
     if (swapLR) c = (c == 'L') ? 'R' : (c == 'R') ? 'L' : c;
     S.typ[idx][i] = (unsigned char)c;
+    word = (word << 8) | (unsigned char)c;
   }
+  S.word[idx] = word;
+  S.L[idx] = L;
+}
+
+// phase 2: set_path :98-141, replayed in generation order over the formulas' results in S.  Warp-collective.
+__device__ __forceinline__ void rs_dedup(rs_warp_smem &S) {
+  const int lane = threadIdx.x & 31;
+  int n_acc = 0;
+  int mine = -1;  // the accepted candidate this lane compares against (acc[lane])
+  // formulas that produced a path, as two ballot words (bit k <-> formula k)
+  const unsigned f_lo = __ballot_sync(0xffffffffu, S.flag[lane] != 0);
+  const unsigned f_hi = __ballot_sync(0xffffffffu, lane + 32 < RS_NCAND && S.flag[lane + 32] != 0);
+  for (unsigned long long todo = ((unsigned long long)f_hi << 32) | f_lo; todo; todo &= todo - 1) {
+    const int k = __ffsll((long long)todo) - 1;
+    bool dup = false;
+    if (mine >= 0 && S.word[mine] == S.word[k]) {
+      const int ns = S.nseg[k];
+      double sum_diff = 0.0;
+      for (int i = 0; i < ns; i++) sum_diff += S.len[mine][i] - S.len[k][i];
+      dup = sum_diff <= 0.01;
+    }
+    if (__any_sync(0xffffffffu, dup)) continue;
+    if (S.L[k] >= RS_MAX_LENGTH) continue;
+    // the reference asserts L >= 0.01 here (aborts when start ~ goal); release-build behaviour is kept
+    if (lane == n_acc) mine = k;
+    if (lane == 0) S.acc[n_acc] = (unsigned char)k;
+    n_acc++;
+  }
+  if (lane == 0) S.n_acc = n_acc;
+  __syncwarp();
+}
+
+// the goal in the start's frame, scaled by maxc (generate_path :799-805) and its "backwards" form (:329-330, :572-573)
+struct rs_frame {
+  double x, y, dth, xb, yb;
+};
+__device__ __forceinline__ rs_frame rs_make_frame(double sx, double sy, double syaw, double gx, double gy, double gyaw,
+                                                  double maxc) {
+  rs_frame f;
+  const double dx = gx - sx, dy = gy - sy;
+  f.dth = gyaw - syaw;
+  const double c = cos(syaw), s = sin(syaw);
+  f.x = (c * dx + s * dy) * maxc;
+  f.y = (-s * dx + c * dy) * maxc;
+  f.xb = f.x * cos(f.dth) + f.y * sin(f.dth);
+  f.yb = f.x * sin(f.dth) - f.y * cos(f.dth);
+  return f;
 }
 
 // phases 1+2: all candidates of (start -> goal), de-duplicated.  Warp-collective.
 __device__ __forceinline__ void rs_generate(rs_warp_smem &S, double sx, double sy, double syaw, double gx, double gy,
                                             double gyaw, double maxc) {
   const int lane = threadIdx.x & 31;
-  // generate_path :799-805
-  const double dx = gx - sx, dy = gy - sy, dth = gyaw - syaw;
-  const double c = cos(syaw), s = sin(syaw);
-  const double x = (c * dx + s * dy) * maxc;
-  const double y = (-s * dx + c * dy) * maxc;
-  const double xb = x * cos(dth) + y * sin(dth);  // :329-330, :572-573
-  const double yb = x * sin(dth) - y * cos(dth);
-  rs_eval_formula(lane, x, y, dth, xb, yb, S);
-  if (lane + 32 < RS_NCAND) rs_eval_formula(lane + 32, x, y, dth, xb, yb, S);
+  const rs_frame f = rs_make_frame(sx, sy, syaw, gx, gy, gyaw, maxc);
+  rs_eval_formula(lane, f.x, f.y, f.dth, f.xb, f.yb, S);
+  if (lane + 32 < RS_NCAND) rs_eval_formula(lane + 32, f.x, f.y, f.dth, f.xb, f.yb, S);
   __syncwarp();
-  // set_path :98-141, replayed in generation order
-  int n_acc = 0;
-  for (int k = 0; k < RS_NCAND; k++) {
-    if (!S.flag[k]) continue;  // warp-uniform (shared memory)
-    bool dup = false;
-    if (lane < n_acc) {
-      const int e = S.acc[lane];
-      if (S.nseg[e] == S.nseg[k]) {
-        bool same = true;
-        for (int i = 0; i < S.nseg[k]; i++) same = same && (S.typ[e][i] == S.typ[k][i]);
-        if (same) {
-          double sum_diff = 0.0;
-          for (int i = 0; i < S.nseg[e]; i++) sum_diff += S.len[e][i] - S.len[k][i];
-          dup = sum_diff <= 0.01;
-        }
-      }
-    }
-    if (__any_sync(0xffffffffu, dup)) continue;
-    double L = 0.0;
-    for (int i = 0; i < S.nseg[k]; i++) L = L + fabs(S.len[k][i]);
-    if (L >= RS_MAX_LENGTH) continue;
-    // the reference asserts L >= 0.01 here (aborts when start ~ goal); release-build behaviour is kept
-    if (lane == 0) {
-      S.L[k] = L;
-      S.acc[n_acc] = (unsigned char)k;
-    }
-    n_acc++;
-    __syncwarp();
-  }
-  if (lane == 0) S.n_acc = n_acc;
-  __syncwarp();
+  rs_dedup(S);
 }
 
 // ------------------------------------------------------------------------------------ sampler
 // interpolate (:750-793 / DB/src/dubins_path.cpp:181-230)
-__device__ __forceinline__ void rs_interpolate(double l, char m, double maxc, double ox, double oy, double oyaw,
+static __device__ __noinline__ void rs_interpolate(double l, char m, double maxc, double ox, double oy, double oyaw,
                                                double &px, double &py, double &pyaw) {
   if (m == 'S') {
     double s, c;
@@ -465,7 +485,7 @@ struct circ_visitor {  // RS: circle-footprint check, lane-parallel over samples
   int hit_zero_idx;  // smallest index of a colliding sample whose local x == 0.0 (may be trimmed later)
   __device__ __forceinline__ bool operator()(bool valid, int idx, double X, double Y, double YAW, double lx) {
     int hit = 0;
-    if (valid) hit = circles_collide(*g, *cc, dist, X, Y, YAW);
+    if (valid) hit = circles_collide_ilp(*g, *cc, dist, X, Y, YAW);
     const unsigned hard = __ballot_sync(0xffffffffu, hit && lx != 0.0);
     const unsigned soft = __ballot_sync(0xffffffffu, hit && lx == 0.0);
     if (soft) {
@@ -556,21 +576,14 @@ struct rs_shot_result {
   double cost;
 };
 
-// phases 3-5 for one start pose.  Warp-collective; S must hold rs_generate's output.
-__device__ __forceinline__ rs_shot_result rs_select(rs_warp_smem &S, const hpp_geom &g, const circ_consts &cc,
-                                                    const float *dist, double sx, double sy, double syaw,
-                                                    double parent_cost, double maxc, double max_steer) {
+// phases 3+4: cost of every accepted path and the order in which they are tried.  Warp-collective.
+__device__ __forceinline__ void rs_order_paths(rs_warp_smem &S, double parent_cost, double maxc, double max_steer) {
   const int lane = threadIdx.x & 31;
-  rs_shot_result R;
-  R.found = 0; R.chosen = -1; R.n_samples = 0; R.cand = -1; R.cost = 0.0;
   const int n_acc = S.n_acc;
-  R.n_paths = n_acc;
-  if (n_acc == 0) return R;
   for (int e = lane; e < n_acc; e += 32) S.cost[e] = rs_path_cost(S, S.acc[e], parent_cost, maxc, max_steer);
   __syncwarp();
-  const bool pq = n_acc > 5;  // RS/src/HybridAstar.cpp:131-142
   if (lane == 0) {
-    if (pq) {
+    if (n_acc > 5) {  // RS/src/HybridAstar.cpp:131-142
       double key[RS_NCAND];
       unsigned char pay[RS_NCAND];
       int hn = 0;
@@ -581,24 +594,49 @@ __device__ __forceinline__ rs_shot_result rs_select(rs_warp_smem &S, const hpp_g
     }
   }
   __syncwarp();
-  double best = INFINITY;
-  for (int o = 0; o < n_acc; o++) {
-    const int e = S.order[o], k = S.acc[e];
-    circ_visitor vis;
-    vis.g = &g; vis.cc = &cc; vis.dist = dist; vis.hit_zero_idx = 0x7fffffff;
-    int n_keep = warp_sample_path<false>(S.len[k], S.typ[k], S.nseg[k], maxc, maxc /* step_size(1) * maxc */, sx, sy,
-                                         syaw, vis);
-    bool collides = (n_keep < 0) || (vis.hit_zero_idx < n_keep);
-    if (collides) continue;
-    if (pq) {  // first collision-free path in pop order (:226-271)
-      R.found = 1; R.chosen = e; R.cand = k; R.cost = S.cost[e]; R.n_samples = n_keep;
-      break;
-    }
-    if (S.cost[e] < best) {  // iterative: strict minimum, first wins (:188-200)
-      best = S.cost[e];
-      R.found = 1; R.chosen = e; R.cand = k; R.cost = best; R.n_samples = n_keep;
-    }
+}
+
+// phase 5 for the o-th path in evaluation order: samples it and checks the footprint; returns the kept sample count
+// (>= 0) when the path is collision-free, -1 when it collides.  Warp-collective.
+__device__ __forceinline__ int rs_check_path(const rs_warp_smem &S, int o, const hpp_geom &g, const circ_consts &cc,
+                                             const float *dist, double sx, double sy, double syaw, double maxc) {
+  const int k = S.acc[S.order[o]];
+  circ_visitor vis;
+  vis.g = &g; vis.cc = &cc; vis.dist = dist; vis.hit_zero_idx = 0x7fffffff;
+  const int n_keep = warp_sample_path<false>(S.len[k], S.typ[k], S.nseg[k], maxc, maxc /* step_size(1) * maxc */, sx, sy,
+                                             syaw, vis);
+  return ((n_keep < 0) || (vis.hit_zero_idx < n_keep)) ? -1 : n_keep;
+}
+
+// folds the verdict of the o-th path into the result; returns true when the search is over
+// (> 5 paths: first collision-free path in pop order, :226-271; else strict minimum, first wins, :188-200)
+__device__ __forceinline__ bool rs_fold_path(const rs_warp_smem &S, int o, int n_keep, rs_shot_result &R, double &best) {
+  if (n_keep < 0) return false;
+  const int e = S.order[o];
+  if (S.n_acc > 5) {
+    R.found = 1; R.chosen = e; R.cand = S.acc[e]; R.cost = S.cost[e]; R.n_samples = n_keep;
+    return true;
   }
+  if (S.cost[e] < best) {
+    best = S.cost[e];
+    R.found = 1; R.chosen = e; R.cand = S.acc[e]; R.cost = best; R.n_samples = n_keep;
+  }
+  return false;
+}
+
+// phases 3-5 for one start pose.  Warp-collective; S must hold rs_generate's output.
+__device__ __forceinline__ rs_shot_result rs_select(rs_warp_smem &S, const hpp_geom &g, const circ_consts &cc,
+                                                    const float *dist, double sx, double sy, double syaw,
+                                                    double parent_cost, double maxc, double max_steer) {
+  rs_shot_result R;
+  R.found = 0; R.chosen = -1; R.n_samples = 0; R.cand = -1; R.cost = 0.0;
+  const int n_acc = S.n_acc;
+  R.n_paths = n_acc;
+  if (n_acc == 0) return R;
+  rs_order_paths(S, parent_cost, maxc, max_steer);
+  double best = INFINITY;
+  for (int o = 0; o < n_acc; o++)
+    if (rs_fold_path(S, o, rs_check_path(S, o, g, cc, dist, sx, sy, syaw, maxc), R, best)) break;
   return R;
 }
 
