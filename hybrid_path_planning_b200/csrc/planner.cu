@@ -127,6 +127,112 @@ __device__ __forceinline__ int gheap_pop(double *key, int *idx, int &n) {
   return top;
 }
 
+// std::pop_heap by a whole warp: the sift-down is a chain of dependent loads (one heap level per memory round trip
+// when one thread walks it), so the 30 descendants of the hole over the next four levels are fetched by the lanes
+// together and the walk takes four levels per round trip.  Same comparisons, same moves, same result as gheap_pop.
+__device__ __forceinline__ int gheap_pop_warp(double *key, int *idx, int &n) {
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int top = 0;
+  if (lane == 0) top = idx[0];
+  top = __shfl_sync(FULLM, top, 0);
+  if (n > 1) {
+    const double vk = key[n - 1];
+    const int vp = idx[n - 1];
+    const int len = n - 1;
+    int hole = 0, second = 0;
+    double k_above = 0.0;  // key now stored at the hole's parent (= the key that was at the hole)
+    int lr = 0;
+    for (int t = lane + 2; t > 1; t >>= 1) lr++;          // lane l holds relative level lr (1..4) ...
+    const int lj = lane + 2 - (1 << lr);                   // ... position lj of the subtree under the hole
+    while (second < (len - 1) / 2) {
+      const int base = hole;
+      const long node = (((long)base + 1) << lr) - 1 + lj;
+      const bool have = lane < 30 && node < len;
+      const double kv = have ? key[node] : 0.0;
+      const int iv = have ? idx[node] : 0;
+      for (int r = 1; r <= 4 && second < (len - 1) / 2; r++) {
+        second = 2 * (second + 1);
+        const int first = ((base + 1) << r) - 1;           // leftmost node of relative level r
+        const int src = (1 << r) - 2 + (second - first);   // lane holding `second`
+        const double kr = __shfl_sync(FULLM, kv, src), kl = __shfl_sync(FULLM, kv, src - 1);
+        const int ir = __shfl_sync(FULLM, iv, src), il = __shfl_sync(FULLM, iv, src - 1);
+        double km = kr;
+        int im = ir;
+        if (kr > kl) {
+          second--;
+          km = kl;
+          im = il;
+        }
+        if (lane == 0) {
+          key[hole] = km;
+          idx[hole] = im;
+        }
+        k_above = km;
+        hole = second;
+      }
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+      second = 2 * (second + 1);
+      const double km = key[second - 1];
+      const int im = idx[second - 1];
+      if (lane == 0) {
+        key[hole] = km;
+        idx[hole] = im;
+      }
+      k_above = km;
+      hole = second - 1;
+    }
+    __syncwarp();
+    // std::__push_heap of the former last element from the hole; its parent's key is known without a load
+    if (lane == 0) {
+      if (hole > 0 && k_above > vk) {
+        int parent = (hole - 1) / 2;
+        while (hole > 0 && key[parent] > vk) {
+          key[hole] = key[parent];
+          idx[hole] = idx[parent];
+          hole = parent;
+          parent = (hole - 1) / 2;
+        }
+      }
+      key[hole] = vk;
+      idx[hole] = vp;
+    }
+    __syncwarp();
+  }
+  n--;
+  return top;
+}
+
+// std::push_heap by a whole warp.  A new f value is usually close to the minimum, so it climbs most of the heap's
+// levels; lane t fetches the t-th ancestor of the new slot, a ballot finds where the climb stops (the first ancestor
+// whose key is not greater), and the lanes shift the entries down together: one memory round trip per push.
+__device__ __forceinline__ void gheap_push_warp(double *key, int *idx, int &n, double k, int p) {
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int node = ((n + 1) >> lane) - 1;  // lane 0: the new slot; -1 beyond the root
+  const bool anc = lane >= 1 && node >= 0;
+  double a = 0.0;
+  int ai = 0;
+  if (anc) {
+    a = key[node];
+    ai = idx[node];
+  }
+  const unsigned gt = __ballot_sync(FULLM, anc && a > k);
+  const int moves = __ffs(~(gt >> 1)) - 1;  // leading run of ancestors that move down
+  const double a_up = __shfl_down_sync(FULLM, a, 1);
+  const int ai_up = __shfl_down_sync(FULLM, ai, 1);
+  if (lane < moves) {
+    key[node] = a_up;
+    idx[node] = ai_up;
+  } else if (lane == moves) {
+    key[node] = k;
+    idx[node] = p;
+  }
+  n++;
+  __syncwarp();
+}
+
 // what the threads of a query's CTA tell each other (two copies, alternating per iteration, so that one barrier per
 // hand-over is enough)
 struct plan_mail {
@@ -142,6 +248,7 @@ struct plan_smem {
   int query;
   int verdict[2][PLAN_WARPS];           // kept sample count (or -1) of the path each warp checked
   unsigned hit;                         // expansion: commands with a colliding state
+  int hit0;                             // RS shot: footprint verdict of the start pose (sample 0 of every path)
   double child[HPP_MAX_COMMANDS][3];    // expansion: last state of every command's rollout
 };
 
@@ -189,7 +296,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
   const int ncmd = pc.ec.n_cmd, n_poses = pc.ec.n_cmd * pc.ec.sim;
 
 #ifdef HPP_PLAN_PROF
-  unsigned long long pf[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tk = 0;
 #define PLAN_MARK(i) { const long long now_ = clock64(); pf[i] += (unsigned long long)(now_ - tk); tk = now_; }
 #else
@@ -245,16 +352,18 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
 #ifdef HPP_PLAN_PROF
       tk = clock64();
 #endif
-      // ---- pop (one thread)
-      if (tid == 0) {
-        int slot = 0;
-        const int top = gheap_pop(hkey, hidx, hn);
-        const pnode &tn = nodes[top];
-        const int tv = table_find(table, nodes, pc.table_mask, tn.x, tn.y, tn.h, slot);
-        if (tv >= 0 && !(tv & 1)) table[slot] = tv | 1;  // openSet.erase + closedSet[currentState] = currentNode
-        mail.hn = hn;
-        mail.tv = tv;
-        sm.hit = 0u;
+      // ---- pop (warp 0)
+      if (wid == 0) {
+        const int top = gheap_pop_warp(hkey, hidx, hn);
+        if (lane == 0) {
+          int slot = 0;
+          const pnode &tn = nodes[top];
+          const int tv = table_find(table, nodes, pc.table_mask, tn.x, tn.y, tn.h, slot);
+          if (tv >= 0 && !(tv & 1)) table[slot] = tv | 1;  // openSet.erase + closedSet[currentState] = currentNode
+          mail.hn = hn;
+          mail.tv = tv;
+          sm.hit = 0u;
+        }
       }
       __syncthreads();
       hn = mail.hn;
@@ -270,9 +379,30 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
         const int idx = plan_formula_of(wid, lane);
         if (idx >= 0) rs_eval_formula(idx, f.x, f.y, f.dth, f.xb, f.yb, S);
         __syncthreads();
+        PLAN_MARK(6)
         if (wid == 0) {
           rs_dedup(S);
           if (S.n_acc) rs_order_paths(S, cn.cost, pc.maxc, pc.max_steer);
+        }
+        if (wid != 0 || PLAN_WARPS == 1) {
+          // meanwhile the other warps roll out the expansion (GetnextNeighbours, RS/src/HybridAstar.cpp:25-79): one
+          // thread per (command, state of its rollout); the result is dropped if the shot succeeds
+          const int t0 = PLAN_WARPS == 1 ? tid : tid - 32, ts = PLAN_WARPS == 1 ? 32 : PLAN_THREADS - 32;
+          for (int p = t0; p <= n_poses; p += ts) {
+            if (p == n_poses) {
+              // sample 0 of every candidate path is the start pose itself: looked at once per shot
+              // (world transform of (0,0,0), RS/src/reeds_shepp_path.cpp:76-81: x, y unchanged, pi_2_pi(yaw))
+              sm.hit0 = circles_collide_ilp(g, pc.cc, dist, cn.x, cn.y, pi_2_pi(0.0 + cn.h));
+              break;
+            }
+            const int c = p / pc.ec.sim, i = p % pc.ec.sim;
+            double x = cn.x, y = cn.y, h = cn.h;
+            for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
+            if (circles_collide_ilp(g, pc.cc, dist, x, y, h)) atomicOr(&sm.hit, 1u << c);
+            if (i == pc.ec.sim - 1) {
+              sm.child[c][0] = x; sm.child[c][1] = y; sm.child[c][2] = h;
+            }
+          }
         }
         __syncthreads();
         PLAN_MARK(1)
@@ -284,7 +414,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
           // PLAN_WARPS paths at a time, one per warp, folded in evaluation order afterwards
           const int o = o0 + wid;
           int verdict = -1;
-          if (o < n_acc) verdict = rs_check_path(S, o, g, pc.cc, dist, cn.x, cn.y, cn.h, pc.maxc);
+          if (o < n_acc) verdict = rs_check_path(S, o, g, pc.cc, dist, cn.x, cn.y, cn.h, pc.maxc, sm.hit0);
           if (lane == 0) sm.verdict[round & 1][wid] = verdict;
           __syncthreads();
           for (int w = 0; w < PLAN_WARPS && o0 + w < n_acc; w++)
@@ -357,19 +487,6 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
         }
       }
 
-      // ---- expansion (RS): one thread per (command, state of its rollout)
-      if (VARIANT == HPP_VARIANT_RS) {
-        for (int p = tid; p < n_poses; p += PLAN_THREADS) {
-          const int c = p / pc.ec.sim, i = p % pc.ec.sim;
-          double x = cn.x, y = cn.y, h = cn.h;
-          for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
-          if (circles_collide_ilp(g, pc.cc, dist, x, y, h)) atomicOr(&sm.hit, 1u << c);
-          if (i == pc.ec.sim - 1) {
-            sm.child[c][0] = x; sm.child[c][1] = y; sm.child[c][2] = h;
-          }
-        }
-        __syncthreads();
-      }
       PLAN_MARK(3)
 
       // ---- insert / replace in command order (warp 0: lane = command)
@@ -422,13 +539,13 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
           }
           __syncwarp();
           PLAN_MARK(4)
-          // heap pushes in command order (one lane; keys fetched with shuffles)
+          // heap pushes in command order (the whole warp per push: see gheap_push_warp)
           for (unsigned mset = vm; mset;) {
             const int b = __ffs(mset) - 1;
             mset &= mset - 1;
             const double k = __shfl_sync(0xffffffffu, fkey, b);
             const int my = n_nodes + __popc(vm & ((1u << b) - 1u));
-            if (lane == 0) gheap_push(hkey, hidx, hn, k, my);
+            gheap_push_warp(hkey, hidx, hn, k, my);
           }
         }
         if (lane == 0) {
@@ -445,11 +562,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
     }
 #ifdef HPP_PLAN_PROF
     if (prof && tid == 0 && iterations > 3000) {
-      for (int i = 0; i < 6; i++) atomicAdd(prof + i, pf[i]);
-      atomicAdd(prof + 6, (unsigned long long)iterations);
-      atomicAdd(prof + 7, 1ull);
+      for (int i = 0; i < 7; i++) atomicAdd(prof + i, pf[i]);
+      atomicAdd(prof + 7, (unsigned long long)iterations);
     }
-    for (int i = 0; i < 6; i++) pf[i] = 0;
+    for (int i = 0; i < 8; i++) pf[i] = 0;
 #endif
     if (wid != 0) continue;  // the back-track is warp 0's
 
@@ -676,9 +792,10 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
     unsigned long long hp[8];
     void *dp = nullptr;
     if (hpp_scratch(c, 5, 64, &dp) == HPP_OK && cudaMemcpy(hp, dp, 64, cudaMemcpyDeviceToHost) == cudaSuccess && hp[7])
-      fprintf(stderr, "[plan prof] %llu long queries, %llu iterations; cycles/iteration: pop %.0f generate %.0f select %.0f "
-              "expand %.0f insert %.0f push %.0f\n", hp[7], hp[6], (double)hp[0] / hp[6], (double)hp[1] / hp[6],
-              (double)hp[2] / hp[6], (double)hp[3] / hp[6], (double)hp[4] / hp[6], (double)hp[5] / hp[6]);
+      fprintf(stderr, "[plan prof] %llu iterations of long queries; cycles/iteration: pop %.0f formulas %.0f dedup+order %.0f "
+              "path checks %.0f expand %.0f insert %.0f push %.0f\n", hp[7], (double)hp[0] / hp[7], (double)hp[6] / hp[7],
+              (double)hp[1] / hp[7], (double)hp[2] / hp[7], (double)hp[3] / hp[7], (double)hp[4] / hp[7],
+              (double)hp[5] / hp[7]);
   }
 #endif
   if (st == HPP_OK) {

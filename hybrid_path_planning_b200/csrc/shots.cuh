@@ -352,9 +352,12 @@ static __device__ __noinline__ void rs_interpolate(double l, char m, double maxc
 // Returns the number of samples the reference keeps after its trailing "px == 0.0" trim.
 //   RS:      world = (cos(-q)x + sin(-q)y + sx, -sin(-q)x + cos(-q)y + sy, pi_2_pi(yaw + q))      (:76-81)
 //   Dubins:  world = (x cos q - y sin q + sx,  x sin q + y cos q + sy,     pi_2_pi(yaw + q))       (DB :365-371)
+// visit0 = false skips the visit of sample 0 (the start pose itself, the same for every path of a shot: the caller has
+// looked at it once).
 template <bool DUBINS, class Visitor>
 __device__ __forceinline__ int warp_sample_path(const double *len, const unsigned char *typ, int nseg, double maxc,
-                                                double step, double sx, double sy, double syaw, Visitor &vis) {
+                                                double step, double sx, double sy, double syaw, Visitor &vis,
+                                                bool visit0 = true) {
   const int lane = threadIdx.x & 31;
   double rs_, rc_;
   if (DUBINS) sincos(syaw, &rs_, &rc_);
@@ -371,7 +374,7 @@ __device__ __forceinline__ int warp_sample_path(const double *len, const unsigne
   };
   int last_nonzero = -1;  // largest sample index whose local x != 0.0 (warp-uniform after each step)
   // sample 0: the untouched (0,0,0) slot
-  {
+  if (visit0) {
     double X, Y, YAW;
     to_world(0.0, 0.0, 0.0, X, Y, YAW);
     if (vis(lane == 0, lane, X, Y, YAW, 0.0)) return -1;
@@ -386,6 +389,7 @@ __device__ __forceinline__ int warp_sample_path(const double *len, const unsigne
     ox = ex; oy = ey; oyaw = eyaw;  // px[ind] read before --ind (:711)
     double pd = (i >= 1 && (len[i - 1] * l) > 0) ? -d - ll : d - ll;
     const double al = fabs(l);
+    const bool last_seg = i == nseg - 1;
     // interior samples: pd, pd + d, (pd + d) + d, ... while |pd| <= |l|
     for (;;) {
       // lane j needs pd advanced j times; every lane replays the chain so the rounding matches the reference
@@ -395,33 +399,29 @@ __device__ __forceinline__ int warp_sample_path(const double *len, const unsigne
       // the reference's while loop stops at the first pd that fails, so only the leading run of lanes counts
       const unsigned vm = __ballot_sync(0xffffffffu, in_range);
       const int cnt = (vm == 0xffffffffu) ? 32 : (__ffs(~vm) - 1);
-      const bool valid = lane < cnt;
+      // the first idle lane of the segment's last step takes the end-of-segment sample (:733-735, length l): it is the
+      // next segment's origin, and for the last segment it survives at the slot after the interior samples
+      const bool is_end = cnt < 32 && lane == cnt;
+      const bool valid = lane < cnt || (is_end && last_seg);
       double px = 0, py = 0, pyaw = 0, X = 0, Y = 0, YAW = 0;
-      if (valid) {
-        rs_interpolate(mine, m, maxc, ox, oy, oyaw, px, py, pyaw);
-        to_world(px, py, pyaw, X, Y, YAW);
-      }
+      if (lane < cnt || is_end) rs_interpolate(is_end ? l : mine, m, maxc, ox, oy, oyaw, px, py, pyaw);
+      if (valid) to_world(px, py, pyaw, X, Y, YAW);
       const unsigned nz = __ballot_sync(0xffffffffu, valid && px != 0.0);
       if (nz) last_nonzero = ind + (31 - __clz(nz));
-      if (cnt && vis(valid, ind + lane, X, Y, YAW, px)) return -1;
+      if ((cnt || (cnt < 32 && last_seg)) && vis(valid, ind + lane, X, Y, YAW, px)) return -1;
       ind += cnt;
       // advance pd by cnt steps (all lanes identically)
       for (int j = 0; j < cnt; j++) pd += d;
-      if (cnt < 32) break;
+      if (cnt < 32) {
+        ex = __shfl_sync(0xffffffffu, px, cnt);
+        ey = __shfl_sync(0xffffffffu, py, cnt);
+        eyaw = __shfl_sync(0xffffffffu, pyaw, cnt);
+        break;
+      }
     }
     ll = l - pd - d;  // :731
-    rs_interpolate(l, m, maxc, ox, oy, oyaw, ex, ey, eyaw);  // end-of-segment sample (:733-735)
   }
-  // the last segment's end sample survives at slot `ind`
-  {
-    double X, Y, YAW;
-    to_world(ex, ey, eyaw, X, Y, YAW);
-    if (nseg > 0) {
-      if (ex != 0.0) last_nonzero = ind;
-      if (vis(lane == 0, ind + lane, X, Y, YAW, ex)) return -1;
-      ind++;
-    }
-  }
+  if (nseg > 0) ind++;  // the last segment's end sample
   int n_keep = last_nonzero + 1;
   if (DUBINS) {
     if (n_keep < 1) n_keep = 1;   // while (px.size() > 1 && back == 0)
@@ -598,13 +598,16 @@ __device__ __forceinline__ void rs_order_paths(rs_warp_smem &S, double parent_co
 
 // phase 5 for the o-th path in evaluation order: samples it and checks the footprint; returns the kept sample count
 // (>= 0) when the path is collision-free, -1 when it collides.  Warp-collective.
+// hit0: the footprint verdict of sample 0 (the start pose) when the caller has it already, -1 to look here.
 __device__ __forceinline__ int rs_check_path(const rs_warp_smem &S, int o, const hpp_geom &g, const circ_consts &cc,
-                                             const float *dist, double sx, double sy, double syaw, double maxc) {
+                                             const float *dist, double sx, double sy, double syaw, double maxc,
+                                             int hit0 = -1) {
   const int k = S.acc[S.order[o]];
   circ_visitor vis;
-  vis.g = &g; vis.cc = &cc; vis.dist = dist; vis.hit_zero_idx = 0x7fffffff;
+  vis.g = &g; vis.cc = &cc; vis.dist = dist;
+  vis.hit_zero_idx = hit0 > 0 ? 0 : 0x7fffffff;  // sample 0 has local x == 0.0: a hit there counts if it is kept
   const int n_keep = warp_sample_path<false>(S.len[k], S.typ[k], S.nseg[k], maxc, maxc /* step_size(1) * maxc */, sx, sy,
-                                             syaw, vis);
+                                             syaw, vis, hit0 < 0);
   return ((n_keep < 0) || (vis.hit_zero_idx < n_keep)) ? -1 : n_keep;
 }
 
