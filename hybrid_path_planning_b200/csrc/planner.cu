@@ -246,7 +246,8 @@ struct plan_smem {
   rs_warp_smem S;
   plan_mail mail[2];
   int query;
-  int verdict[2][PLAN_WARPS];           // kept sample count (or -1) of the path each warp checked
+  int verdict[RS_NCAND];                // kept sample count (or -1) of every accepted path
+  int next_path, any_free;              // RS shot: path hand-out counter, "some path is collision-free"
   unsigned hit;                         // expansion: commands with a colliding state
   int hit0;                             // RS shot: footprint verdict of the start pose (sample 0 of every path)
   double child[HPP_MAX_COMMANDS][3];    // expansion: last state of every command's rollout
@@ -363,6 +364,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
           mail.hn = hn;
           mail.tv = tv;
           sm.hit = 0u;
+          sm.next_path = 0;
+          sm.any_free = 0;
         }
       }
       __syncthreads();
@@ -380,10 +383,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
         if (idx >= 0) rs_eval_formula(idx, f.x, f.y, f.dth, f.xb, f.yb, S);
         __syncthreads();
         PLAN_MARK(6)
-        if (wid == 0) {
-          rs_dedup(S);
-          if (S.n_acc) rs_order_paths(S, cn.cost, pc.maxc, pc.max_steer);
-        }
+        if (wid == 0) rs_dedup(S);
         if (wid != 0 || PLAN_WARPS == 1) {
           // meanwhile the other warps roll out the expansion (GetnextNeighbours, RS/src/HybridAstar.cpp:25-79): one
           // thread per (command, state of its rollout); the result is dropped if the shot succeeds
@@ -408,20 +408,28 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
         PLAN_MARK(1)
         const int n_acc = S.n_acc;
         SR.found = 0; SR.chosen = -1; SR.n_samples = 0; SR.cand = -1; SR.cost = 0.0; SR.n_paths = n_acc;
-        double best = INFINITY;
-        bool done = false;
-        for (int o0 = 0, round = 0; o0 < n_acc && !done; o0 += PLAN_WARPS, round++) {
-          // PLAN_WARPS paths at a time, one per warp, folded in evaluation order afterwards
-          const int o = o0 + wid;
-          int verdict = -1;
-          if (o < n_acc) verdict = rs_check_path(S, o, g, pc.cc, dist, cn.x, cn.y, cn.h, pc.maxc, sm.hit0);
-          if (lane == 0) sm.verdict[round & 1][wid] = verdict;
+        // every accepted path is sampled and footprint-checked, the warps taking them one at a time from a counter.
+        // The reference tries them in cost order and stops at the first free one (> 5 paths) or keeps the cheapest
+        // free one; which path that is does not depend on how many were looked at, so the order -- a sequential
+        // heap replay -- is only worked out when some path is free (once per successful query).
+        for (;;) {
+          int e = 0;
+          if (lane == 0) e = atomicAdd(&sm.next_path, 1);
+          e = __shfl_sync(0xffffffffu, e, 0);
+          if (e >= n_acc) break;
+          const int verdict = rs_check_path(S, e, g, pc.cc, dist, cn.x, cn.y, cn.h, pc.maxc, sm.hit0);
+          if (lane == 0) {
+            sm.verdict[e] = verdict;
+            if (verdict >= 0) sm.any_free = 1;
+          }
+        }
+        __syncthreads();
+        if (sm.any_free) {
+          if (wid == 0) rs_order_paths(S, cn.cost, pc.maxc, pc.max_steer);
           __syncthreads();
-          for (int w = 0; w < PLAN_WARPS && o0 + w < n_acc; w++)
-            if (rs_fold_path(S, o0 + w, sm.verdict[round & 1][w], SR, best)) {
-              done = true;
-              break;
-            }
+          double best = INFINITY;
+          for (int o = 0; o < n_acc; o++)
+            if (rs_fold_path(S, o, sm.verdict[S.order[o]], SR, best)) break;
         }
         if (SR.found) {
           shot_samples = SR.n_samples;

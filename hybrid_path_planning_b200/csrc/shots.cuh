@@ -596,13 +596,13 @@ __device__ __forceinline__ void rs_order_paths(rs_warp_smem &S, double parent_co
   __syncwarp();
 }
 
-// phase 5 for the o-th path in evaluation order: samples it and checks the footprint; returns the kept sample count
+// phase 5 for the e-th accepted path: samples it and checks the footprint; returns the kept sample count
 // (>= 0) when the path is collision-free, -1 when it collides.  Warp-collective.
 // hit0: the footprint verdict of sample 0 (the start pose) when the caller has it already, -1 to look here.
-__device__ __forceinline__ int rs_check_path(const rs_warp_smem &S, int o, const hpp_geom &g, const circ_consts &cc,
+__device__ __forceinline__ int rs_check_path(const rs_warp_smem &S, int e, const hpp_geom &g, const circ_consts &cc,
                                              const float *dist, double sx, double sy, double syaw, double maxc,
                                              int hit0 = -1) {
-  const int k = S.acc[S.order[o]];
+  const int k = S.acc[e];
   circ_visitor vis;
   vis.g = &g; vis.cc = &cc; vis.dist = dist;
   vis.hit_zero_idx = hit0 > 0 ? 0 : 0x7fffffff;  // sample 0 has local x == 0.0: a hit there counts if it is kept
@@ -639,7 +639,7 @@ __device__ __forceinline__ rs_shot_result rs_select(rs_warp_smem &S, const hpp_g
   rs_order_paths(S, parent_cost, maxc, max_steer);
   double best = INFINITY;
   for (int o = 0; o < n_acc; o++)
-    if (rs_fold_path(S, o, rs_check_path(S, o, g, cc, dist, sx, sy, syaw, maxc), R, best)) break;
+    if (rs_fold_path(S, o, rs_check_path(S, S.order[o], g, cc, dist, sx, sy, syaw, maxc), R, best)) break;
   return R;
 }
 
