@@ -24,7 +24,9 @@
 #include "expand.cuh"
 #include "shots.cuh"
 
+#ifndef PLAN_WARPS
 #define PLAN_WARPS 4
+#endif
 #define PLAN_THREADS (PLAN_WARPS * 32)
 #define PLAN_ITER_CAP 3500
 #define PI_ASTAR 3.14159 /* RS/include/HybridAstar.h:24 */
@@ -263,6 +265,17 @@ __device__ __forceinline__ int plan_formula_of(int wid, int lane) {
     case 1: return lane < 12 ? 10 + lane : -1;
     case 2: return lane < 8 ? 22 + lane : (lane < 12 ? 26 + lane : -1);
     default: return lane < 4 ? 30 + lane : (lane < 12 ? 34 + lane : -1);
+  }
+#elif PLAN_WARPS == 8
+  switch (wid) {
+    case 0: return lane < 6 ? lane : -1;
+    case 1: return lane < 4 ? 6 + lane : -1;
+    case 2: return lane < 8 ? 10 + lane : -1;
+    case 3: return lane < 4 ? 18 + lane : -1;
+    case 4: return lane < 4 ? 22 + lane : -1;
+    case 5: return lane < 4 ? 26 + lane : (lane < 8 ? 30 + lane : -1);
+    case 6: return lane < 4 ? 30 + lane : (lane < 8 ? 34 + lane : -1);
+    default: return lane < 4 ? 42 + lane : -1;
   }
 #else
   const int t = wid * 32 + lane;
