@@ -441,11 +441,76 @@ def extras(ctx, torch, hpp, stream):
     for j in jobs:
         j["map"].close()
         j["ctx"].close()
+    try:
+        out["cfg1_cfg2_latency"] = fixture_latency(ctx, hpp, O)
+    except Exception as e:  # pragma: no cover  (never let an extra sink the headline line)
+        out["cfg1_cfg2_latency"] = {"error": str(e)[-200:]}
     nq = nmaps * npairs
     out["cfg5_queries"] = {"queries_per_s": nq / t_gpu, "queries": nq, "solved": solved, "maps_in_flight": nmaps,
                            "api": "hpp_plan_batch per map (host buffers; heuristic fields + device-resident A*), one "
                                   "context per map, maps planned concurrently from host threads",
                            "cpu": {"queries_per_s": n_cpu / t_cpu, "cores": 1, "kind": "port", "sample": f"{n_cpu} queries"}}
+    return out
+
+
+def fixture_latency(ctx, hpp, O):
+    """BASELINE configs[0] / configs[1]: single start/goal queries on the reference's own fixture maps
+    (tests/golden/maps.npz = the PNGs of grid_map_publisher in its OccupancyGrid convention), one hpp_plan_batch call
+    per query (what the ROS node does), next to HybridAstar::run of the compiled reference (oracle/_ref; the oracle
+    port when it is absent) on the same pairs, one host core, stopped after ~10 s per case.  Latency only."""
+    maps = np.load(os.path.join(ROOT, "tests", "golden", "maps.npz"))
+    res = float(np.float32(0.2))
+    cases = [("cfg1 reeds_shepp_hybrid_astar, map_parking.png 0.2 m", maps["map_parking"], 0, 0.3, 12, None),
+             ("cfg1b reeds_shepp_hybrid_astar, gridmap.png 0.2 m", maps["gridmap"], 0, 10.0, 6,
+              ((66.8, -36.7, 0.785), (21.4, -45.7, 2.356))),
+             ("cfg2 dubins_hybrid_star, map_maze.png 0.2 m inflated by 0.2 m", ctx.inflate(maps["map_maze"], res, 0.2), 1,
+              0.5, 12, None)]
+    out = {}
+    for name, occ, variant, margin, n, extra_pair in cases:
+        H, W = occ.shape
+        t0 = time.perf_counter()
+        m = hpp.Map(ctx, occ, res)
+        ctx.sync()
+        t_map = time.perf_counter() - t0
+        cand = random_poses(4000, W, H, res=res, margin=margin, seed=11)
+        v = m.collide_circles(cand) if variant == 0 else m.collide_sat(cand)
+        free = cand[v == 0][:2 * n]
+        k = len(free) // 2
+        starts, goals = free[:k], free[k:2 * k]
+        if extra_pair is not None:
+            starts = np.vstack([starts, [extra_pair[0]]])
+            goals = np.vstack([goals, [extra_pair[1]]])
+        if variant == 0 and name.startswith("cfg1 "):
+            starts = np.vstack([starts, [[-0.7, -4.9, np.pi]]])   # the solvable pair of SURVEY 8(d)
+            goals = np.vstack([goals, [[-0.1, -4.7, np.pi]]])
+        m.plan_batch(variant, starts[:1], goals[:1], traj_cap=1 << 16)
+        ts, its, ok = [], [], 0
+        for i in range(len(starts)):
+            t0 = time.perf_counter()
+            plans, _ = m.plan_batch(variant, starts[i:i + 1], goals[i:i + 1], traj_cap=1 << 16)
+            ts.append(time.perf_counter() - t0)
+            its.append(int(plans["iterations"][0]))
+            ok += int(plans["n_states"][0] > 1)
+        use_ref = O.ref_available()
+        ref = O.Ref(variant, occ, res) if use_ref else None
+        om = None if use_ref else O.Map(occ, res)
+        tc, t_begin = [], time.perf_counter()
+        for i in range(len(starts)):
+            t0 = time.perf_counter()
+            if use_ref:
+                ref.run(tuple(starts[i]), tuple(goals[i]))
+            else:
+                O.run(om, variant, tuple(starts[i]), tuple(goals[i]), quirks=True)
+            tc.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_begin > 10.0:
+                break
+        out[name] = {"cells": int(W * H), "queries": len(starts), "solved": ok, "iterations_mean": float(np.mean(its)),
+                     "iterations_max": int(max(its)), "map_build_ms": t_map * 1e3,
+                     "ms_per_query": 1e3 * float(np.mean(ts)), "ms_per_query_max": 1e3 * float(max(ts)),
+                     "cpu": {"ms_per_query": 1e3 * float(np.mean(tc)), "ms_per_query_max": 1e3 * float(max(tc)),
+                             "queries": len(tc), "kind": "reference" if use_ref else "port", "cores": 1,
+                             "same_queries_device_ms": 1e3 * float(np.mean(ts[:len(tc)]))}}
+        m.close()
     return out
 
 
