@@ -1557,16 +1557,23 @@ double env_double(const char *name, double dflt) {
 template <int NB, int VARIANT>
 hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   using C = tile_cfg<NB>;
-  // warp-tile kernel: 20 warps per CTA when every field gets its own CTA (throughput), else 16 (latency)
+  // warp-tile kernel: 20 warps per CTA when every field gets its own CTA (throughput), else 16 (latency).  Small maps
+  // (a wave front of a few tiles: most of a big CTA's warps would idle) with many fields get 4-warp CTAs, five per SM,
+  // so that five fields share an SM instead of one.
   const bool many = NB == 1 && VARIANT == HPP_VARIANT_RS && ctas_per_field_hint <= 1 && a.n_fields >= c->sm_count / 2;
-  const int WT_WARPS = many ? 20 : 16;
+  const int warps_env = (int)env_double("HPP_HEUR_WARPS", 0);
+  const bool small = NB == 1 && ctas_per_field_hint <= 1 && a.n_fields >= 4 * c->sm_count &&
+                     (warps_env ? warps_env == 4 : a.n_tiles <= 256);  // up to 512^2 cells (measured: 128^2 2.3x,
+                                                                        // 256^2 1.5x, 512^2 1.06x, 1024^2 0.88x)
+  const int WT_WARPS = small ? 4 : (many ? 20 : 16);
   const int threads = NB == 1 ? WT_WARPS * 32 : C::THREADS;
   size_t smem;
   const void *kern;
   if constexpr (NB == 1) {
     smem = (size_t)WT_WARPS * C::ROWS * C::S * (sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? 1 : 0)) + 16;
-    kern = many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
-                : (const void *)heur_warp_kernel<VARIANT, 16>;
+    kern = small ? (const void *)heur_warp_kernel<VARIANT, 4>
+                 : (many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
+                         : (const void *)heur_warp_kernel<VARIANT, 16>);
   } else {
     smem = heur_smem_bytes<NB>(VARIANT);
     kern = (const void *)heur_persist_kernel<NB, VARIANT>;
@@ -1575,7 +1582,7 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   int per_sm = 0;
   HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic kernel does not fit on an SM (%zu B shared)", smem);
-  const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", NB == 2 ? HPP_NB2_CTAS : 1);
+  const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", NB == 2 ? HPP_NB2_CTAS : (small ? 5 : 1));
   if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   const int G = per_sm * c->sm_count;  // co-resident CTAs
   // CTA groups: one field at a time per group, the groups never synchronise with each other.  A tile solve is a
