@@ -84,6 +84,7 @@ struct heur_args {
   double delta;                    // width of the global cost window
   double delta_in;                 // width of the sub-windows inside a tile visit
   int group_size, n_groups;
+  int compact;                     // warp-tile kernel: 1 = compacted sweeps (sweep_compact), 0 = row-wise sweeps (sweep)
   heur_weights wt;
 };
 
@@ -715,13 +716,159 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // `bound` (sub-windows of delta_in), writes the changed rows and the deferred masks back.  af = ring sides to
 // re-evaluate (DIR_* flags posted by the neighbours).  Returns the cheapest cost left deferred (bit pattern, INF_BITS
 // if none); *wc.s_out holds the DIR_* flags of the neighbour tiles whose halo this visit changed.
+// per-warp scratch of the compacted sweep, in shared memory (all zero between sweeps)
+#define WAUX_LIST 128
+struct warp_aux {
+  uint32_t push[HB + 2];            // row r (-1..32) at [r + 1]: cells (columns 0..31) a change of this sweep may improve
+  uint32_t spill[HB + 2];           // same for the columns just outside the tile: bit 0 = column -1, bit 1 = column 32
+  uint32_t low[HB];                 // cells improved below the bound (their deferred bit is cleared)
+  uint32_t high[HB];                // cells improved at or above the bound (deferred)
+  uint16_t list[WAUX_LIST];         // the sweep's needed cells, row << 5 | column
+};
+
 struct warp_ctx {
   double *cs_nv;
   uint8_t *cl_nv;
   uint32_t *s_out;
+  warp_aux *aux;
   uint32_t mbar, parity;
   bool tma_ok;
 };
+
+// the three neighbours (columns x-1, x, x+1; m3 bit 0 = column x-1) of one row as a mask of the columns 0..31
+__device__ __forceinline__ uint32_t row_mask3(int x, uint32_t m3) { return x >= 1 ? (m3 << (x - 1)) : (m3 >> 1); }
+
+// an improved cell (row r, column x) below the bound: its neighbours that may improve (nmask) go to their rows' words
+__device__ __forceinline__ void aux_deliver(warp_aux *ax, int r, int x, uint32_t k) {
+  const uint32_t up = k & 7u, own = ((k >> 3) & 1u) | ((k >> 2) & 4u), dn = (k >> 5) & 7u;
+  atomicOr(&ax->push[r], row_mask3(x, up));
+  atomicOr(&ax->push[r + 1], row_mask3(x, own));
+  atomicOr(&ax->push[r + 2], row_mask3(x, dn));
+  atomicOr(&ax->low[r], 1u << x);
+  if (x == 0 || x == 31) {  // columns just outside the tile
+    const uint32_t sh = x == 0 ? 0u : 2u, bit = x == 0 ? 1u : 2u;
+    if ((up >> sh) & 1u) atomicOr(&ax->spill[r], bit);
+    if ((own >> sh) & 1u) atomicOr(&ax->spill[r + 1], bit);
+    if ((dn >> sh) & 1u) atomicOr(&ax->spill[r + 2], bit);
+  }
+}
+
+// One sweep of a warp's 32x32 tile with the needed cells COMPACTED over the lanes.  The row-wise sweep above keeps
+// lane = row, so a thin wave front (one or two needed cells in each of a few rows) occupies a few lanes for several
+// iterations; here the rows write their needed cells into one list, every lane takes two list entries whatever
+// their rows, and the results go back to the rows through shared-memory ORs: (nearly) all lanes evaluate, and a sweep
+// with up to 64 needed cells is a single evaluation step.  The fixed point does not depend on the evaluation order,
+// so the cost field is bit-identical.
+template <int VARIANT>
+__device__ __forceinline__ bool sweep_compact(volatile double *cs, const volatile uint8_t *cl, warp_aux *ax, uint32_t *s_out,
+                                              blk_state &st, int lane, double bound, const eval_w &wt) {
+  constexpr int S = tile_cfg<1>::S;
+  if (!__any_sync(FULL, st.need != 0)) return false;
+  const int ebase = S + 2;
+  // the rows' needed cells, back to back; rows that do not fit in the list keep theirs for the next sweep
+  const int cnt = __popc(st.need);
+  int inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(FULL, inc, d);
+    if (lane >= d) inc += o;
+  }
+  const bool fits = inc <= WAUX_LIST;
+  const unsigned fit_m = __ballot_sync(FULL, fits);  // a prefix of the rows
+  const int n_rows = __popc(fit_m);
+  int total = __shfl_sync(FULL, inc, n_rows > 0 ? n_rows - 1 : 0);
+  if (n_rows == 0) total = 0;
+  HPP_COUNT(st.c_sweeps++; st.c_imp += (total + 63) >> 6; st.c_on += total;)
+  // rows with many needed cells (a front along the row) are written by the whole warp, one lane per column; the
+  // others by their own lane, one cell per step
+  uint32_t heavy = __ballot_sync(FULL, fits && cnt > 4);
+  while (heavy) {
+    const int r = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    const uint32_t m = __shfl_sync(FULL, st.need, r);
+    const int base = __shfl_sync(FULL, inc - cnt, r);
+    if ((m >> lane) & 1u) ax->list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((r << 5) | lane);
+  }
+  if (fits) {
+    if (cnt <= 4) {
+      int pos = inc - cnt;
+      for (uint32_t m = st.need; m; m &= m - 1) ax->list[pos++] = (uint16_t)((lane << 5) | (__ffs(m) - 1));
+    }
+    st.need = 0;
+  }
+  __syncwarp();
+  for (int q0 = 0; q0 < total; q0 += 64) {
+    HPP_COUNT(st.c_sparse++;)
+    const int qa = q0 + lane, qb = q0 + 32 + lane;
+    const bool on0 = qa < total, on1 = qb < total;
+    const int c0i = on0 ? ax->list[qa] : 0, c1i = on1 ? ax->list[qb] : 0;
+    const int r0 = c0i >> 5, x0 = c0i & 31, r1 = c1i >> 5, x1 = c1i & 31;
+    const uint32_t nm0 = __shfl_sync(FULL, st.nearm, r0), nm1 = __shfl_sync(FULL, st.nearm, r1);
+    const int e0 = ebase + r0 * S + x0, e1 = ebase + r1 * S + x1;
+    const double c0 = cs[e0], c1 = cs[e1];
+    uint32_t k0, k1;
+    const double b0 = eval_cell<VARIANT, S>(cs, cl, e0, (nm0 >> x0) & 1u, wt, k0);
+    double b1 = c1;
+    k1 = 0;
+    if (q0 + 32 < total) b1 = eval_cell<VARIANT, S>(cs, cl, e1, (nm1 >> x1) & 1u, wt, k1);  // warp-uniform
+    if (on0 && b0 < c0) {
+      cs[e0] = b0;
+      if (b0 < bound) {
+        aux_deliver(ax, r0, x0, k0);
+      } else {
+        atomicOr(&ax->high[r0], 1u << x0);
+      }
+    }
+    if (on1 && b1 < c1) {
+      cs[e1] = b1;
+      if (b1 < bound) {
+        aux_deliver(ax, r1, x1, k1);
+      } else {
+        atomicOr(&ax->high[r1], 1u << x1);
+      }
+    }
+    __syncwarp();
+  }
+  // back to the rows
+  const uint32_t low = ax->low[lane], high = ax->high[lane];
+  const uint32_t pm = ax->push[lane + 1], sp = ax->spill[lane + 1];
+  uint32_t pm_e = 0, sp_e = 0;  // the row above the tile (lane 0) / below it (lane 31)
+  if (lane == 0) {
+    pm_e = ax->push[0];
+    sp_e = ax->spill[0];
+  } else if (lane == 31) {
+    pm_e = ax->push[HB + 1];
+    sp_e = ax->spill[HB + 1];
+  }
+  __syncwarp();
+  if (low | high) {
+    ax->low[lane] = 0;
+    ax->high[lane] = 0;
+    st.dirty = 1;
+    st.defer = (st.defer | high) & ~low;
+  }
+  if (pm) ax->push[lane + 1] = 0;
+  if (sp) ax->spill[lane + 1] = 0;
+  if (pm_e | sp_e) {
+    const int h = lane == 0 ? 0 : HB + 1;
+    ax->push[h] = 0;
+    ax->spill[h] = 0;
+  }
+  __syncwarp();
+  st.need |= pm & st.freem;
+  // what leaves the tile: flags for the neighbouring tiles (the scheduler turns them into their activity)
+  if (__any_sync(FULL, (sp | pm_e | sp_e) != 0u)) {
+    __threadfence_block();
+    uint32_t d = 0;
+    if (sp & 1u) d |= DIR_W;
+    if (sp & 2u) d |= DIR_E;
+    if (lane == 0) d |= (pm_e ? DIR_N : 0u) | ((sp_e & 1u) ? DIR_NW : 0u) | ((sp_e & 2u) ? DIR_NE : 0u);
+    if (lane == 31) d |= (pm_e ? DIR_S : 0u) | ((sp_e & 1u) ? DIR_SW : 0u) | ((sp_e & 2u) ? DIR_SE : 0u);
+    d = __reduce_or_sync(FULL, d);
+    if (lane == 0) atomicOr(s_out, d);
+  }
+  return true;
+}
 
 template <int VARIANT>
 __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a, double *__restrict__ cost,
@@ -827,7 +974,12 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
     double lb = 0.0;
     unsigned long long left = INF_BITS;
     for (;;) {
-      while (sweep<1, VARIANT>(cs, cl, nullptr, wc.s_out, st, 0, 0, 0, lane, lb, wt)) {
+      if (a.compact) {
+        while (sweep_compact<VARIANT>(cs, cl, wc.aux, wc.s_out, st, lane, lb, wt)) {
+        }
+      } else {
+        while (sweep<1, VARIANT>(cs, cl, nullptr, wc.s_out, st, 0, 0, 0, lane, lb, wt)) {
+        }
       }
       unsigned long long mn = INF_BITS;
       for (uint32_t m = st.defer; m; m &= m - 1) {
@@ -898,6 +1050,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *cs_all = (double *)smem_raw;                                  // WT_WARPS x ROWS*S
   uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);          // WT_WARPS x ROWS*S (Dubins only)
+  warp_aux *aux_all = (warp_aux *)(cl_all + (VARIANT == HPP_VARIANT_DUBINS ? WT_WARPS * ROWS * S : 0));
   __shared__ unsigned long long s_gmin;
   __shared__ uint32_t s_mine, s_next, s_lnext, s_warp_cnt[32], s_outw[WT_WARPS], s_pref[WT_WARPS * 32];
   __shared__ double s_db[20];
@@ -922,6 +1075,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   warp_ctx wc;
   wc.cs_nv = cs_all + wid * ROWS * S;
   wc.cl_nv = cl_all + wid * ROWS * S;
+  wc.aux = aux_all + wid;
+  for (int i = lane; i < (int)(sizeof(warp_aux) / 4); i += 32) ((uint32_t *)wc.aux)[i] = 0u;
   wc.s_out = &s_outw[wid];
   wc.mbar = smem_u32(&s_mbar[wid]);
   wc.parity = 0;
@@ -1261,6 +1416,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_async_kernel(const __gr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *cs_all = (double *)smem_raw;
   uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);
+  warp_aux *aux_all = (warp_aux *)(cl_all + (VARIANT == HPP_VARIANT_DUBINS ? WT_WARPS * ROWS * S : 0));
   __shared__ uint32_t s_outw[WT_WARPS];
   __shared__ double s_db[20];
   __shared__ __align__(16) double2 s_rs[2];
@@ -1278,6 +1434,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_async_kernel(const __gr
   warp_ctx wc;
   wc.cs_nv = cs_all + wid * ROWS * S;
   wc.cl_nv = cl_all + wid * ROWS * S;
+  wc.aux = aux_all + wid;
+  for (int i = lane; i < (int)(sizeof(warp_aux) / 4); i += 32) ((uint32_t *)wc.aux)[i] = 0u;
   wc.s_out = &s_outw[wid];
   wc.mbar = smem_u32(&s_mbar[wid]);
   wc.parity = 0;
@@ -1570,7 +1728,7 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   size_t smem;
   const void *kern;
   if constexpr (NB == 1) {
-    smem = (size_t)WT_WARPS * C::ROWS * C::S * (sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? 1 : 0)) + 16;
+    smem = (size_t)WT_WARPS * (C::ROWS * C::S * (sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? 1 : 0)) + sizeof(warp_aux)) + 16;
     kern = small ? (const void *)heur_warp_kernel<VARIANT, 4>
                  : (many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
                          : (const void *)heur_warp_kernel<VARIANT, 16>);
@@ -1674,6 +1832,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   // window width: wide windows = fewer rounds (latency of a lone field), narrow = fewer re-evaluations (throughput)
   a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 384.0 : 64.0) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 16.0);
+  a.compact = (int)env_double("HPP_HEUR_COMPACT", 1);
   const bool debug = getenv("HPP_HEUR_DEBUG") != nullptr;
   const size_t prof_n = ((size_t)c->sm_count * 8 + n_fields) * 8 + 8;
   if (debug) {
@@ -1713,7 +1872,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
       HPP_CUDA(c, cudaMemsetAsync(a.aq + AQ_HDR + n_tiles, 0xff, sizeof(uint32_t) * ring, c->stream));
       heur_async_seed_kernel<NB><<<1, 32, 0, c->stream>>>(a.aq, d_goals, tiles_x, n_tiles, a.delta);
       HPP_LAUNCHED(c);
-      const size_t smem = (size_t)16 * C::ROWS * C::S * (sizeof(double) + (variant == HPP_VARIANT_DUBINS ? 1 : 0)) + 16;
+      const size_t smem = (size_t)16 * (C::ROWS * C::S * (sizeof(double) + (variant == HPP_VARIANT_DUBINS ? 1 : 0)) + sizeof(warp_aux)) + 16;
       const void *kern = variant == HPP_VARIANT_RS ? (const void *)heur_async_kernel<HPP_VARIANT_RS, 16>
                                                    : (const void *)heur_async_kernel<HPP_VARIANT_DUBINS, 16>;
       HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
