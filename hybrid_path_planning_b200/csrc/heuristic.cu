@@ -719,11 +719,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // per-warp scratch of the compacted sweep, in shared memory (all zero between sweeps)
 #define WAUX_LIST 128
 struct warp_aux {
-  uint32_t push[HB + 2];            // row r (-1..32) at [r + 1]: cells (columns 0..31) a change of this sweep may improve
-  uint32_t spill[HB + 2];           // same for the columns just outside the tile: bit 0 = column -1, bit 1 = column 32
-  uint32_t low[HB];                 // cells improved below the bound (their deferred bit is cleared)
-  uint32_t high[HB];                // cells improved at or above the bound (deferred)
-  uint16_t list[WAUX_LIST];         // the sweep's needed cells, row << 5 | column
+  uint4 row[HB];             // per row: .x = cells a change of this sweep may improve, .y = cells improved below the
+                             // bound (their deferred bit is cleared), .z = cells improved at or above it (deferred)
+  uint16_t list[WAUX_LIST];  // the sweep's needed cells, row << 5 | column
 };
 
 struct warp_ctx {
@@ -738,18 +736,25 @@ struct warp_ctx {
 // the three neighbours (columns x-1, x, x+1; m3 bit 0 = column x-1) of one row as a mask of the columns 0..31
 __device__ __forceinline__ uint32_t row_mask3(int x, uint32_t m3) { return x >= 1 ? (m3 << (x - 1)) : (m3 >> 1); }
 
-// an improved cell (row r, column x) below the bound: its neighbours that may improve (nmask) go to their rows' words
-__device__ __forceinline__ void aux_deliver(warp_aux *ax, int r, int x, uint32_t k) {
+// an improved cell (row r, column x) below the bound: its neighbours that may improve (nmask k: bit 0 NW, 1 N, 2 NE,
+// 3 W, 4 E, 5 SW, 6 S, 7 SE) go to their rows' words; what lies outside the tile becomes a flag for that neighbour tile
+__device__ __forceinline__ void aux_deliver(warp_aux *ax, uint32_t *s_out, int r, int x, uint32_t k) {
   const uint32_t up = k & 7u, own = ((k >> 3) & 1u) | ((k >> 2) & 4u), dn = (k >> 5) & 7u;
-  atomicOr(&ax->push[r], row_mask3(x, up));
-  atomicOr(&ax->push[r + 1], row_mask3(x, own));
-  atomicOr(&ax->push[r + 2], row_mask3(x, dn));
-  atomicOr(&ax->low[r], 1u << x);
-  if (x == 0 || x == 31) {  // columns just outside the tile
-    const uint32_t sh = x == 0 ? 0u : 2u, bit = x == 0 ? 1u : 2u;
-    if ((up >> sh) & 1u) atomicOr(&ax->spill[r], bit);
-    if ((own >> sh) & 1u) atomicOr(&ax->spill[r + 1], bit);
-    if ((dn >> sh) & 1u) atomicOr(&ax->spill[r + 2], bit);
+  atomicOr(&ax->row[r].x, row_mask3(x, own));
+  atomicOr(&ax->row[r].y, 1u << x);
+  if (r > 0) atomicOr(&ax->row[r - 1].x, row_mask3(x, up));
+  if (r < HB - 1) atomicOr(&ax->row[r + 1].x, row_mask3(x, dn));
+  if (r == 0 || r == HB - 1 || x == 0 || x == 31) {
+    uint32_t d = 0;
+    if (r == 0) d |= ((up & 2u) ? DIR_N : 0u) | ((up & 1u) ? (x == 0 ? DIR_NW : DIR_N) : 0u) | ((up & 4u) ? (x == 31 ? DIR_NE : DIR_N) : 0u);
+    else if (x == 0 && (up & 1u)) d |= DIR_W;
+    else if (x == 31 && (up & 4u)) d |= DIR_E;
+    if (r == HB - 1) d |= ((dn & 2u) ? DIR_S : 0u) | ((dn & 1u) ? (x == 0 ? DIR_SW : DIR_S) : 0u) | ((dn & 4u) ? (x == 31 ? DIR_SE : DIR_S) : 0u);
+    else if (x == 0 && (dn & 1u)) d |= DIR_W;
+    else if (x == 31 && (dn & 4u)) d |= DIR_E;
+    if (x == 0 && (own & 1u)) d |= DIR_W;
+    if (x == 31 && (own & 4u)) d |= DIR_E;
+    if (d) atomicOr(s_out, d);
   }
 }
 
@@ -814,59 +819,33 @@ __device__ __forceinline__ bool sweep_compact(volatile double *cs, const volatil
     if (on0 && b0 < c0) {
       cs[e0] = b0;
       if (b0 < bound) {
-        aux_deliver(ax, r0, x0, k0);
+        aux_deliver(ax, s_out, r0, x0, k0);
       } else {
-        atomicOr(&ax->high[r0], 1u << x0);
+        atomicOr(&ax->row[r0].z, 1u << x0);
       }
     }
     if (on1 && b1 < c1) {
       cs[e1] = b1;
       if (b1 < bound) {
-        aux_deliver(ax, r1, x1, k1);
+        aux_deliver(ax, s_out, r1, x1, k1);
       } else {
-        atomicOr(&ax->high[r1], 1u << x1);
+        atomicOr(&ax->row[r1].z, 1u << x1);
       }
     }
     __syncwarp();
   }
   // back to the rows
-  const uint32_t low = ax->low[lane], high = ax->high[lane];
-  const uint32_t pm = ax->push[lane + 1], sp = ax->spill[lane + 1];
-  uint32_t pm_e = 0, sp_e = 0;  // the row above the tile (lane 0) / below it (lane 31)
-  if (lane == 0) {
-    pm_e = ax->push[0];
-    sp_e = ax->spill[0];
-  } else if (lane == 31) {
-    pm_e = ax->push[HB + 1];
-    sp_e = ax->spill[HB + 1];
+  const uint4 w = ax->row[lane];
+  __syncwarp();
+  if (w.x | w.y | w.z) {
+    ax->row[lane] = make_uint4(0u, 0u, 0u, 0u);
+    if (w.y | w.z) {
+      st.dirty = 1;
+      st.defer = (st.defer | w.z) & ~w.y;
+    }
+    st.need |= w.x & st.freem;
   }
   __syncwarp();
-  if (low | high) {
-    ax->low[lane] = 0;
-    ax->high[lane] = 0;
-    st.dirty = 1;
-    st.defer = (st.defer | high) & ~low;
-  }
-  if (pm) ax->push[lane + 1] = 0;
-  if (sp) ax->spill[lane + 1] = 0;
-  if (pm_e | sp_e) {
-    const int h = lane == 0 ? 0 : HB + 1;
-    ax->push[h] = 0;
-    ax->spill[h] = 0;
-  }
-  __syncwarp();
-  st.need |= pm & st.freem;
-  // what leaves the tile: flags for the neighbouring tiles (the scheduler turns them into their activity)
-  if (__any_sync(FULL, (sp | pm_e | sp_e) != 0u)) {
-    __threadfence_block();
-    uint32_t d = 0;
-    if (sp & 1u) d |= DIR_W;
-    if (sp & 2u) d |= DIR_E;
-    if (lane == 0) d |= (pm_e ? DIR_N : 0u) | ((sp_e & 1u) ? DIR_NW : 0u) | ((sp_e & 2u) ? DIR_NE : 0u);
-    if (lane == 31) d |= (pm_e ? DIR_S : 0u) | ((sp_e & 1u) ? DIR_SW : 0u) | ((sp_e & 2u) ? DIR_SE : 0u);
-    d = __reduce_or_sync(FULL, d);
-    if (lane == 0) atomicOr(s_out, d);
-  }
   return true;
 }
 
