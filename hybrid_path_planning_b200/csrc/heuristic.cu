@@ -1810,7 +1810,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.n_fields = (int)n_fields;
   // window width: wide windows = fewer rounds (latency of a lone field), narrow = fewer re-evaluations (throughput)
   a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 384.0 : 64.0) : 2.0 * C::T);
-  a.delta_in = env_double("HPP_HEUR_DELTA_IN", 16.0);
+  a.delta_in = env_double("HPP_HEUR_DELTA_IN", 32.0);
   a.compact = (int)env_double("HPP_HEUR_COMPACT", 1);
   const bool debug = getenv("HPP_HEUR_DEBUG") != nullptr;
   const size_t prof_n = ((size_t)c->sm_count * 8 + n_fields) * 8 + 8;
