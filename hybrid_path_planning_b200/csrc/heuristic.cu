@@ -950,9 +950,7 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
     }
     // relax under the bound in sub-windows (see heur_persist_kernel); everything is warp-local
     const int ebase = S + 2;
-    double lb = 0.0;
-    unsigned long long left = INF_BITS;
-    for (;;) {
+    auto run_sweeps = [&](double lb) {
       if (a.compact) {
         while (sweep_compact<VARIANT>(cs, cl, wc.aux, wc.s_out, st, lane, lb, wt)) {
         }
@@ -960,33 +958,70 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
         while (sweep<1, VARIANT>(cs, cl, nullptr, wc.s_out, st, 0, 0, 0, lane, lb, wt)) {
         }
       }
-      unsigned long long mn = INF_BITS;
+    };
+    // One pass over my row's deferred cells: those below lb are released (returned mask), the cheapest of the others
+    // is returned in `rest` (bit pattern; costs are non-negative, so the integer order is the numeric order).
+    auto scan_deferred = [&](double lb, unsigned long long &rest) {
+      uint32_t rel = 0;
+      rest = INF_BITS;
       for (uint32_t m = st.defer; m; m &= m - 1) {
         const int x = __ffs(m) - 1;
-        const unsigned long long v = (unsigned long long)__double_as_longlong(cs[ebase + lane * S + x]);
-        mn = v < mn ? v : mn;
+        const double v = cs[ebase + lane * S + x];
+        if (v < lb) rel |= 1u << x;
+        else {
+          const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+          rest = vb < rest ? vb : rest;
+        }
       }
+      return rel;
+    };
+    auto warp_min = [&](unsigned long long mn) {
       for (int d = 16; d; d >>= 1) {
         const unsigned long long o = __shfl_xor_sync(FULL, mn, d);
         mn = o < mn ? o : mn;
       }
-      left = mn;
-      const double gm = __longlong_as_double((long long)mn);
-      if (mn == INF_BITS || !(gm < bound)) break;
-      lb = gm + a.delta_in;
-      if (lb > bound) lb = bound;
-      uint32_t rel = 0;
-      push3 ps = {0ull, 0ull, 0ull};
-      for (uint32_t m = st.defer; m; m &= m - 1) {
-        const int x = __ffs(m) - 1;
-        if (cs[ebase + lane * S + x] < lb) {
-          rel |= 1u << x;
-          add_push(ps, x, 0xffu);
-        }
-      }
+      return mn;
+    };
+    // released cells may improve all eight neighbours (the exact set is not known any more): need bits of my row and
+    // of the rows above / below, flags for the neighbouring tiles
+    auto release = [&](uint32_t rel) {
       st.defer &= ~rel;
+      const uint32_t h = rel | (rel << 1) | (rel >> 1);
+      uint32_t from_below = __shfl_down_sync(FULL, h, 1), from_above = __shfl_up_sync(FULL, h, 1);
+      if (lane == 31) from_below = 0;
+      if (lane == 0) from_above = 0;
+      st.need |= ((rel << 1) | (rel >> 1) | from_below | from_above) & st.freem;
+      uint32_t d = 0;
+      if (rel & 1u) d |= DIR_W;
+      if (rel >> 31) d |= DIR_E;
+      if (lane == 0 && rel) d |= DIR_N | ((rel & 1u) ? DIR_NW : 0u) | ((rel >> 31) ? DIR_NE : 0u);
+      if (lane == 31 && rel) d |= DIR_S | ((rel & 1u) ? DIR_SW : 0u) | ((rel >> 31) ? DIR_SE : 0u);
+      d = __reduce_or_sync(FULL, d);
+      if (d && lane == 0) atomicOr(wc.s_out, d);
+    };
+    // The first sub-window starts at the cheapest deferred cost; after that the lower bound moves in steps of delta_in
+    // (one pass over the deferred cells per step), jumping over empty ranges.
+    unsigned long long left = INF_BITS;
+    run_sweeps(0.0);
+    double lb = 0.0;
+    for (;;) {
+      unsigned long long rest;
+      uint32_t rel = scan_deferred(lb, rest);
+      if (!__any_sync(FULL, rel != 0)) {
+        // nothing below lb: every deferred cost is in `rest` (no sweep ran since), so its minimum is exact
+        const unsigned long long mn = warp_min(rest);
+        left = mn;
+        const double gm = __longlong_as_double((long long)mn);
+        if (mn == INF_BITS || !(gm < bound)) break;
+        lb = gm + a.delta_in;
+        if (lb > bound) lb = bound;
+        rel = scan_deferred(lb, rest);
+      }
+      release(rel);
       __syncwarp();
-      if (__any_sync(FULL, rel != 0)) propagate<1>(ps, st, nullptr, wc.s_out, 0, 0, lane);
+      run_sweeps(lb);
+      lb += a.delta_in;
+      if (lb > bound) lb = bound;
     }
     // write back
     __stcg(dmask + (size_t)tile * 32 + lane, st.defer);
