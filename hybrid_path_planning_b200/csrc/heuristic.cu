@@ -2011,11 +2011,13 @@ extern "C" hpp_status hpp_heuristic_batch(hpp_map *m, int variant, const int32_t
   size_t free_b = 0, total_b = 0;
   HPP_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   const size_t field_b = m->n * sizeof(double);
-  // four chunks of >= 32 fields: a 32-field launch (~75 ms at 4096^2) takes about as long as its 4.3 GB copy-out
+  // chunks of >= 16 fields: the relaxation of a chunk takes about as long as its copy-out (2.4 ms per 134 MB field over
+  // PCIe), and the first chunk's relaxation is the only part that no copy overlaps
   size_t chunk = n_fields;
-  if (n_fields >= 64) {
-    chunk = (n_fields + 3) / 4;
-    if (chunk < 32) chunk = 32;
+  const size_t n_chunks = (size_t)env_double("HPP_HEUR_CHUNKS", 8);
+  if (n_fields >= 64 && n_chunks > 1) {
+    chunk = (n_fields + n_chunks - 1) / n_chunks;
+    if (chunk < 16) chunk = 16;
   }
   const size_t have = c->d_scratch_bytes[3] + free_b / 2;
   const int nbuf = chunk < n_fields ? 2 : 1;
