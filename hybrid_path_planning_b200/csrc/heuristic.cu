@@ -1736,9 +1736,9 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   // so that five fields share an SM instead of one.
   const bool many = NB == 1 && VARIANT == HPP_VARIANT_RS && ctas_per_field_hint <= 1 && a.n_fields >= c->sm_count / 2;
   const int warps_env = (int)env_double("HPP_HEUR_WARPS", 0);
-  const bool small = NB == 1 && ctas_per_field_hint <= 1 && a.n_fields >= 4 * c->sm_count &&
-                     (warps_env ? warps_env == 4 : a.n_tiles <= 256);  // up to 512^2 cells (measured: 128^2 2.3x,
-                                                                        // 256^2 1.5x, 512^2 1.06x, 1024^2 0.88x)
+  const bool small = NB == 1 && ctas_per_field_hint <= 1 &&
+                     (warps_env ? warps_env == 4 : (a.n_fields >= 4 * c->sm_count && a.n_tiles <= 256));
+  // (up to 512^2 cells; measured: 128^2 2.3x, 256^2 1.5x, 512^2 1.06x, 1024^2 0.88x)
   const int WT_WARPS = small ? 4 : (many ? 20 : 16);
   const int threads = NB == 1 ? WT_WARPS * 32 : C::THREADS;
   size_t smem;

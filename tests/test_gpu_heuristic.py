@@ -217,3 +217,34 @@ def test_heuristic_one_cta_per_field_list_schedule(ctx, monkeypatch):
         g = tuple(int(v) for v in goals[f])
         assert bits_equal(cost[f].cpu().numpy(), O.heuristic_rs(occ, g, (0, 0), quirks=False)[0]), f
     m.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_heuristic_sweep_modes_and_cta_shapes_agree(ctx, monkeypatch, variant):
+    """the warp-tile kernel's two sweep forms (HPP_HEUR_COMPACT=1: needed cells compacted over the lanes, =0: row-wise),
+    every sub-window width, and the 4-warp CTAs that big batches on small maps use (HPP_HEUR_WARPS=4) give the oracle's
+    bits -- on a map with long straight fronts (empty), thin diagonal ones (blocks) and an odd width (no TMA staging)"""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    cases = [(np.zeros((96, 130), np.int8), (5, 90)), (block_map(161, 131, 0.2, 4, seed=7), (80, 65)),
+             (block_map(224, 192, 0.3, 8, seed=8), (3, 3))]
+    for occ, goal in cases:
+        occ = occ.copy()
+        occ[goal[1], goal[0]] = 0
+        want = O.heuristic_rs(occ, goal, (0, 0), quirks=False)[0] if variant == 0 else O.heuristic_dubins(occ, goal)
+        m = hpp.Map(ctx, occ, 0.2)
+        for compact in ("1", "0"):
+            for din in ("4", "32", "1000"):
+                monkeypatch.setenv("HPP_HEUR_COMPACT", compact)
+                monkeypatch.setenv("HPP_HEUR_DELTA_IN", din)
+                got = m.heuristic_rs(goal, (0, 0))[0] if variant == 0 else m.heuristic_dubins(goal)[0]
+                assert bits_equal(got, want), (occ.shape, compact, din)
+        monkeypatch.delenv("HPP_HEUR_DELTA_IN")
+        monkeypatch.setenv("HPP_HEUR_COMPACT", "1")
+        monkeypatch.setenv("HPP_HEUR_WARPS", "4")
+        monkeypatch.setenv("HPP_HEUR_GROUP", "1")
+        got = m.heuristic_rs(goal, (0, 0))[0] if variant == 0 else m.heuristic_dubins(goal)[0]
+        assert bits_equal(got, want), (occ.shape, "4 warps")
+        monkeypatch.delenv("HPP_HEUR_WARPS")
+        monkeypatch.delenv("HPP_HEUR_GROUP")
+        m.close()
