@@ -19,6 +19,7 @@
 // Child trajectories are not stored: they are re-rolled from (parent state, command) at back-track time.
 // The heuristic field of every distinct goal cell comes from K3 (hpp_heuristic_batch_dev) beforehand.
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "expand.cuh"
@@ -668,6 +669,12 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   if (n == 0) return HPP_OK;
   if (n > 0x7fffffff) return HPP_ERR_ARG;
   hpp_ctx *c = m->ctx;
+  const bool timing = getenv("HPP_PLAN_TIMING") != nullptr;
+  auto t_now = [] { return std::chrono::steady_clock::now(); };
+  auto t_us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  const auto t0 = t_now();
   HPP_CUDA(c, cudaSetDevice(c->device));
   const int W = m->g.W, H = m->g.H;
 
@@ -704,14 +711,21 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   pc.table_mask = slots - 1;
 
   // device buffers: inputs, per-warp pools, outputs, heuristic fields for a chunk of goal cells
-  size_t free_b = 0, total_b = 0;
-  HPP_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  // free device memory bounds the pools and the field chunk; small batches reuse the answer of the last large one
+  size_t free_b = c->plan_free_bytes, total_b = 0;
+  if (free_b == 0 || n > 64) {
+    HPP_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    c->plan_free_bytes = free_b;
+  }
   const size_t per_warp = (size_t)pc.max_nodes * (sizeof(pnode) + 12) + (size_t)slots * 4;
-  int occ_blocks = 0;
-  if (variant == HPP_VARIANT_RS)
-    HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, plan_kernel<HPP_VARIANT_RS>, PLAN_WARPS * 32, 0));
-  else
-    HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, plan_kernel<HPP_VARIANT_DUBINS>, PLAN_WARPS * 32, 0));
+  int occ_blocks = c->plan_occ_blocks[variant];
+  if (occ_blocks == 0) {
+    if (variant == HPP_VARIANT_RS)
+      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, plan_kernel<HPP_VARIANT_RS>, PLAN_WARPS * 32, 0));
+    else
+      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, plan_kernel<HPP_VARIANT_DUBINS>, PLAN_WARPS * 32, 0));
+    c->plan_occ_blocks[variant] = occ_blocks;
+  }
   if (occ_blocks < 1) occ_blocks = 1;
   size_t max_warps = (size_t)c->sm_count * occ_blocks;  // CTAs (= queries in flight): one resident wave, persistent
   if (max_warps > n) max_warps = n;
@@ -724,6 +738,7 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   const int grid = (int)max_warps;
   const size_t n_warps = (size_t)grid;  // one node pool / heap / table per CTA
 
+  const auto t1 = t_now();
   char *d_pool = nullptr, *d_io = nullptr;
   double *d_fields = nullptr;
   const size_t io_bytes = n * 48 + n * 8 + n * sizeof(hpp_plan) + traj_cap * 40 + 64;
@@ -732,7 +747,10 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   cudaError_t e = cudaSuccess;
   hpp_status st = hpp_scratch(c, 1, n_warps * per_warp + 256, (void **)&d_pool);
   if (st == HPP_OK) st = hpp_scratch(c, 0, io_bytes, (void **)&d_io);
-  if (st != HPP_OK) st = HPP_ERR_NOMEM;
+  if (st != HPP_OK) {
+    st = HPP_ERR_NOMEM;
+    c->plan_free_bytes = 0;  // the cached figure was stale: ask again next time
+  }
   double *d_starts = nullptr, *d_goals = nullptr, *d_traj = nullptr;
   int *d_qids = nullptr, *d_fq = nullptr;
   hpp_plan *d_plans = nullptr;
@@ -781,13 +799,18 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
       if (nf > fields_alloc) {
         if (hpp_scratch(c, 3, nf * field_bytes, (void **)&d_fields) != HPP_OK) {
           st = HPP_ERR_NOMEM;
+          c->plan_free_bytes = 0;
           d_fields = nullptr;
           break;
         }
         fields_alloc = nf;
       }
+      const auto t2 = t_now();
       st = hpp_heuristic_batch_dev(m, variant, chunk_goals.data(), nf, d_fields, nullptr);
       if (st != HPP_OK) break;
+      const auto t3 = t_now();
+      if (timing) fprintf(stderr, "[plan timing] setup %.0f us, alloc+h2d %.0f us, heuristic (returns after the kernel) %.0f us\n",
+                          t_us(t0, t1), t_us(t1, t2), t_us(t2, t3));
       cudaMemcpyAsync(d_fq + q0, fq.data() + q0, (q1 - q0) * 4, cudaMemcpyHostToDevice, c->stream);
       cudaMemsetAsync(d_cursor + 1, 0, 8, c->stream);  // the kernel's query counter
       if (variant == HPP_VARIANT_RS)
@@ -800,7 +823,9 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
             d_fields, d_nodes, d_keys, d_idx, d_table, d_plans, d_traj, traj_cap, d_cursor, d_prof);
       c->launches++;
       e = cudaGetLastError();
+      const auto t4 = t_now();
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // fq / chunk_goals are reused by the next chunk
+      if (timing) fprintf(stderr, "[plan timing] plan kernel + sync %.0f us\n", t_us(t4, t_now()));
       if (e != cudaSuccess) {
         snprintf(c->err, sizeof c->err, "plan kernel failed: %s", cudaGetErrorString(e));
         st = HPP_ERR_CUDA;
@@ -842,5 +867,6 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
     }
   }
   cudaStreamSynchronize(c->stream);
+  if (timing) fprintf(stderr, "[plan timing] total %.0f us\n", t_us(t0, t_now()));
   return st;
 }
