@@ -50,8 +50,15 @@ class HybridAstarT {
   hpp_quirk_report report_{};
 };
 
-using HybridAstar = HybridAstarT<HPP_VARIANT_RS>;
+// `HybridAstar` is the Reeds-Shepp planner; the dubins_hybrid_star package defines HPP_SHELL_DEFAULT_DUBINS before
+// including this header (its forwarding HybridAstar.h does), which makes `HybridAstar` the Dubins planner there.
+using HybridAstarReedsShepp = HybridAstarT<HPP_VARIANT_RS>;
 using HybridAstarDubins = HybridAstarT<HPP_VARIANT_DUBINS>;
+#ifdef HPP_SHELL_DEFAULT_DUBINS
+using HybridAstar = HybridAstarDubins;
+#else
+using HybridAstar = HybridAstarReedsShepp;
+#endif
 
 // drop-in for map_inflate_node::InflateMap + CreateInflatedOccupancyGrid (MI/src/map_inflate_node.cpp:17,:118-161):
 // occupancy in, inflated occupancy out (same geometry), through hpp_inflate.

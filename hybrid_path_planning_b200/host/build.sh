@@ -6,3 +6,24 @@ g++ -std=c++17 -O2 -fPIC -Wall -shared -o ../libhpp_host.so shells.cpp -L.. -l:l
 echo "built hybrid_path_planning_b200/libhpp_host.so"
 g++ -std=c++17 -O2 -Wall -o ../shell_demo shell_demo.cpp -L.. -l:libhpp_host.so -l:libhpp_b200.so -Wl,-rpath,'$ORIGIN'
 echo "built hybrid_path_planning_b200/shell_demo"
+
+# Drop-in check (only where the reference checkout is present): the reference's UNMODIFIED planner nodes compiled against
+# the shells inside the stand-in ROS of tests/ros_mock; the binaries travel to the GPU box for tests/test_gpu_dropin_node.py.
+CXX="${CXX:-g++}"
+CXXFLAGS="-std=c++17 -O2 -w"
+REF="${HPP_REF:-/root/reference}"
+MOCK="$(cd ../../tests/ros_mock && pwd)"
+if [ -f "$REF/reeds_shepp_hybrid_astar/src/main_path_planning.cpp" ] && [ -d "$MOCK" ]; then
+  for pkg in rs:reeds_shepp_hybrid_astar db:dubins_hybrid_star; do
+    tag="${pkg%%:*}"; dir="${pkg##*:}"
+    tmp="$(mktemp -d)"
+    cp "$MOCK/dropin_$tag/"*.h "$tmp/"
+    cp "$REF/$dir/include/main_path_planning.h" "$tmp/"      # temporary, outside the repository
+    $CXX $CXXFLAGS -Dmain=reference_node_main -I"$tmp" -I"$MOCK/include" -I. -I../../include \
+      -c "$REF/$dir/src/main_path_planning.cpp" -o "$tmp/node.o"
+    $CXX $CXXFLAGS -I"$tmp" -I"$MOCK/include" -I. -I../../include "$MOCK/node_harness.cpp" "$tmp/node.o" \
+      -L.. -l:libhpp_host.so -l:libhpp_b200.so -Wl,-rpath,'$ORIGIN' -o "../ref_node_$tag"
+    rm -rf "$tmp"
+    echo "built hybrid_path_planning_b200/ref_node_$tag (reference node source, unmodified, on the shells)"
+  done
+fi
