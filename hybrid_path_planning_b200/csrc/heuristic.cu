@@ -788,7 +788,7 @@ __device__ __forceinline__ bool sweep_compact(volatile double *cs, const volatil
   HPP_COUNT(st.c_sweeps++; st.c_imp += (total + 63) >> 6; st.c_on += total;)
   // rows with many needed cells (a front along the row) are written by the whole warp, one lane per column; the
   // others by their own lane, one cell per step
-  uint32_t heavy = __ballot_sync(FULL, fits && cnt > 4);
+  uint32_t heavy = __ballot_sync(FULL, fits && cnt > 8);
   while (heavy) {
     const int r = __ffs(heavy) - 1;
     heavy &= heavy - 1;
@@ -797,7 +797,7 @@ __device__ __forceinline__ bool sweep_compact(volatile double *cs, const volatil
     if ((m >> lane) & 1u) ax->list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((r << 5) | lane);
   }
   if (fits) {
-    if (cnt <= 4) {
+    if (cnt <= 8) {
       int pos = inc - cnt;
       for (uint32_t m = st.need; m; m &= m - 1) ax->list[pos++] = (uint16_t)((lane << 5) | (__ffs(m) - 1));
     }
