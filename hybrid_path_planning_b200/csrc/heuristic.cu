@@ -1846,7 +1846,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.n_tiles = n_tiles;
   a.n_fields = (int)n_fields;
   // window width: wide windows = fewer rounds (latency of a lone field), narrow = fewer re-evaluations (throughput)
-  a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 384.0 : 64.0) : 2.0 * C::T);
+  a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 768.0 : (n_fields < 64 ? 128.0 : 64.0)) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 32.0);
   a.compact = (int)env_double("HPP_HEUR_COMPACT", 1);
   const bool debug = getenv("HPP_HEUR_DEBUG") != nullptr;
