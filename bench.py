@@ -324,7 +324,7 @@ def ours_arm(args):
                 "fields_per_call": Fe,
                 "checksum": checksum},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"heur_warp_kernel (one persistent cooperative launch, {F} fields, one warp per 32x32 tile)",
+        "roofline": {"bound": "hbm", "kernel": f"heur_warp_kernel (one persistent launch, {F} fields, one CTA of 20 warps per field, one warp per 32x32 tile, compacted sweeps)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes": HEUR_BYTES_PER_CELL * n * F,
                      "ms": heur_ms,
