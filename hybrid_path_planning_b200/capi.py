@@ -100,6 +100,7 @@ def lib():
             "hpp_rs_shot": [vp, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)],
             "hpp_dubins_shot": [vp, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)],
             "hpp_rs_all_paths": [vp, vp, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, sz],
+            "hpp_test_heap_ops": [vp, vp, vp, sz, vp, vp],
             "hpp_dubins_path": [vp, vp, vp, dbl, dbl, vp, vp, vp, vp, sz],
             "hpp_plan_batch": [vp, C.c_int, vp, vp, sz, vp, vp, sz, C.POINTER(sz)],
         }
@@ -175,6 +176,17 @@ class Context:
 
     def inflate_dev(self, occ_dev, W, H, resolution, radius, out_dev):
         self.check(self.L.hpp_inflate_dev(self.h, _ptr(occ_dev), W, H, float(resolution), float(radius), _ptr(out_dev)))
+
+    def test_heap_ops(self, keys, ops):
+        """unit hook: (payload of every pop, index of the first operation after which the warp-collective heap differs
+        from the one-thread replay, -1 if never)"""
+        keys = np.ascontiguousarray(keys, np.float64)
+        ops = np.ascontiguousarray(ops, np.int32)
+        pops = np.full(len(ops), -1, np.int32)
+        bad = C.c_int64(0)
+        self.check(self.L.hpp_test_heap_ops(self.h, keys.ctypes.data, ops.ctypes.data, len(ops), pops.ctypes.data,
+                                            C.byref(bad)))
+        return pops, bad.value
 
     def rs_all_paths(self, s, g, maxc, step=1.0, max_paths=48, samples_cap=400000):
         s3 = (C.c_double * 3)(*s)

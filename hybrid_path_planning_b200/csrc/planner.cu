@@ -662,6 +662,61 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
   }
 }
 
+// ---- unit hook: the warp-collective heap against the one-thread replay on the same operations (one warp)
+__global__ void heap_ops_kernel(const double *__restrict__ keys, const int *__restrict__ ops, int n_ops,
+                                double *ka, int *ia, double *kb, int *ib, int *pops, long long *first_mismatch) {
+  const int lane = threadIdx.x & 31;
+  int na = 0, nb = 0;
+  long long bad = -1;
+  for (int i = 0; i < n_ops; i++) {
+    const int op = ops[i];
+    int pa = -1, pb = -1;
+    if (op >= 0) {
+      if (lane == 0) gheap_push(ka, ia, na, keys[op], i);
+      na = __shfl_sync(0xffffffffu, na, 0);
+      __syncwarp();
+      gheap_push_warp(kb, ib, nb, keys[op], i);
+    } else if (na > 0) {
+      if (lane == 0) pa = gheap_pop(ka, ia, na);
+      na = __shfl_sync(0xffffffffu, na, 0);
+      pa = __shfl_sync(0xffffffffu, pa, 0);
+      __syncwarp();
+      pb = gheap_pop_warp(kb, ib, nb);
+    }
+    __syncwarp();
+    if (pops && lane == 0) pops[i] = pb;
+    // the two heaps must be the same arrays after every operation
+    bool diff = pa != pb || na != nb;
+    for (int j = lane; j < na && !diff; j += 32) diff = ka[j] != kb[j] || ia[j] != ib[j];
+    if (__any_sync(0xffffffffu, diff) && bad < 0) bad = i;
+    __syncwarp();
+  }
+  if (lane == 0) *first_mismatch = bad;
+}
+
+extern "C" hpp_status hpp_test_heap_ops(hpp_ctx *c, const double *keys, const int32_t *ops, size_t n_ops,
+                                        int32_t *pops_out, int64_t *first_mismatch) {
+  if (!c || !keys || !ops || !first_mismatch || n_ops == 0 || n_ops > (1u << 24)) return HPP_ERR_ARG;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  void *buf;
+  const size_t n = n_ops;
+  hpp_status st = hpp_scratch(c, 1, n * (8 + 4 + 8 + 4 + 8 + 4 + 4) + 64, &buf);
+  if (st != HPP_OK) return st;
+  double *d_keys = (double *)buf, *ka = d_keys + n, *kb = ka + n;
+  int *d_ops = (int *)(kb + n), *ia = d_ops + n, *ib = ia + n, *d_pops = ib + n;
+  long long *d_bad = (long long *)(((uintptr_t)(d_pops + n) + 7) & ~(uintptr_t)7);
+  HPP_CUDA(c, cudaMemcpyAsync(d_keys, keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+  HPP_CUDA(c, cudaMemcpyAsync(d_ops, ops, n * 4, cudaMemcpyHostToDevice, c->stream));
+  heap_ops_kernel<<<1, 32, 0, c->stream>>>(d_keys, d_ops, (int)n, ka, ia, kb, ib, d_pops, d_bad);
+  HPP_LAUNCHED(c);
+  long long bad = 0;
+  if (pops_out) HPP_CUDA(c, cudaMemcpyAsync(pops_out, d_pops, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  HPP_CUDA(c, cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, c->stream));
+  HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  *first_mismatch = bad;
+  return HPP_OK;
+}
+
 extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *starts, const double *goals, size_t n,
                                      hpp_plan *plans, double *traj, size_t traj_cap, size_t *traj_used) {
   if (!m || variant < 0 || variant > 1 || (n && (!starts || !goals || !plans)) || (traj_cap && !traj)) return HPP_ERR_ARG;

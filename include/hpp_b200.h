@@ -225,6 +225,13 @@ hpp_status hpp_dubins_path(hpp_ctx *ctx, const double start_xyh[3], const double
                            double step_size, double *length, char mode[3], int32_t *n_samples,
                            double *samples_xyyaw, size_t samples_cap);
 
+/* unit-level hook for the planner's open list: replays n_ops operations (op[i] >= 0: push key[op[i]] with payload
+ * i; op[i] < 0: pop) twice on the device -- with the one-thread libstdc++ heap replay and with the warp-collective
+ * pop / push the planner kernel uses -- and reports the first operation after which the two heaps or the popped
+ * payloads differ (-1: identical throughout).  pops_out (n_ops ints, may be NULL): payload of every pop, -1 elsewhere. */
+hpp_status hpp_test_heap_ops(hpp_ctx *ctx, const double *keys, const int32_t *ops, size_t n_ops, int32_t *pops_out,
+                             int64_t *first_mismatch);
+
 /* ---------------------------------------------------------------- whole queries
  * Replaces HybridAstar::run (RS/include/HybridAstar.h:47, RS/src/HybridAstar.cpp:553-729;
  * DB/src/HybridAstar.cpp:315-496) for a batch of independent start/goal queries on one map: heuristic

@@ -97,3 +97,32 @@ def test_plan_batch_shared_goal_and_failure_convention(ctx):
         tr = traj[int(plans[i]["traj_offset"])]
         assert np.array_equal(tr, w["traj"][0])
     m.close()
+
+
+def test_open_list_warp_heap_matches_libstdcxx_replay(ctx):
+    """the planner's warp-collective pop_heap / push_heap (four levels per memory round trip, whole ancestor chain at
+    once) leave exactly the arrays of the one-thread libstdc++ replay after every operation -- on A*-like traffic
+    (bursts of pushes with many equal keys, then a pop), on heaps that cross level boundaries, and on drains to empty --
+    and the popped payloads follow the comparator's order with ties resolved identically"""
+    rng = np.random.default_rng(5)
+    for n_keys, levels, burst in ((200, 4, 3), (5000, 16, 26), (40000, 64, 26), (3000, 10 ** 9, 7)):
+        keys = rng.integers(0, levels, n_keys).astype(np.float64) * 0.5
+        keys[rng.integers(0, n_keys, n_keys // 50)] = np.inf
+        ops, size, k = [], 0, 0
+        while k < n_keys:
+            b = int(rng.integers(1, burst + 1))
+            for _ in range(min(b, n_keys - k)):
+                ops.append(k)
+                k += 1
+                size += 1
+            for _ in range(int(rng.integers(0, 3))):
+                ops.append(-1)
+                size = max(0, size - 1)
+        ops += [-1] * (size + 3)                     # drain (three pops on the empty heap are ignored)
+        pops, bad = ctx.test_heap_ops(keys, np.array(ops, np.int32))
+        assert bad == -1, (n_keys, levels, bad)
+        popped = pops[pops >= 0]
+        assert len(popped) == n_keys and len(set(popped.tolist())) == n_keys
+        # keys come out in non-decreasing order between pushes of smaller keys: check the drain at the end
+        drain = keys[np.array(ops)[popped[-size:]]] if size else np.array([])
+        assert np.all(np.diff(drain[np.isfinite(drain)]) >= 0)
