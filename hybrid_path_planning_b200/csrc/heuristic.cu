@@ -29,6 +29,7 @@
 //     the host launches once and never polls.  Batches of fields are split over independent CTA groups.
 // Costs are fp64 with exactly the reference's additions (library built with -fmad=false).
 #include <cooperative_groups.h>
+#include <cuda.h>  // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
 #include <math.h>
 #include <stdlib.h>
 
@@ -85,6 +86,8 @@ struct heur_args {
   double delta_in;                 // width of the sub-windows inside a tile visit
   int group_size, n_groups;
   int compact;                     // warp-tile kernel: 1 = compacted sweeps (sweep_compact), 0 = row-wise sweeps (sweep)
+  int tmap_ok;                     // warp-tile kernel: the tensor map below is valid (tiles staged by one TMA box copy)
+  alignas(64) CUtensorMap tmap;    // cost_all as a (W, H, n_fields) fp64 tensor, box 38 x 34 x 1 = a tile with its halo
   heur_weights wt;
 };
 
@@ -383,7 +386,7 @@ template <int NB, int VARIANT>
 __global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : HPP_NB2_CTAS) heur_persist_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<NB>;
   constexpr int T = C::T, S = C::S, ROWS = C::ROWS, NBLK = C::NBLK, THREADS = C::THREADS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double *cs_nv = (double *)smem_raw;                                   // ROWS * S
   uint32_t *s_inc = (uint32_t *)(cs_nv + ROWS * S);                     // NBLK * 32
   uint32_t *s_list = s_inc + NBLK * 32;                                 // THREADS
@@ -708,6 +711,13 @@ __device__ __forceinline__ void tma_load_row(uint32_t dst, const void *src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// global -> shared tensor box copy (TMA, 3-D tiled tensor map): one instruction stages a tile with its halo; elements
+// outside the tensor arrive as zeros.  dst must be 128-byte aligned.
+__device__ __forceinline__ void tma_load_box3(uint32_t dst, const CUtensorMap *tmap, int x, int y, int z, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"((unsigned long long)tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
+               : "memory");
+}
 // order this thread's generic-proxy accesses with async-proxy (TMA) accesses, per state space (a tile visit needs one of
 // each; the unrestricted fence.proxy.async twice per visit was 4.6 % of the stall samples)
 __device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -718,6 +728,10 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // `bound` (sub-windows of delta_in), writes the changed rows and the deferred masks back.  af = ring sides to
 // re-evaluate (DIR_* flags posted by the neighbours).  Returns the cheapest cost left deferred (bit pattern, INF_BITS
 // if none); *wc.s_out holds the DIR_* flags of the neighbour tiles whose halo this visit changed.
+// a warp's tile slot in shared memory: ROWS*S doubles, padded to a multiple of 128 bytes (TMA tensor copies need a
+// 128-byte aligned destination)
+#define WSLOT_DOUBLES ((((HB + 2) * (HB + 6) * 8 + 127) / 128) * 128 / 8)
+
 // per-warp scratch of the compacted sweep, in shared memory (all zero between sweeps)
 #define WAUX_LIST 128
 struct warp_aux {
@@ -732,7 +746,9 @@ struct warp_ctx {
   uint32_t *s_out;
   warp_aux *aux;
   uint32_t mbar, parity;
-  bool tma_ok;
+  bool tma_ok;   // rows can be bulk-copied (W even, aligned base)
+  bool tma_2d;   // ... and the whole tile + halo comes as one tensor box copy
+  int field;     // field index (third tensor coordinate)
 };
 
 // the three neighbours (columns x-1, x, x+1; m3 bit 0 = column x-1) of one row as a mask of the columns 0..31
@@ -867,7 +883,39 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
     // ---- stage the tile + halo.  TMA path: one bulk copy per row (columns x0-2 .. x0+33, 16-byte aligned),
     // all rows in flight at once, completion counted on the warp's mbarrier.  Cells outside the map keep the
     // initial value: edge tiles are pre-filled before the copies land.
-    if (wc.tma_ok) {
+    if (wc.tma_2d) {
+      // one box copy: columns x0-2 .. x0+35, rows y0-1 .. y0+32 of field wc.field; what lies outside the map comes as
+      // zeros and is overwritten with the initial value afterwards (edge tiles only)
+      fence_proxy_async_shared();  // my generic-proxy accesses to this buffer before the async-proxy writes
+      if (lane == 0) {
+        mbar_expect_tx(wc.mbar, (uint32_t)(ROWS * S * sizeof(double)));
+        tma_load_box3(smem_u32(cs_nv), &a.tmap, x0 - 2, y0 - 1, wc.field, wc.mbar);
+      }
+      __syncwarp();
+      if (VARIANT == HPP_VARIANT_DUBINS) {
+        for (int r = 0; r < ROWS; r++) {
+          const int gy = y0 - 1 + r;
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const int c = lane + 32 * k, gx = x0 - 1 + c;
+            if (c < T + 2) {
+              uint8_t k8 = CLS_BLOCKED | 9;
+              if (gy >= 0 && gy < H && gx >= 0 && gx < W) k8 = a.cls[(size_t)gy * W + gx];
+              cl_nv[r * S + c + 1] = k8;
+            }
+          }
+        }
+      }
+      mbar_wait(wc.mbar, wc.parity);
+      wc.parity ^= 1u;
+      if (x0 == 0 || x0 + T + 1 > W || y0 == 0 || y0 + T + 1 > H) {
+        for (int i = lane; i < ROWS * S; i += 32) {
+          const int gy = y0 - 1 + i / S, gx = x0 - 2 + i % S;
+          if (gy < 0 || gy >= H || gx < 0 || gx >= W) cs_nv[i] = wt.init;
+        }
+        __syncwarp();
+      }
+    } else if (wc.tma_ok) {
       const int cx0 = x0 - 2 < 0 ? 0 : x0 - 2, cx1 = x0 + T + 2 > W ? W : x0 + T + 2;
       const int ry0 = y0 - 1 < 0 ? 0 : y0 - 1, ry1 = y0 + T + 1 > H ? H : y0 + T + 1;  // valid global rows
       const bool edge = x0 == 0 || x0 + T + 2 > W || y0 == 0 || y0 + T + 1 > H;
@@ -1063,9 +1111,9 @@ template <int VARIANT, int WT_WARPS>
 __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<1>;
   constexpr int S = C::S, ROWS = C::ROWS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *cs_all = (double *)smem_raw;                                  // WT_WARPS x ROWS*S
-  uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);          // WT_WARPS x ROWS*S (Dubins only)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *cs_all = (double *)smem_raw;                                  // WT_WARPS x WSLOT_DOUBLES (128-byte aligned slots)
+  uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * WSLOT_DOUBLES);     // WT_WARPS x ROWS*S (Dubins only)
   warp_aux *aux_all = (warp_aux *)(cl_all + (VARIANT == HPP_VARIANT_DUBINS ? WT_WARPS * ROWS * S : 0));
   __shared__ unsigned long long s_gmin;
   __shared__ uint32_t s_mine, s_next, s_lnext, s_warp_cnt[32], s_outw[WT_WARPS], s_pref[WT_WARPS * 32];
@@ -1089,7 +1137,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   wt.rs = s_rs;
   wt.db = s_db;
   warp_ctx wc;
-  wc.cs_nv = cs_all + wid * ROWS * S;
+  wc.cs_nv = cs_all + wid * WSLOT_DOUBLES;
   wc.cl_nv = cl_all + wid * ROWS * S;
   wc.aux = aux_all + wid;
   for (int i = lane; i < (int)(sizeof(warp_aux) / 4); i += 32) ((uint32_t *)wc.aux)[i] = 0u;
@@ -1101,8 +1149,11 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   __syncthreads();
   // rows can be bulk-copied when every row start (x0 - 2 doubles) is 16-byte aligned: W even and an aligned base
   wc.tma_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.cost_all) & 15) == 0);
+  wc.tma_2d = wc.tma_ok && a.tmap_ok && ((smem_u32(wc.cs_nv) & 127u) == 0u);
+  wc.field = 0;
 
   for (int field = group; field < a.n_fields; field += a.n_groups) {
+    wc.field = field;
     double *cost = a.cost_all + (size_t)field * n;
     uint32_t *act = a.act + (size_t)field * 3 * n_tiles;
     unsigned long long *pmin = a.pmin + (size_t)field * 2 * n_tiles;
@@ -1429,9 +1480,9 @@ template <int VARIANT, int WT_WARPS>
 __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_async_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<1>;
   constexpr int S = C::S, ROWS = C::ROWS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double *cs_all = (double *)smem_raw;
-  uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * ROWS * S);
+  uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * WSLOT_DOUBLES);
   warp_aux *aux_all = (warp_aux *)(cl_all + (VARIANT == HPP_VARIANT_DUBINS ? WT_WARPS * ROWS * S : 0));
   __shared__ uint32_t s_outw[WT_WARPS];
   __shared__ double s_db[20];
@@ -1448,7 +1499,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_async_kernel(const __gr
   wt.rs = s_rs;
   wt.db = s_db;
   warp_ctx wc;
-  wc.cs_nv = cs_all + wid * ROWS * S;
+  wc.cs_nv = cs_all + wid * WSLOT_DOUBLES;
   wc.cl_nv = cl_all + wid * ROWS * S;
   wc.aux = aux_all + wid;
   for (int i = lane; i < (int)(sizeof(warp_aux) / 4); i += 32) ((uint32_t *)wc.aux)[i] = 0u;
@@ -1459,6 +1510,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_async_kernel(const __gr
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   wc.tma_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.cost_all) & 15) == 0);
+  wc.tma_2d = wc.tma_ok && a.tmap_ok && ((smem_u32(wc.cs_nv) & 127u) == 0u);
+  wc.field = 0;
 
   uint32_t *ctl = a.aq;                     // control words
   uint32_t *state = a.aq + AQ_HDR;          // [n_tiles]
@@ -1744,7 +1797,7 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   size_t smem;
   const void *kern;
   if constexpr (NB == 1) {
-    smem = (size_t)WT_WARPS * (C::ROWS * C::S * (sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? 1 : 0)) + sizeof(warp_aux)) + 16;
+    smem = (size_t)WT_WARPS * (WSLOT_DOUBLES * sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? C::ROWS * C::S : 0) + sizeof(warp_aux)) + 128;
     kern = small ? (const void *)heur_warp_kernel<VARIANT, 4>
                  : (many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
                          : (const void *)heur_warp_kernel<VARIANT, 16>);
@@ -1849,6 +1902,37 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 768.0 : (n_fields < 64 ? 128.0 : 64.0)) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 32.0);
   a.compact = (int)env_double("HPP_HEUR_COMPACT", 1);
+  // the fields as one (W, H, n_fields) fp64 tensor for the TMA: a tile with its halo is one 38 x 34 box.  Needs 16-byte
+  // multiples for the row pitch (W even); anything else keeps the row-wise bulk copies / plain loads.
+  a.tmap_ok = 0;
+  memset(&a.tmap, 0, sizeof a.tmap);
+  if (NB == 1 && (W % 2) == 0 && ((uintptr_t)cost_dev & 15) == 0 && env_double("HPP_HEUR_TMA2D", 1) != 0) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+      looked = true;
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+          qres == cudaDriverEntryPointSuccess)
+        encode = (encode_fn)fn;
+      else
+        (void)cudaGetLastError();
+    }
+    if (encode) {
+      const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_fields};
+      const cuuint64_t gstride[2] = {(cuuint64_t)W * 8, (cuuint64_t)W * H * 8};
+      const cuuint32_t box[3] = {(cuuint32_t)C::S, (cuuint32_t)C::ROWS, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      if (encode(&a.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)cost_dev, gdim, gstride, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        a.tmap_ok = 1;
+    }
+  }
   const bool debug = getenv("HPP_HEUR_DEBUG") != nullptr;
   const size_t prof_n = ((size_t)c->sm_count * 8 + n_fields) * 8 + 8;
   if (debug) {
@@ -1888,7 +1972,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
       HPP_CUDA(c, cudaMemsetAsync(a.aq + AQ_HDR + n_tiles, 0xff, sizeof(uint32_t) * ring, c->stream));
       heur_async_seed_kernel<NB><<<1, 32, 0, c->stream>>>(a.aq, d_goals, tiles_x, n_tiles, a.delta);
       HPP_LAUNCHED(c);
-      const size_t smem = (size_t)16 * (C::ROWS * C::S * (sizeof(double) + (variant == HPP_VARIANT_DUBINS ? 1 : 0)) + sizeof(warp_aux)) + 16;
+      const size_t smem = (size_t)16 * (WSLOT_DOUBLES * sizeof(double) + (variant == HPP_VARIANT_DUBINS ? C::ROWS * C::S : 0) + sizeof(warp_aux)) + 128;
       const void *kern = variant == HPP_VARIANT_RS ? (const void *)heur_async_kernel<HPP_VARIANT_RS, 16>
                                                    : (const void *)heur_async_kernel<HPP_VARIANT_DUBINS, 16>;
       HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -241,6 +241,10 @@ def test_heuristic_sweep_modes_and_cta_shapes_agree(ctx, monkeypatch, variant):
                 assert bits_equal(got, want), (occ.shape, compact, din)
         monkeypatch.delenv("HPP_HEUR_DELTA_IN")
         monkeypatch.setenv("HPP_HEUR_COMPACT", "1")
+        monkeypatch.setenv("HPP_HEUR_TMA2D", "0")       # row-wise bulk copies instead of one tensor box copy per tile
+        got = m.heuristic_rs(goal, (0, 0))[0] if variant == 0 else m.heuristic_dubins(goal)[0]
+        assert bits_equal(got, want), (occ.shape, "row-wise TMA staging")
+        monkeypatch.delenv("HPP_HEUR_TMA2D")
         monkeypatch.setenv("HPP_HEUR_WARPS", "4")
         monkeypatch.setenv("HPP_HEUR_GROUP", "1")
         got = m.heuristic_rs(goal, (0, 0))[0] if variant == 0 else m.heuristic_dubins(goal)[0]
