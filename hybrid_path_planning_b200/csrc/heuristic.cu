@@ -10,23 +10,31 @@
 //     Dubins:  cost[v] = min(1000, min_u fl(cost[u] + fl(hypot(dir) + 10*cnt3x3(u))))  (DB/src/HybridAstar.cpp:198-221,:286-297)
 // over free cells v, which does not depend on the relaxation order (fl(a + w) is monotone in a).
 //
-// Device algorithm: ONE persistent cooperative kernel per batch of fields -- delta-stepping over tiles.
-//   * The field is cut into T x T tiles (T = 32*NB).  A CTA of NB*NB warps stages one tile (+ one-cell halo) of fp64
-//     costs in shared memory; every warp owns one 32x32 block of it, lane = row.  The frontier lives in REGISTERS:
-//     one 32-bit "needs evaluation" mask per lane; a changed cell is dilated to its 8 neighbours with shifts and
-//     two warp shuffles; block-border changes are posted to the neighbouring warp through a shared-memory mask
-//     (atomicOr), so warps relax asynchronously and only meet at one __syncthreads_or per PHASE_SWEEPS sweeps.
+// Device algorithm: ONE persistent kernel per batch of fields -- delta-stepping over tiles.  Two tile kernels:
+//   heur_warp_kernel (default)  32x32 tiles, ONE WARP per tile (no block-level barrier inside a tile solve), 16 / 20 / 4
+//                      warps per CTA.  A tile with its halo is staged by one TMA tensor box copy (3-D tensor map over
+//                      the batch's fields; row-wise bulk copies or plain loads as fall-backs).  The frontier lives in
+//                      REGISTERS, one 32-bit "needs evaluation" mask per lane (= row).  Sweeps are COMPACTED
+//                      (sweep_compact): the rows' needed cells go into one shared-memory list, every lane takes two
+//                      entries whatever their rows, improved cells OR their push masks into their rows' words with
+//                      32-bit shared atomics.  The row-wise sweep (HPP_HEUR_COMPACT=0) is kept for comparison.
+//   heur_persist_kernel (HPP_HEUR_NB=2|4)  the earlier 64x64 / 128x128 tiles: a CTA of NB*NB warps stages one tile,
+//                      every warp owns one 32x32 block (lane = row), block-border changes are posted to the neighbouring
+//                      warp through a shared-memory mask, one __syncthreads_or per PHASE_SWEEPS sweeps.
 //   * A cell is evaluated by PULL: min over its 8 neighbours, exactly the reference's additions (no FMA; min
-//     before add is legal because fl(a+w) is monotone).  Rows with many needed cells are evaluated one lane per
-//     column (ballot collects the changes), sparse rows one cell per lane -- no list compaction at all.
+//     before add is legal because fl(a+w) is monotone).  An improved cell pushes only the neighbours it can still
+//     improve, so settled cells behind the front are not re-evaluated.
 //   * Cost window: a change whose new cost is >= bound is DEFERRED (bit kept in a per-tile mask in global memory)
 //     instead of propagated; a tile is scheduled when a neighbour posted a border change or when its cheapest
 //     deferred cell falls below the bound; when nothing is schedulable the bound advances to (global minimum of
 //     deferred costs) + delta.  This keeps expensive waves (the +5 near-obstacle cells) from running ahead of the
-//     cheap ones and being corrected later: 3 evaluations per cell instead of 27 on the cfg3 map.
-//   * Scheduling is done on the device by every CTA identically from read-only "current" tables (tile activity
-//     flags are triple-buffered, the deferred minima double-buffered), so a round costs exactly one group barrier;
-//     the host launches once and never polls.  Batches of fields are split over independent CTA groups.
+//     cheap ones and being corrected later: 3 evaluations per cell instead of 27 on the cfg3 map.  Inside a tile visit
+//     the same mechanism runs with sub-windows of delta_in.
+//   * Scheduling is done on the device.  A batch is split over independent CTA groups, one field per group at a time:
+//     a group of several CTAs (cooperative launch) scans the tile table in slices and meets at two group barriers per
+//     round; ONE CTA per field (plain launch, large batches) keeps the round's schedule as the list of tiles posted
+//     to during the previous round and scans the table only when the window moves.  The host launches once and
+//     never polls.  heur_async_kernel (HPP_HEUR_ASYNC=1) is an experimental barrier-free tile queue for a lone field.
 // Costs are fp64 with exactly the reference's additions (library built with -fmad=false).
 #include <cooperative_groups.h>
 #include <cuda.h>  // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
