@@ -94,6 +94,7 @@ struct heur_args {
   double delta_in;                 // width of the sub-windows inside a tile visit
   int group_size, n_groups;
   int compact;                     // warp-tile kernel: 1 = compacted sweeps (sweep_compact), 0 = row-wise sweeps (sweep)
+  int lpt;                         // one-CTA-per-field mode: longest-first ordering of a round's tiles
   int tmap_ok;                     // warp-tile kernel: the tensor map below is valid (tiles staged by one TMA box copy)
   alignas(64) CUtensorMap tmap;    // cost_all as a (W, H, n_fields) fp64 tensor, box 38 x 34 x 1 = a tile with its halo
   heur_weights wt;
@@ -736,6 +737,9 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // `bound` (sub-windows of delta_in), writes the changed rows and the deferred masks back.  af = ring sides to
 // re-evaluate (DIR_* flags posted by the neighbours).  Returns the cheapest cost left deferred (bit pattern, INF_BITS
 // if none); *wc.s_out holds the DIR_* flags of the neighbour tiles whose halo this visit changed.
+// warp-tile kernel: n_tiles-sized arrays per CTA in a.lists (schedule of the current / next round, last visit times)
+#define LISTS_PER_CTA 3
+
 // a warp's tile slot in shared memory: ROWS*S doubles, padded to a multiple of 128 bytes (TMA tensor copies need a
 // 128-byte aligned destination)
 #define WSLOT_DOUBLES ((((HB + 2) * (HB + 6) * 8 + 127) / 128) * 128 / 8)
@@ -1124,7 +1128,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * WSLOT_DOUBLES);     // WT_WARPS x ROWS*S (Dubins only)
   warp_aux *aux_all = (warp_aux *)(cl_all + (VARIANT == HPP_VARIANT_DUBINS ? WT_WARPS * ROWS * S : 0));
   __shared__ unsigned long long s_gmin;
-  __shared__ uint32_t s_mine, s_next, s_lnext, s_warp_cnt[32], s_outw[WT_WARPS], s_pref[WT_WARPS * 32];
+  __shared__ uint32_t s_mine, s_next, s_lnext, s_dsum, s_dcnt, s_warp_cnt[32], s_outw[WT_WARPS], s_pref[WT_WARPS * 32];
   __shared__ double s_db[20];
   __shared__ __align__(8) unsigned long long s_mbar[WT_WARPS];  // one TMA completion barrier per warp
 
@@ -1132,7 +1136,8 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
   const int group = blockIdx.x / a.group_size, grank = blockIdx.x % a.group_size;
   if (group >= a.n_groups) return;
   uint32_t *bar = a.bar + group * 32;
-  uint32_t *my_list = a.lists + (size_t)blockIdx.x * 2 * a.n_tiles;  // two lists (current / next round) per CTA
+  uint32_t *my_list = a.lists + (size_t)blockIdx.x * LISTS_PER_CTA * a.n_tiles;  // two lists (current / next round) per CTA and,
+                                                                     // one-CTA-per-field mode, the tiles' last visit times
   const int W = a.W, H = a.H, n_tiles = a.n_tiles;
   const size_t n = (size_t)W * H;
   if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
@@ -1183,7 +1188,15 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
       // flag), and the tile table is only scanned when that list runs empty and the cost window has to move.
       uint32_t *lcur = my_list, *lnext = my_list + n_tiles;
       uint32_t *acur = act, *anext = act + n_tiles;
-      if (tid == 0) s_mine = 0;
+      // Longest first: the warps pull the round's tiles from a shared counter and the round ends with its slowest
+      // visit, so tiles whose previous visit was longer than the previous round's average go to the front of the list.
+      uint32_t *dur = my_list + 2 * n_tiles;
+      for (int t = tid; t < n_tiles; t += WT_WARPS * 32) dur[t] = 0u;
+      if (tid == 0) {
+        s_mine = 0;
+        s_dsum = 0;
+        s_dcnt = 0;
+      }
       __syncthreads();
       for (;;) {
         uint32_t ncur = s_mine;
@@ -1213,6 +1226,29 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
           __syncthreads();
         }
         rounds++;
+        if (a.lpt && ncur > WT_WARPS && ncur <= WT_WARPS * 32) {
+          const uint32_t thr = s_dcnt ? s_dsum / s_dcnt : 0u;
+          __syncthreads();
+          if (tid == 0) {
+            s_next = 0;   // front cursor
+            s_lnext = 0;  // back cursor
+            s_dsum = 0;
+            s_dcnt = 0;
+          }
+          __syncthreads();
+          if (tid < (int)ncur) {
+            const uint32_t t = __ldcg(lcur + tid);
+            const bool longer = __ldcg(dur + t) > thr;
+            const uint32_t pos = longer ? atomicAdd(&s_next, 1u) : ncur - 1u - atomicAdd(&s_lnext, 1u);
+            s_pref[pos] = t;
+          }
+          __syncthreads();
+          if (tid < (int)ncur) __stcg(lcur + tid, s_pref[tid]);
+          __syncthreads();
+        } else if (tid == 0) {
+          s_dsum = 0;
+          s_dcnt = 0;
+        }
         if (tid == 0) {
           s_next = 0;
           s_lnext = 0;
@@ -1227,9 +1263,14 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
           const int tile = (int)__ldcg(lcur + i);
           const uint32_t af = __ldcg(acur + tile) & 0xffu;
           visits++;
+          const long long t_visit = clock64();
           const unsigned long long left = warp_visit_tile<VARIANT>(a, cost, dmask, tile, af, bound, wt, wc, lane);
           pf[5]++;
           if (lane == 0) {
+            const uint32_t dt = (uint32_t)min((long long)0xfffff, (clock64() - t_visit) >> 4);
+            __stcg(dur + tile, dt);
+            atomicAdd(&s_dsum, dt);
+            atomicAdd(&s_dcnt, 1u);
             __stcg(acur + tile, 0u);  // this buffer receives the posts of the next round
             __stcg(pmin + tile, left);
             const uint32_t o = ((volatile uint32_t *)s_outw)[wid];
@@ -1415,7 +1456,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
               if (s_pref[mid] <= rk) lo = mid;
               else hi = mid - 1;
             }
-            tl = (int)__ldcg(a.lists + (size_t)(group * a.group_size + lo) * 2 * a.n_tiles + (rk - s_pref[lo]));
+            tl = (int)__ldcg(a.lists + (size_t)(group * a.group_size + lo) * LISTS_PER_CTA * a.n_tiles + (rk - s_pref[lo]));
           }
           tile = __shfl_sync(FULL, tl, 0);
         }
@@ -1841,7 +1882,7 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   const int grid = gs * n_groups;
   if constexpr (NB == 1) {
     void *lp;
-    const size_t lists_b = ((sizeof(uint32_t) * (size_t)grid * 2 * a.n_tiles) + 255) & ~(size_t)255;
+    const size_t lists_b = ((sizeof(uint32_t) * (size_t)grid * LISTS_PER_CTA * a.n_tiles) + 255) & ~(size_t)255;
     hpp_status s = hpp_scratch(c, 4, lists_b + sizeof(uint32_t) * 4 * (size_t)grid + 256, &lp);
     if (s != HPP_OK) return s;
     a.lists = (uint32_t *)lp;
@@ -1910,6 +1951,7 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 768.0 : (n_fields < 64 ? 128.0 : 64.0)) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 32.0);
   a.compact = (int)env_double("HPP_HEUR_COMPACT", 1);
+  a.lpt = (int)env_double("HPP_HEUR_LPT", 1);
   // the fields as one (W, H, n_fields) fp64 tensor for the TMA: a tile with its halo is one 38 x 34 box.  Needs 16-byte
   // multiples for the row pitch (W even); anything else keeps the row-wise bulk copies / plain loads.
   a.tmap_ok = 0;
