@@ -1960,18 +1960,16 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
-    static bool looked = false;
-    if (!looked) {
-      looked = true;
+    // looked up once per process (thread-safe static initialisation: plan_batch calls come from several host threads)
+    static const encode_fn encode = []() -> encode_fn {
       void *fn = nullptr;
       cudaDriverEntryPointQueryResult qres;
       if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
           qres == cudaDriverEntryPointSuccess)
-        encode = (encode_fn)fn;
-      else
-        (void)cudaGetLastError();
-    }
+        return (encode_fn)fn;
+      (void)cudaGetLastError();
+      return nullptr;
+    }();
     if (encode) {
       const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_fields};
       const cuuint64_t gstride[2] = {(cuuint64_t)W * 8, (cuuint64_t)W * H * 8};
