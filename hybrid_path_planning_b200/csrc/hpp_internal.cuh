@@ -27,7 +27,7 @@ struct hpp_ctx {
   size_t h_pinned_bytes[2];
   // hpp_plan_batch: values that cost a driver round trip each (tens of microseconds of a 0.3 ms single-query call)
   size_t plan_free_bytes;   // cudaMemGetInfo at the last large call (0 = never asked)
-  int plan_occ_blocks[2];   // resident plan_kernel CTAs per SM, per variant (0 = not asked yet)
+  int plan_occ_blocks[4];   // resident plan_kernel CTAs per SM, per variant and kernel shape (0 = not asked yet)
 };
 
 // per-cell class byte (see map.cu: build_cls_kernel)

@@ -1,7 +1,7 @@
 // planner.cu -- whole Hybrid A* queries on the device: HybridAstar::run (RS/src/HybridAstar.cpp:553-729,
 // DB/src/HybridAstar.cpp:315-496) for a batch of independent start/goal pairs on one map.
 //
-// One CTA of PLAN_WARPS warps owns one query from start to finish (and then takes the next one from a counter): no
+// One CTA of four (batches) or eight (small batches) warps owns one query from start to finish (and then takes the next one from a counter): no
 // host round trip per A* iteration.  The iterations of a query are a sequential chain, so the CTA's job is to make
 // one iteration short: the 46 Reeds-Shepp closed forms are spread over the warps family by family, the candidate
 // paths are sampled and footprint-checked one per warp, and the expansion's rollouts run one thread per
@@ -25,10 +25,10 @@
 #include "expand.cuh"
 #include "shots.cuh"
 
-#ifndef PLAN_WARPS
-#define PLAN_WARPS 4
-#endif
-#define PLAN_THREADS (PLAN_WARPS * 32)
+// warps per query: 4 for batches (three CTAs per SM: more queries in flight), 8 for small batches (a lone query's
+// iteration is ~11 % shorter with its paths and formulas spread over eight warps; one CTA per SM)
+#define PLAN_WARPS_BATCH 4
+#define PLAN_WARPS_LONE 8
 #define PLAN_ITER_CAP 3500
 #define PI_ASTAR 3.14159 /* RS/include/HybridAstar.h:24 */
 
@@ -259,33 +259,34 @@ struct plan_smem {
 // formula evaluated by (warp, lane): the closed forms of one family share their code path, so each warp gets at most
 // three families (RS/src/reeds_shepp_path.cpp:795-817 issue order: SLS 0-1, LSL 2-5, LSR 6-9, LRL 10-17, LRLRn 18-21,
 // LRLRp 22-25, LRSL 26-29 and 34-37, LRSR 30-33 and 38-41, LRSLR 42-45)
+template <int NW>
 __device__ __forceinline__ int plan_formula_of(int wid, int lane) {
-#if PLAN_WARPS == 4
-  switch (wid) {
-    case 0: return lane < 10 ? lane : -1;
-    case 1: return lane < 12 ? 10 + lane : -1;
-    case 2: return lane < 8 ? 22 + lane : (lane < 12 ? 26 + lane : -1);
-    default: return lane < 4 ? 30 + lane : (lane < 12 ? 34 + lane : -1);
+  if (NW == 4) {
+    switch (wid) {
+      case 0: return lane < 10 ? lane : -1;
+      case 1: return lane < 12 ? 10 + lane : -1;
+      case 2: return lane < 8 ? 22 + lane : (lane < 12 ? 26 + lane : -1);
+      default: return lane < 4 ? 30 + lane : (lane < 12 ? 34 + lane : -1);
+    }
+  } else if (NW == 8) {
+    switch (wid) {
+      case 0: return lane < 6 ? lane : -1;
+      case 1: return lane < 4 ? 6 + lane : -1;
+      case 2: return lane < 8 ? 10 + lane : -1;
+      case 3: return lane < 4 ? 18 + lane : -1;
+      case 4: return lane < 4 ? 22 + lane : -1;
+      case 5: return lane < 4 ? 26 + lane : (lane < 8 ? 30 + lane : -1);
+      case 6: return lane < 4 ? 30 + lane : (lane < 8 ? 34 + lane : -1);
+      default: return lane < 4 ? 42 + lane : -1;
+    }
+  } else {
+    const int t = wid * 32 + lane;
+    return t < RS_NCAND ? t : -1;
   }
-#elif PLAN_WARPS == 8
-  switch (wid) {
-    case 0: return lane < 6 ? lane : -1;
-    case 1: return lane < 4 ? 6 + lane : -1;
-    case 2: return lane < 8 ? 10 + lane : -1;
-    case 3: return lane < 4 ? 18 + lane : -1;
-    case 4: return lane < 4 ? 22 + lane : -1;
-    case 5: return lane < 4 ? 26 + lane : (lane < 8 ? 30 + lane : -1);
-    case 6: return lane < 4 ? 30 + lane : (lane < 8 ? 34 + lane : -1);
-    default: return lane < 4 ? 42 + lane : -1;
-  }
-#else
-  const int t = wid * 32 + lane;
-  return t < RS_NCAND ? t : -1;
-#endif
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, const float *__restrict__ dist,
+template <int VARIANT, int PLAN_WARPS>
+__global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, const float *__restrict__ dist,
                                                             const uint32_t *__restrict__ bits, int pitch,
                                                             const double *__restrict__ starts,
                                                             const double *__restrict__ goals,
@@ -298,6 +299,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
                                                             unsigned long long traj_cap,
                                                             unsigned long long *__restrict__ cursor,
                                                             unsigned long long *__restrict__ prof) {
+  static_assert(PLAN_WARPS >= 2, "warp 0 and at least one helper warp");
+  constexpr int PLAN_THREADS = PLAN_WARPS * 32;
   __shared__ plan_smem sm;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   rs_warp_smem &S = sm.S;
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(plan_consts pc, cons
       // ---- analytic shot (+ for Dubins, the expansion's footprint checks on the other warps meanwhile)
       if (VARIANT == HPP_VARIANT_RS) {
         const rs_frame f = rs_make_frame(cn.x, cn.y, cn.h, gx, gy, gh, pc.maxc);
-        const int idx = plan_formula_of(wid, lane);
+        const int idx = plan_formula_of<PLAN_WARPS>(wid, lane);
         if (idx >= 0) rs_eval_formula(idx, f.x, f.y, f.dth, f.xb, f.yb, S);
         __syncthreads();
         PLAN_MARK(6)
@@ -773,13 +776,22 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
     c->plan_free_bytes = free_b;
   }
   const size_t per_warp = (size_t)pc.max_nodes * (sizeof(pnode) + 12) + (size_t)slots * 4;
-  int occ_blocks = c->plan_occ_blocks[variant];
+  // kernel shape: eight warps per query while the batch leaves SMs free anyway, four otherwise (HPP_PLAN_WARPS forces one)
+  int plan_warps = n <= (size_t)c->sm_count ? PLAN_WARPS_LONE : PLAN_WARPS_BATCH;
+  if (const char *e = getenv("HPP_PLAN_WARPS")) {
+    const int v = atoi(e);
+    if (v == PLAN_WARPS_LONE || v == PLAN_WARPS_BATCH) plan_warps = v;
+  }
+  const void *kern = variant == HPP_VARIANT_RS
+                         ? (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_LONE>
+                                                          : (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_BATCH>)
+                         : (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_LONE>
+                                                          : (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_BATCH>);
+  const int occ_slot = variant * 2 + (plan_warps == PLAN_WARPS_LONE ? 1 : 0);
+  int occ_blocks = c->plan_occ_blocks[occ_slot];
   if (occ_blocks == 0) {
-    if (variant == HPP_VARIANT_RS)
-      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, plan_kernel<HPP_VARIANT_RS>, PLAN_WARPS * 32, 0));
-    else
-      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, plan_kernel<HPP_VARIANT_DUBINS>, PLAN_WARPS * 32, 0));
-    c->plan_occ_blocks[variant] = occ_blocks;
+    HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, kern, plan_warps * 32, 0));
+    c->plan_occ_blocks[occ_slot] = occ_blocks;
   }
   if (occ_blocks < 1) occ_blocks = 1;
   size_t max_warps = (size_t)c->sm_count * occ_blocks;  // CTAs (= queries in flight): one resident wave, persistent
@@ -868,14 +880,19 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
                           t_us(t0, t1), t_us(t1, t2), t_us(t2, t3));
       cudaMemcpyAsync(d_fq + q0, fq.data() + q0, (q1 - q0) * 4, cudaMemcpyHostToDevice, c->stream);
       cudaMemsetAsync(d_cursor + 1, 0, 8, c->stream);  // the kernel's query counter
-      if (variant == HPP_VARIANT_RS)
-        plan_kernel<HPP_VARIANT_RS><<<grid, PLAN_WARPS * 32, 0, c->stream>>>(
-            pc, m->d_distance, m->d_occ_bits, m->bits_pitch, d_starts, d_goals, d_qids + q0, (int)(q1 - q0), d_fq + q0,
-            d_fields, d_nodes, d_keys, d_idx, d_table, d_plans, d_traj, traj_cap, d_cursor, d_prof);
-      else
-        plan_kernel<HPP_VARIANT_DUBINS><<<grid, PLAN_WARPS * 32, 0, c->stream>>>(
-            pc, m->d_distance, m->d_occ_bits, m->bits_pitch, d_starts, d_goals, d_qids + q0, (int)(q1 - q0), d_fq + q0,
-            d_fields, d_nodes, d_keys, d_idx, d_table, d_plans, d_traj, traj_cap, d_cursor, d_prof);
+      {
+        const float *a_dist = m->d_distance;
+        const uint32_t *a_bits = m->d_occ_bits;
+        int a_pitch = m->bits_pitch;
+        const double *a_starts = d_starts, *a_goals = d_goals, *a_fields = d_fields;
+        const int *a_qids = d_qids + q0, *a_fq = d_fq + q0;
+        int a_nq = (int)(q1 - q0);
+        unsigned long long a_cap = traj_cap;
+        void *params[] = {&pc,      &a_dist, &a_bits,  &a_pitch, &a_starts, &a_goals,  &a_qids, &a_nq,     &a_fq,
+                          &a_fields, &d_nodes, &d_keys, &d_idx,   &d_table,  &d_plans, &d_traj, &a_cap,    &d_cursor,
+                          &d_prof};
+        cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, 0, c->stream);
+      }
       c->launches++;
       e = cudaGetLastError();
       const auto t4 = t_now();
