@@ -17,7 +17,7 @@ if [ -f "$REF/reeds_shepp_hybrid_astar/src/main_path_planning.cpp" ] && [ -d "$M
   for pkg in rs:reeds_shepp_hybrid_astar db:dubins_hybrid_star; do
     tag="${pkg%%:*}"; dir="${pkg##*:}"
     tmp="$(mktemp -d)"
-    cp "$MOCK/dropin_$tag/"*.h "$tmp/"
+    cp "dropin/$tag/"*.h "$tmp/"
     cp "$REF/$dir/include/main_path_planning.h" "$tmp/"      # temporary, outside the repository
     $CXX $CXXFLAGS -Dmain=reference_node_main -I"$tmp" -I"$MOCK/include" -I. -I../../include \
       -c "$REF/$dir/src/main_path_planning.cpp" -o "$tmp/node.o"

@@ -1,6 +1,6 @@
 """Drop-in check at the source level: the reference's UNMODIFIED ROS 2 node sources (main_path_planning.cpp of
 reeds_shepp_hybrid_astar and dubins_hybrid_star) compile against the hpp-b200 host shells when the package's five class
-headers are replaced by forwarding headers.  ROS itself is not installed here: tests/ros_mock
+headers are replaced by the forwarding headers of hybrid_path_planning_b200/host/dropin/ (INTEGRATION.md section 1).  ROS itself is not installed here: tests/ros_mock
 holds stand-ins for the rclcpp / message / tf2 headers the nodes include.  Needs the reference checkout (skipped on
 machines without it, e.g. the GPU box); nothing of the reference is copied into the repository -- its node header goes to
 a temporary directory for the duration of the compile."""
@@ -23,8 +23,9 @@ def test_reference_node_compiles_on_the_shells(tag, pkg):
         pytest.skip("reference checkout not present")
     tmp = tempfile.mkdtemp()
     try:
-        for f in os.listdir(os.path.join(MOCK, "dropin_" + tag)):
-            shutil.copy(os.path.join(MOCK, "dropin_" + tag, f), tmp)
+        fwd = os.path.join(ROOT, "hybrid_path_planning_b200", "host", "dropin", tag)
+        for f in os.listdir(fwd):
+            shutil.copy(os.path.join(fwd, f), tmp)
         shutil.copy(os.path.join(REF, pkg, "include", "main_path_planning.h"), tmp)
         cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-I" + tmp, "-I" + os.path.join(MOCK, "include"),
                "-I" + os.path.join(ROOT, "hybrid_path_planning_b200", "host"), "-I" + os.path.join(ROOT, "include"), src]
