@@ -53,3 +53,52 @@ def test_header_cites_the_reference_interface():
     for cite in ("RS/include/Grid_map.h:85", "RS/include/HybridAstar.h:62", "RS/include/HybridAstar.h:52",
                  "RS/include/reeds_shepp_path.h:51", "DB/include/dubins_path.h:57", "MI/src/map_inflate_node.cpp"):
         assert cite in src
+
+
+def _classify_c(param):
+    p = param.strip()
+    if "*" in p or "[" in p:
+        return "p"
+    t = re.sub(r"\b(const|volatile)\b", "", p).split()
+    t = " ".join(t[:-1]) if len(t) > 1 else t[0]
+    if t == "float":
+        return "f"
+    if t == "double":
+        return "d"
+    if t in ("size_t", "uint64_t", "int64_t"):
+        return "z"
+    if t in ("int", "int32_t", "uint32_t", "hpp_status"):
+        return "i"
+    raise AssertionError(f"unclassified parameter type: {param!r}")
+
+
+def _classify_ctypes(t):
+    if t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+        return "p"
+    if t is ctypes.c_float:
+        return "f"
+    if t is ctypes.c_double:
+        return "d"
+    if ctypes.sizeof(t) == 8:
+        return "z"
+    return "i"
+
+
+def test_ctypes_signatures_match_the_header():
+    """every prototype of include/hpp_b200.h against the argtypes the Python binding declares: same parameter count, and
+    pointer / float / double / 32-bit / 64-bit class per parameter (a float passed as a double is silent garbage)"""
+    import hybrid_path_planning_b200.capi as capi
+    L = capi.lib()
+    src = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+    protos = re.findall(r"\b(hpp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) >= 30
+    checked = 0
+    for name, params in protos:
+        f = getattr(L, name)
+        if f.argtypes is None:
+            continue
+        want = [] if params.strip() in ("", "void") else [_classify_c(p) for p in params.split(",")]
+        got = [_classify_ctypes(t) for t in f.argtypes]
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
+        checked += 1
+    assert checked >= 30
