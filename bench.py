@@ -67,22 +67,54 @@ def patch_goals(side, k):
     return g
 
 
+def bench_config(side, F):
+    """config of the headline line -- shared by both arms (the reference arm runs a bounded sample of this workload)"""
+    return {"workload": "cfg3", "map": f"{side}x{side} 8x8-block Bernoulli(0.30), seed 1+rank", "resolution": RES,
+            "fields_per_step": F,
+            "goals": "the 25 cells of the cleared 5x5 goal patch, then seeded free cells of the central quarter",
+            "step": f"one map message (layers: K1 / Grid_map ctor) + {F} goal fields on it "
+                    f"(K3a / holonomicCostsWithObstacles_planning)",
+            "per_rank": "own map",
+            "l2": "flushed between steps by a 256 MiB write outside the per-step event pair; one cost field "
+                  "(134 MB) alone exceeds the 126 MB L2",
+            "timing": "CUDA events on the library's stream, per step, summed; max over ranks"}
+
+
 # --------------------------------------------------------------------------------------------- reference arm
-_REF_OCC = None  # the map, synthesised once in the parent and inherited by the forked workers
+# The reference's own CPU implementation of the cfg3 step on all host cores.  Like the device arm, ONE layer build per
+# map message and F goal fields on it:
+#   * layers: cv2.distanceTransform (IPP off, all cores) -- the library call RS/src/Grid_map.cpp:64 makes -- built once
+#     per map message in the parent and handed to the workers' planner instances through shared memory;
+#   * fields: one worker process per core, each holding ONE planner instance per map message (reference's Grid_map
+#     stand-in constructed from the supplied layers + HybridAstar, oracle/_ref) and calling the reference's
+#     holonomicCostsWithObstacles_planning on it once per goal -- no second Grid_map, no layer rebuild per field.
+# A timed "step" is a bounded sample of the workload: one wave of `cores` fields, plus cores/F of a layer build
+# (the build is timed for real on every map message of the run and charged pro rata, exactly the device arm's ratio of
+# one build per F fields).
+_REF = {}  # parent -> forked workers: occupancy, shared layer buffers, side
 
 
-def _ref_worker(args):
-    """One cfg3 step on one host core: Grid_map construction (layers) + heuristic field."""
-    goal = args
+def _ref_init():
+    _REF["planner"] = None
+    _REF["version"] = -1
+
+
+def _ref_worker(task):
+    """One goal field on one host core."""
+    goal, version, want_sum = task
     from oracle import pyorc as O
-    occ = _REF_OCC
+    occ = _REF["occ"]
     if O.ref_available():
-        r = O.Ref(0, occ, RES)               # reference-side Grid_map (stand-in ctor builds the layers)
-        h = r.heuristic(goal)                # reference's own HybridAstar::holonomicCostsWithObstacles_planning
+        if _REF["version"] != version:          # new map message: this worker's planner instance is rebuilt
+            _REF["planner"] = None
+            _REF["planner"] = O.Ref(0, occ, RES, layers=(_REF["obstacle"], _REF["distance"]))
+            _REF["version"] = version
+        h = _REF["planner"].heuristic(goal, want=want_sum)
     else:
-        O.edt_layers(occ, np.float32(RES))
         h, _ = O.heuristic_rs(occ, goal, (0, 0), True)
-    return float(h[goal[1], goal[0]])
+    if want_sum:
+        return float(np.nan_to_num(h[goal[1], :], posinf=0.0).sum())
+    return 0.0
 
 
 def reference_arm(args):
@@ -93,38 +125,161 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = min(os.cpu_count() or 1, args.ref_cores or 64)
-    side = args.side
-    c = side // 2
-    goals = patch_goals(side, cores)   # same goal list as the device arm
+    side, F = args.side, args.fields
+    n = side * side
+    goals = patch_goals(side, F)                # same goal list as the device arm
     kind = "reference" if O.ref_available() else "port"
-    global _REF_OCC
-    _REF_OCC, _ = cfg3_map(side, seed=1)
+    occ, _ = cfg3_map(side, seed=1)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        tasks = [goals[i] for i in range(cores)]
-        for _ in range(args.warmup):
-            pool.map(_ref_worker, tasks)
+    ob_raw, di_raw = ctx.RawArray("f", n), ctx.RawArray("f", n)
+    _REF.update(occ=occ, obstacle=np.frombuffer(ob_raw, np.float32), distance=np.frombuffer(di_raw, np.float32))
+    layer_ms = {}
+
+    def map_message(threads):
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pool.map(_ref_worker, tasks)
-        dt = time.perf_counter() - t0
-    cells = side * side * cores * args.steps
-    value = cells / dt / 1e6
+        ob, di = O.cv2_layers(occ, RES, threads)
+        _REF["obstacle"][:] = ob
+        _REF["distance"][:] = di
+        return (time.perf_counter() - t0) * 1e3
+
+    layer_ms["1_thread"] = map_message(1)
+    builds = [map_message(cores)]
+    version = 0
+    fields_done = 0
+    with ctx.Pool(cores, initializer=_ref_init) as pool:
+        def wave(k, want_sum=False):
+            return pool.map(_ref_worker, [(goals[(k * cores + i) % F], version, want_sum) for i in range(cores)],
+                            chunksize=1)
+        for k in range(args.warmup):
+            wave(k)
+        t_waves = []
+        sums = None
+        for k in range(args.steps):
+            if fields_done // F != (fields_done + cores) // F and k > 0:   # the next map message of the stream is due
+                builds.append(map_message(cores))
+                version += 1
+            t0 = time.perf_counter()
+            r = wave(k, want_sum=(k == 0))
+            t_waves.append(time.perf_counter() - t0)
+            fields_done += cores
+            if k == 0:
+                sums = r
+    layer_ms["n_threads"] = min(builds)
+    t_layer_share = layer_ms["n_threads"] / 1e3 * cores / F
+    dt = sum(t_waves) + t_layer_share * args.steps
+    value = n * cores * args.steps / dt / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg3", "map": f"{side}x{side} 8x8-block Bernoulli(0.30), seed 1", "resolution": RES,
-                   "fields_per_step": cores},
+        "config": bench_config(side, F),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{args.steps} steps x {cores} concurrent fields (one per core, goals inside the "
-                                   f"cleared goal patch) of the cfg3 step: Grid_map layers + heuristic; wall clock "
-                                   f"over the process pool, map synthesis excluded",
+                         "sample": f"per step one wave of {cores} goal fields (one per core, first {cores}-field waves "
+                                   f"of the device arm's {F}-goal list) by the reference's own "
+                                   f"holonomicCostsWithObstacles_planning on one planner instance per worker and map "
+                                   f"message, plus {cores}/{F} of one layer build (cv2.distanceTransform, IPP off, "
+                                   f"{cores} threads: {layer_ms['n_threads']:.0f} ms; 1 thread: "
+                                   f"{layer_ms['1_thread']:.0f} ms) -- the device arm's ratio of one layer build per "
+                                   f"{F} fields; wall clock of the waves over the process pool, map synthesis excluded",
+                         "layers_ms": layer_ms, "layer_builds_timed": len(builds),
+                         "wave_ms": [t * 1e3 for t in t_waves[:8]],
+                         "field_row_sums_first_wave": sums,
                          "flags": "-O2 -ffp-contract=off (upstream default is -O0)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- CPU legs of the extras
+# (run in a child process started before/outside CUDA: fork after CUDA initialisation is unsafe)
+def _cfg4_worker(task):
+    lo, hi = task
+    from oracle import pyorc as O
+    return O.collide_circles(_REF["om"], _REF["poses"][lo:hi])
+
+
+def _cfg5_worker(task):
+    k, lo, hi = task
+    from oracle import pyorc as O
+    j = _REF["jobs"][k]
+    use_ref = O.ref_available()
+    pl = O.Ref(0, j["pm"], RES) if use_ref else O.Map(j["pm"], RES)
+    solved = 0
+    for i in range(lo, hi):
+        if use_ref:
+            solved += len(pl.run(tuple(j["starts"][i]), tuple(j["goals"][i]), max_states=20000)) > 1
+        else:
+            solved += len(O.run(pl, 0, tuple(j["starts"][i]), tuple(j["goals"][i]), quirks=True)["traj"]) > 1
+    return solved
+
+
+def cfg5_jobs(nmaps, npairs, collide):
+    """cfg5 workload: nmaps synthetic parking maps x npairs collision-free start/goal pairs (collide(map k, poses) ->
+    verdicts; device and oracle verdicts are bit-identical, so both arms draw the same pairs)"""
+    jobs = []
+    for k in range(nmaps):
+        pm = parking_map(256, seed=k)
+        cand = random_poses(6 * npairs + 2000, 256, 256, margin=3.0, seed=100 + k)
+        free = cand[collide(k, pm, cand) == 0][:2 * npairs]
+        jobs.append(dict(pm=pm, starts=free[:npairs], goals=free[npairs:2 * npairs]))
+    return jobs
+
+
+def cpu_extras(args):
+    """cfg4 / cfg5 on all host cores: JSON on stdout"""
+    import multiprocessing as mp
+    from oracle import pyorc as O
+    O.build()
+    cores = min(os.cpu_count() or 1, args.ref_cores or 64)
+    ctx = mp.get_context("fork")
+    out = {}
+    # cfg4: the full 8192^2 distance layer (cv2 EDT = the oracle's, bit-identical), a 2*10^6-pose sample of the 10^7
+    side, ns = 8192, 2_000_000
+    occ, _ = cfg3_map(side, seed=2)
+    om = O.Map(occ, RES, with_layers=False)
+    om.obstacle, om.distance = O.cv2_layers(occ, RES, cores)
+    om.c.distance = om.distance.ctypes.data
+    poses = random_poses(10_000_000, side, side, margin=2.0, seed=3)[:ns]
+    _REF.update(om=om, poses=poses)
+    with ctx.Pool(cores) as pool:
+        chunks = [(i * ns // (4 * cores), (i + 1) * ns // (4 * cores)) for i in range(4 * cores)]
+        pool.map(_cfg4_worker, chunks[:cores])
+        t0 = time.perf_counter()
+        v = np.concatenate(pool.map(_cfg4_worker, chunks, chunksize=1))
+        t = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.collide_circles(om, poses[:200_000])
+    t1 = time.perf_counter() - t0
+    out["cfg4"] = {"checks_per_s": ns / t, "cores": cores, "kind": "port",
+                   "sample": f"the first {ns} of the 10^7 poses on the full 8192^2 layer, C loop over the poses "
+                             f"(orc_collide_circles_batch), {cores} worker processes; RS/src/Grid_map.cpp itself needs "
+                             f"grid_map_core and cannot be compiled here, so this is the oracle port of "
+                             f"isSingleStateCollisionFree",
+                   "checks_per_s_1core": 200_000 / t1, "colliding_fraction": float(v.mean()),
+                   "verdict_sum": int(v.sum())}
+    del _REF["om"], _REF["poses"]
+    # cfg5: all 8192 queries (8 maps x 1024 pairs) through the compiled reference's HybridAstar::run, one planner instance
+    # per (worker, map chunk)
+    nmaps, npairs = 8, 1024
+    jobs = cfg5_jobs(nmaps, npairs, lambda k, pm, cand: O.collide_circles(O.Map(pm, RES), cand))
+    _REF["jobs"] = jobs
+    per = 64
+    tasks = [(k, lo, min(lo + per, npairs)) for lo in range(0, npairs, per) for k in range(nmaps)]
+    with ctx.Pool(cores) as pool:
+        pool.map(_cfg5_worker, [(k, 0, 2) for k in range(min(nmaps, cores))])
+        t0 = time.perf_counter()
+        solved = sum(pool.map(_cfg5_worker, tasks, chunksize=1))
+        t = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _cfg5_worker((0, 0, 64))
+    t1 = time.perf_counter() - t0
+    out["cfg5"] = {"queries_per_s": nmaps * npairs / t, "cores": cores,
+                   "kind": "reference" if O.ref_available() else "port", "queries": nmaps * npairs, "solved": solved,
+                   "sample": f"all {nmaps * npairs} queries, HybridAstar::run of the compiled reference, {cores} worker "
+                             f"processes, {per} queries per task",
+                   "queries_per_s_1core": 64 / t1}
+    print(json.dumps(out), flush=True)
 
 
 # --------------------------------------------------------------------------------------------- clocks sampler
@@ -296,6 +451,12 @@ def ours_arm(args):
     m.heuristic_rs(goal, (0, 0), out=cost_h[0])
     t_single_e2e = time.perf_counter() - t0
 
+    # goal-row sums of the first fields of the device-resident batch: compared with the reference arm's (cpu_baseline)
+    m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost_dev)
+    ctx.sync()
+    cview = cost_dev.view(F, side, side)
+    row_sums = [float(np.nan_to_num(cview[f, int(goals[f][1]), :].cpu().numpy(), posinf=0.0).sum())
+                for f in range(min(F, 64))]
     peak, peak_src = measured_peak()
     heur_ms = statistics.mean(ms_heur)
     achieved = HEUR_BYTES_PER_CELL * n * F / (heur_ms / 1e3) / 1e9
@@ -311,13 +472,7 @@ def ours_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg3", "map": f"{side}x{side} 8x8-block Bernoulli(0.30), seed 1+rank", "resolution": RES,
-                   "fields_per_step": F, "goals": "the 25 cells of the cleared 5x5 goal patch, then seeded free cells of the central quarter",
-                   "step": f"hpp_map_update_dev (K1) + hpp_heuristic_batch_dev (K3a, {F} fields in one launch)",
-                   "per_rank": "own map",
-                   "l2": "flushed between steps by a 256 MiB write outside the per-step event pair; one cost field "
-                         "(134 MB) alone exceeds the 126 MB L2",
-                   "timing": "CUDA events on the library's stream, per step, summed; max over ranks"},
+        "config": bench_config(side, F),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(8 * n * F),
                 "steps": e2e_steps, "api": "hpp_map_update + hpp_heuristic_batch (host buffers, pinned)",
@@ -336,8 +491,14 @@ def ours_arm(args):
     line["extra"] = {"single_field": {"ms_device": min(ts1) * 1e3, "mcells_per_s_device": n / min(ts1) / 1e6,
                                       "ms_e2e": t_single_e2e * 1e3, "api": "hpp_heuristic_rs (host buffer, D2H inside)"}}
     if rank == 0 and world == 1 and not args.no_extras:
-        line["extra"].update(extras(ctx, torch, hpp, stream))
-        line["cpu_baseline"] = cpu_baseline(args)
+        cpu_x = cpu_extras_child(args)
+        line["extra"].update(extras(ctx, torch, hpp, stream, cpu_x))
+        cb = cpu_baseline(args)
+        ref_sums = cb.pop("field_row_sums_first_wave", None) if isinstance(cb, dict) else None
+        if ref_sums:
+            cb["fields_checked_against_device"] = len(ref_sums)
+            cb["device_fields_match_reference"] = bool(ref_sums == row_sums[:len(ref_sums)])
+        line["cpu_baseline"] = cb
     if rank == 0:
         print(json.dumps(line), flush=True)
     m.close()
@@ -353,8 +514,8 @@ def k4_traffic():
         return None
 
 
-def extras(ctx, torch, hpp, stream):
-    """cfg4 (collision checks/s) and a cfg5 sample (queries/s), device numbers + bounded CPU samples."""
+def extras(ctx, torch, hpp, stream, cpu_x):
+    """cfg4 (collision checks/s) and cfg5 (queries/s): device numbers, with the all-core CPU figures of cpu_x beside."""
     from oracle import pyorc as O
     out = {}
     # ---- cfg4: 8192^2 distance layer, 10^7 poses
@@ -387,12 +548,9 @@ def extras(ctx, torch, hpp, stream):
     t0 = time.perf_counter()
     m.collide_circles(pin, out=vout)
     t_e2e = time.perf_counter() - t0
-    ns = 200_000
-    om = O.Map(occ[:2048, :2048], RES)            # CPU sample: a 2048^2 corner of the same map
-    ps = random_poses(ns, 2048, 2048, margin=2.0, seed=4)
-    t0 = time.perf_counter()
-    vo = O.collide_circles(om, ps)
-    t_cpu = time.perf_counter() - t0
+    cpu4 = dict(cpu_x.get("cfg4", {"error": cpu_x.get("error", "no CPU leg")}))
+    if "verdict_sum" in cpu4:   # the CPU leg checked the first 2*10^6 poses of the same list on the same map
+        cpu4["device_verdicts_match"] = bool(int(verd[:2_000_000].sum().item()) == cpu4["verdict_sum"])
     out["cfg4_collision"] = {
         "checks_per_s": npose / t, "ms": t * 1e3, "colliding_fraction": float(verd.float().mean().item()),
         "roofline": {"bound": "hbm", "achieved": COLLIDE_BYTES_PER_POSE * npose / t / 1e9, "peak": peak,
@@ -401,9 +559,7 @@ def extras(ctx, torch, hpp, stream):
                      "note": "random 4-byte gathers cost whole DRAM sectors: the measured DRAM traffic (ncu) is 3.6x the "
                              "algorithmic bytes and runs at 87 % of the measured HBM peak"},
         "e2e_checks_per_s": npose / t_e2e, "h2d_bytes": 24 * npose, "d2h_bytes": npose,
-        "cpu": {"checks_per_s": ns / t_cpu, "cores": 1, "kind": "port",
-                "sample": f"{ns} poses on a 2048^2 corner (python-loop overhead of the ctypes harness included)",
-                "colliding_fraction": float(vo.mean())}}
+        "cpu": cpu4}
     m.close()
     del poses, verd, d_occ
     # ---- cfg5: 8192 RS queries = 8 synthetic parking maps x 1024 start/goal pairs.  A query is one warp from start to
@@ -411,14 +567,15 @@ def extras(ctx, torch, hpp, stream):
     # per map, from host threads (the C ABI is re-entrant across contexts; ctypes releases the GIL during the calls).
     import threading
     nmaps, npairs = 8, 1024
-    jobs = []
-    for k in range(nmaps):
-        pm = parking_map(256, seed=k)
-        cx = hpp.Context(torch.cuda.current_device())
-        mm = hpp.Map(cx, pm, RES)
-        cand = random_poses(6 * npairs + 2000, 256, 256, margin=3.0, seed=100 + k)
-        free = cand[mm.collide_circles(cand) == 0][:2 * npairs]     # device verdicts (bit-exact with the oracle: tests)
-        jobs.append(dict(ctx=cx, map=mm, pm=pm, starts=free[:npairs], goals=free[npairs:2 * npairs]))
+    cxs, mms = {}, {}
+
+    def dev_collide(k, pm, cand):                    # device verdicts (bit-exact with the oracle: tests)
+        cxs[k] = hpp.Context(torch.cuda.current_device())
+        mms[k] = hpp.Map(cxs[k], pm, RES)
+        return mms[k].collide_circles(cand)
+    jobs = cfg5_jobs(nmaps, npairs, dev_collide)
+    for k, j in enumerate(jobs):
+        j.update(ctx=cxs[k], map=mms[k])
     for j in jobs:                                   # warm-up: every context grows its device scratch once
         j["map"].plan_batch(hpp.VARIANT_RS, j["starts"], j["goals"])
 
@@ -434,12 +591,6 @@ def extras(ctx, torch, hpp, stream):
             t.join()
         t_gpu = min(t_gpu, time.perf_counter() - t0)
     solved = int(sum((j["plans"]["n_states"] > 1).sum() for j in jobs))
-    om0 = O.Map(jobs[0]["pm"], RES)
-    t0 = time.perf_counter()
-    n_cpu = 32
-    for i in range(n_cpu):
-        O.run(om0, 0, tuple(jobs[0]["starts"][i]), tuple(jobs[0]["goals"][i]), quirks=True)
-    t_cpu = time.perf_counter() - t0
     for j in jobs:
         j["map"].close()
         j["ctx"].close()
@@ -451,7 +602,9 @@ def extras(ctx, torch, hpp, stream):
     out["cfg5_queries"] = {"queries_per_s": nq / t_gpu, "queries": nq, "solved": solved, "maps_in_flight": nmaps,
                            "api": "hpp_plan_batch per map (host buffers; heuristic fields + device-resident A*), one "
                                   "context per map, maps planned concurrently from host threads; best of 3 passes",
-                           "cpu": {"queries_per_s": n_cpu / t_cpu, "cores": 1, "kind": "port", "sample": f"{n_cpu} queries"}}
+                           "cpu": cpu_x.get("cfg5", {"error": cpu_x.get("error", "no CPU leg")})}
+    if "solved" in out["cfg5_queries"]["cpu"]:
+        out["cfg5_queries"]["cpu"]["device_solved_count_matches"] = bool(out["cfg5_queries"]["cpu"]["solved"] == solved)
     return out
 
 
@@ -516,11 +669,24 @@ def fixture_latency(ctx, hpp, O):
     return out
 
 
+def cpu_extras_child(args):
+    """cfg4 / cfg5 on all host cores, in a child process (fork after CUDA init is unsafe)."""
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "cpu-extras"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "RANK": "0"})
+        for ln in r.stdout.splitlines():
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or "no output")[-300:]}
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)}
+
+
 def cpu_baseline(args):
     """The reference arm on a bounded sample, in a child process (fork after CUDA init is unsafe)."""
     try:
-        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-               "--side", str(args.side)]
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+               "--side", str(args.side), "--fields", str(args.fields)]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0"})
         for ln in r.stdout.splitlines():
             if ln.startswith("{"):
@@ -535,7 +701,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-extras"])
     ap.add_argument("--side", type=int, default=4096)
     ap.add_argument("--fields", type=int, default=148, help="goal fields (queries) per step; default = one per SM of a B200")
     ap.add_argument("--ref-cores", type=int, default=0)
@@ -544,6 +710,8 @@ def main():
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         reference_arm(args)
+    elif args.impl == "cpu-extras":
+        cpu_extras(args)
     else:
         if args.warmup < 3:
             args.warmup = 3                 # timing rule: W >= 3

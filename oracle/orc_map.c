@@ -386,6 +386,12 @@ int orc_collide_circles(const orc_map *m, const orc_car *car, double x, double y
   return 0;
 }
 
+/* the same check over n poses (xyh: n x 3), one call per pose exactly as above: the loop the CPU baselines time */
+void orc_collide_circles_batch(const orc_map *m, const orc_car *car, const double *xyh, size_t n, uint8_t *verdict) {
+  size_t i;
+  for (i = 0; i < n; i++) verdict[i] = (uint8_t)orc_collide_circles(m, car, xyh[3 * i], xyh[3 * i + 1], xyh[3 * i + 2]);
+}
+
 /* ------------------------------------------------------------------ a9 */
 typedef struct { float x, y; } pt32;
 
@@ -468,6 +474,11 @@ int orc_collide_sat(const orc_map *m, const orc_car *car, double x, double y, do
   gx = orc_cell_x(m, x);
   gy = orc_cell_y(m, y);
   return !orc_in_bounds(m, gx, gy);
+}
+
+void orc_collide_sat_batch(const orc_map *m, const orc_car *car, const double *xyh, size_t n, uint8_t *verdict) {
+  size_t i;
+  for (i = 0; i < n; i++) verdict[i] = (uint8_t)orc_collide_sat(m, car, xyh[3 * i], xyh[3 * i + 1], xyh[3 * i + 2]);
 }
 
 /* ------------------------------------------------------------------ f1 */

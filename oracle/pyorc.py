@@ -78,6 +78,9 @@ def lib():
         L = C.CDLL(os.path.join(HERE, "liborc.so"))
         L.orc_collide_circles.argtypes = [C.POINTER(OrcMap), C.POINTER(OrcCar), C.c_double, C.c_double, C.c_double]
         L.orc_collide_sat.argtypes = [C.POINTER(OrcMap), C.POINTER(OrcCar), C.c_double, C.c_double, C.c_double]
+        L.orc_collide_circles_batch.argtypes = [C.POINTER(OrcMap), C.POINTER(OrcCar), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_collide_sat_batch.argtypes = L.orc_collide_circles_batch.argtypes
+        L.orc_collide_circles_batch.restype = L.orc_collide_sat_batch.restype = None
         L.orc_rs_all_paths.argtypes = [C.c_double] * 8 + [C.POINTER(OrcRsPaths)]
         L.orc_dubins_path.argtypes = [C.c_double] * 8 + [C.POINTER(OrcDubins)]
         L.orc_inflate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
@@ -135,6 +138,24 @@ def edt_layers(occ, resolution):
     return obstacle, distance
 
 
+def cv2_layers(occ, resolution, threads=None):
+    """The `obstacle` and `distance` layers with the library call the reference itself makes
+    (RS/src/Grid_map.cpp:56-74: cv::distanceTransform(DIST_L2, DIST_MASK_PRECISE) of the [x][y] image, cv::flip(-1),
+    times the float resolution), through cv2 with IPP off -- bit-identical to edt_layers() (tests/golden/layers_cv2.npz).
+    Used by bench.py's reference arm as the CPU layer build; threads = OpenCV worker threads (None: leave as is)."""
+    import cv2
+    cv2.ipp.setUseIPP(False)
+    if threads is not None:
+        cv2.setNumThreads(int(threads))
+    occ = _i8(occ)
+    free = ~((occ > 20) | (occ < 0))
+    obstacle = free.astype(np.float32).reshape(-1)
+    d = cv2.distanceTransform(np.ascontiguousarray(free.T.astype(np.uint8)), cv2.DIST_L2, cv2.DIST_MASK_PRECISE)
+    d = cv2.flip(d, -1)
+    distance = np.ascontiguousarray((d * np.float32(resolution)).astype(np.float32).T).reshape(-1)
+    return obstacle, distance
+
+
 def edt_sq_exact(occ):
     occ = _i8(occ)
     H, W = occ.shape
@@ -181,17 +202,20 @@ def heuristic_dubins(occ, goal):
 
 
 def collide_circles(m, poses, car=DEFAULT_CAR):
+    """isSingleStateCollisionFree per pose (a C loop over the poses, one orc_collide_circles call each)"""
     cs = car_struct(car)
-    L = lib()
-    poses = np.asarray(poses, np.float64).reshape(-1, 3)
-    return np.array([L.orc_collide_circles(C.byref(m.c), C.byref(cs), p[0], p[1], p[2]) for p in poses], np.uint8)
+    poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 3)
+    out = np.empty(len(poses), np.uint8)
+    lib().orc_collide_circles_batch(C.byref(m.c), C.byref(cs), poses.ctypes.data, len(poses), out.ctypes.data)
+    return out
 
 
 def collide_sat(m, poses, car=DEFAULT_CAR):
     cs = car_struct(car)
-    L = lib()
-    poses = np.asarray(poses, np.float64).reshape(-1, 3)
-    return np.array([L.orc_collide_sat(C.byref(m.c), C.byref(cs), p[0], p[1], p[2]) for p in poses], np.uint8)
+    poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 3)
+    out = np.empty(len(poses), np.uint8)
+    lib().orc_collide_sat_batch(C.byref(m.c), C.byref(cs), poses.ctypes.data, len(poses), out.ctypes.data)
+    return out
 
 
 def motion_commands(variant, car=DEFAULT_CAR):
@@ -290,7 +314,9 @@ def ref_available():
 class Ref:
     """One reference planner instance (variant 0 = RS, 1 = Dubins) on one map."""
 
-    def __init__(self, variant, occ, resolution=0.2, origin=None, car=DEFAULT_CAR, sim_len=4.0, step=1.0):
+    def __init__(self, variant, occ, resolution=0.2, origin=None, car=DEFAULT_CAR, sim_len=4.0, step=1.0, layers=None):
+        """layers = (obstacle, distance) float32 arrays in grid_map layout: RS only, handed to the stand-in Grid_map
+        instead of letting its constructor run the oracle's EDT (the reference arm builds them with cv2)."""
         lib()  # libref_rs.so links against liborc.so
         self.variant = variant
         self.p = "ref_rs_" if variant == 0 else "ref_db_"
@@ -308,8 +334,19 @@ class Ref:
         f = getattr(self.L, self.p + "create")
         f.restype = C.c_void_p
         f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_double]
-        self.ctx = C.c_void_p(f(self.occ.ctypes.data, self.W, self.H, C.c_float(float(res_f)), self.ox, self.oy,
-                                self.car, sim_len, step))
+        if layers is not None and variant == 0:
+            ob = np.ascontiguousarray(layers[0], np.float32).reshape(-1)
+            di = np.ascontiguousarray(layers[1], np.float32).reshape(-1)
+            assert ob.size == di.size == self.W * self.H
+            f = self.L.ref_rs_create_layers
+            f.restype = C.c_void_p
+            f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_void_p, C.c_double,
+                          C.c_double, C.c_void_p, C.c_void_p]
+            self.ctx = C.c_void_p(f(self.occ.ctypes.data, self.W, self.H, C.c_float(float(res_f)), self.ox, self.oy,
+                                    self.car, sim_len, step, ob.ctypes.data, di.ctypes.data))
+        else:
+            self.ctx = C.c_void_p(f(self.occ.ctypes.data, self.W, self.H, C.c_float(float(res_f)), self.ox, self.oy,
+                                    self.car, sim_len, step))
 
     def __del__(self):
         try:
@@ -319,24 +356,29 @@ class Ref:
         except Exception:
             pass
 
-    def heuristic(self, goal):
-        cost = np.empty((self.H, self.W), np.float64)
+    def heuristic(self, goal, want=True):
+        """holonomicCostsWithObstacles_planning of this planner instance; want=False skips the copy of the result"""
+        cost = np.empty((self.H, self.W), np.float64) if want else None
         if self.variant == 0:
-            f = self.L.ref_rs_heuristic
-            f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p]
-            f(self.occ.ctypes.data, self.W, self.H, C.c_float(float(self.res_f)), self.ox, self.oy, goal[0], goal[1],
-              cost.ctypes.data)
+            f = self.L.ref_rs_heuristic_ctx
+            f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            f.restype = None
+            f(self.ctx, goal[0], goal[1], cost.ctypes.data if want else None)
         else:
+            cost = np.empty((self.H, self.W), np.float64)
             f = self.L.ref_db_heuristic
             f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
             f(self.ctx, goal[0], goal[1], cost.ctypes.data)
         return cost
 
     def collide(self, poses):
-        f = getattr(self.L, self.p + "collide")
-        f.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
-        poses = np.asarray(poses, np.float64).reshape(-1, 3)
-        return np.array([f(self.ctx, p[0], p[1], p[2]) for p in poses], np.uint8)
+        f = getattr(self.L, self.p + "collide_batch")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        f.restype = None
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 3)
+        out = np.empty(len(poses), np.uint8)
+        f(self.ctx, poses.ctypes.data, len(poses), out.ctypes.data)
+        return out
 
     def expand(self, pose, cost, steer, direction):
         f = getattr(self.L, self.p + "expand")

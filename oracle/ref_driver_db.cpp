@@ -53,6 +53,13 @@ API int ref_db_collide(void *ctx, double x, double y, double h)
     return (c->gm.checkCollision(s, poly) || !c->gm.isPointInBounds(s.gridx, s.gridy)) ? 1 : 0;
 }
 
+// the same predicate over n poses: the loop the CPU baseline of the SAT footprint check times
+API void ref_db_collide_batch(void *ctx, const double *xyh, size_t n, uint8_t *verdict)
+{
+    for (size_t i = 0; i < n; ++i)
+        verdict[i] = (uint8_t)ref_db_collide(ctx, xyh[3 * i], xyh[3 * i + 1], xyh[3 * i + 2]);
+}
+
 API int ref_db_expand(void *ctx, double x, double y, double h, double cost, double steer, int dir,
                       double *traj, double *ccost, double *csteer, int *cdir, int sim)
 {

@@ -30,15 +30,6 @@ static void poison_heuristic_cache(int goal_gx, int goal_gy)
     (void)ha.holonomicCostsWithObstacles_planning(n);
 }
 
-API int ref_rs_motion_commands(const double *car, double *steer, double *dir)
-{
-    // motionCommand is private; re-run the reference's loop bounds through a HybridAstar and read the
-    // commands back from the children of a free-space expansion is overkill -- the command list is
-    // produced by HybridAstar::motionCommands (RS/src/HybridAstar.cpp:14-23), exercised via ref_rs_expand.
-    (void)car; (void)steer; (void)dir;
-    return 0;
-}
-
 API void ref_rs_heuristic(const int8_t *occ, int W, int H, float res, double ox, double oy, int goal_gx, int goal_gy, double *cost)
 {
     MuteCout mute;
@@ -105,6 +96,41 @@ API void *ref_rs_create(const int8_t *occ, int W, int H, float res, double ox, d
     return new RsCtx(g, car, sim_len, step);
 }
 API void ref_rs_destroy(void *ctx) { delete (RsCtx *)ctx; }
+
+// Same, with the obstacle / distance layers supplied by the caller (grid_map layout, W*H floats each) instead of being
+// computed by the stand-in constructor: the reference arm of bench.py builds them once per map message with
+// cv2.distanceTransform -- the call RS/src/Grid_map.cpp:64 makes -- and hands them to every planner instance.
+API void *ref_rs_create_layers(const int8_t *occ, int W, int H, float res, double ox, double oy, const double *car,
+                               double sim_len, double step, const float *obstacle, const float *distance)
+{
+    MuteCout mute;
+    auto g = make_grid(occ, W, H, res, ox, oy);
+    ref_standin_ext_obstacle = obstacle;
+    ref_standin_ext_distance = distance;
+    RsCtx *c = new RsCtx(g, car, sim_len, step);
+    ref_standin_ext_obstacle = ref_standin_ext_distance = nullptr;
+    return c;
+}
+
+// holonomicCostsWithObstacles_planning of an existing planner instance (no second Grid_map): one field per call
+API void ref_rs_heuristic_ctx(void *ctx, int goal_gx, int goal_gy, double *cost)
+{
+    MuteCout mute;
+    RsCtx *c = (RsCtx *)ctx;
+    poison_heuristic_cache(goal_gx, goal_gy);
+    auto n = make_node(0, 0, 0, goal_gx, goal_gy, 0, 0, 1);
+    std::vector<double> out = c->ha.holonomicCostsWithObstacles_planning(n);
+    if (cost)
+        std::memcpy(cost, out.data(), sizeof(double) * out.size());
+}
+
+// isSingleStateCollisionFree over n poses (verdict 1 = collision / outside, the C ABI's polarity)
+API void ref_rs_collide_batch(void *ctx, const double *xyh, size_t n, uint8_t *verdict)
+{
+    RsCtx *c = (RsCtx *)ctx;
+    for (size_t i = 0; i < n; ++i)
+        verdict[i] = c->gm.isSingleStateCollisionFree(State(xyh[3 * i], xyh[3 * i + 1], xyh[3 * i + 2])) ? 1 : 0;
+}
 
 API void ref_rs_distance_layer(void *ctx, float *out)
 {

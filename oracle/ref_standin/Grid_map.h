@@ -21,6 +21,11 @@
 #include "State.h"
 #include "../orc.h"
 
+// Layers computed elsewhere (bench.py's reference arm builds them with cv2.distanceTransform, the library call the real
+// RS/src/Grid_map.cpp:64 makes): when set, the constructor copies them instead of running the oracle's EDT.
+inline const float *ref_standin_ext_obstacle = nullptr;
+inline const float *ref_standin_ext_distance = nullptr;
+
 class Grid_map
 {
 private:
@@ -45,8 +50,14 @@ public:
         height = map_data.info.height;
         obstacle_layer_.resize((size_t)width * height);
         distance_layer_.resize((size_t)width * height);
-        orc_edt_layers(map_data_.data.data(), (int)width, (int)height, map_data.info.resolution,
-                       obstacle_layer_.data(), distance_layer_.data());
+        if (ref_standin_ext_obstacle && ref_standin_ext_distance)
+        {
+            std::copy(ref_standin_ext_obstacle, ref_standin_ext_obstacle + obstacle_layer_.size(), obstacle_layer_.begin());
+            std::copy(ref_standin_ext_distance, ref_standin_ext_distance + distance_layer_.size(), distance_layer_.begin());
+        }
+        else
+            orc_edt_layers(map_data_.data.data(), (int)width, (int)height, map_data.info.resolution,
+                           obstacle_layer_.data(), distance_layer_.data());
     }
     ~Grid_map() {}
 

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from tests.common import block_map, random_poses
+from tests.common import bits_equal, block_map, random_poses
 
 pytestmark = pytest.mark.gpu
 
@@ -81,8 +81,7 @@ def test_collide_empty_batch_and_cells(ctx):
 
 
 def test_collide_circles_cfg4_size(ctx):
-    """BASELINE cfg4 scale-down that the oracle finishes in seconds (2048^2 layer, 2*10^5 poses) bit-exact, plus the
-    full 8192^2 / 10^7 run checked through a checksum of the verdicts of a strided 1% sample against the oracle."""
+    """BASELINE cfg4 scale-down that the oracle finishes in seconds (2048^2 layer, 2*10^5 poses), bit-exact."""
     import hybrid_path_planning_b200 as hpp
     from oracle import pyorc as O
     from tests.common import cfg3_map
@@ -93,4 +92,32 @@ def test_collide_circles_cfg4_size(ctx):
     got = m.collide_circles(poses)
     want = O.collide_circles(om, poses)
     assert np.array_equal(got, want)
+    m.close()
+
+
+def test_collide_circles_cfg4_full_size(ctx):
+    """BASELINE cfg4 at its named size -- the launch bench.py times: 8192^2 distance layer (same generator and seed),
+    10^7 poses.  The distance layer is bit-compared with the oracle's; a strided 1 % sample of the verdicts (every
+    100th pose, 10^5 of them) is bit-compared with the oracle's isSingleStateCollisionFree; the whole verdict vector
+    is checked through its colliding fraction against the sample's and through the host-buffer entry point."""
+    import torch
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    from tests.common import cfg3_map
+    side, npose = 8192, 10_000_000
+    occ, _ = cfg3_map(side, seed=2)
+    m = hpp.Map(ctx, occ, 0.2)
+    om = O.Map(occ, 0.2)
+    _, dist = m.layers()
+    assert bits_equal(dist, om.distance)
+    poses = random_poses(npose, side, side, margin=2.0, seed=3)
+    d_poses = torch.from_numpy(poses).cuda()
+    verd = torch.empty(npose, dtype=torch.uint8, device="cuda")
+    m.collide_circles_dev(d_poses, npose, verd)
+    ctx.sync()
+    got = verd.cpu().numpy()
+    want = O.collide_circles(om, poses[::100])
+    assert np.array_equal(got[::100], want), f"{(got[::100] != want).sum()} of {len(want)} sampled verdicts differ"
+    assert abs(got.mean() - want.mean()) < 5e-3
+    assert np.array_equal(m.collide_circles(poses[:1_000_000]), got[:1_000_000])   # host-buffer path, same verdicts
     m.close()

@@ -118,6 +118,74 @@ def test_heuristic_cfg3_full_size(ctx):
     m.close()
 
 
+def test_heuristic_cfg3_bench_launch_148_fields(ctx):
+    """The launch bench.py times: hpp_heuristic_batch_dev, 148 goal fields on the 4096^2 cfg3 map, default
+    environment (one CTA of 20 warps per field, list schedule, longest-first ordering).  Fields of the patch goal, of
+    two drawn goals and of the last goal are bit-compared with the oracle (reference-equivalent: quirks on, and the
+    test asserts they do not fire); every other field is checked through size-independent properties: zero at its
+    goal and nowhere else, +inf exactly on the occupied cells and the cells the oracle finds unreachable, and the
+    fixed-point equation on a strided sample of rows."""
+    import torch
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    from bench import patch_goals
+    side, F = 4096, 148
+    occ, _ = cfg3_map(side, seed=1)
+    goals = np.array(patch_goals(side, F), np.int32)
+    d_occ = torch.from_numpy(occ).cuda()
+    m = hpp.Map(ctx, (side, side), 0.2, device_occ=d_occ)
+    cost = torch.empty(F * side * side, dtype=torch.float64, device="cuda")
+    reps = m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost, want_reports=True)
+    ctx.sync()
+    cost = cost.view(F, side, side)
+    want0 = None
+    for f in (0, 25, 77, F - 1):
+        gx, gy = (int(v) for v in goals[f])
+        want, q = O.heuristic_rs(occ, (gx, gy), (0, 0), quirks=True)
+        assert not q.h1_fired and not q.h2_clamped
+        got = cost[f].cpu().numpy()
+        assert bits_equal(got, want), f"field {f}: {(got != want).sum()} cells differ"
+        assert reps[f].reachable == int(np.isfinite(want).sum())
+        if want0 is None:
+            want0 = want
+    # all fields: the reachable set is one connected component of the free cells, shared by every goal inside it
+    reach = torch.from_numpy(np.isfinite(want0)).cuda()
+    occ_t = d_occ.view(side, side) > 0
+    for f in range(F):
+        gx, gy = (int(v) for v in goals[f])
+        c = cost[f]
+        assert float(c[gy, gx]) == 0.0
+        if bool(reach[gy, gx]):
+            assert bool((torch.isfinite(c) == reach).all()), f
+            assert int((c == 0).sum()) == 1
+        assert bool(torch.isinf(c[occ_t]).all())   # every goal of the list is a free cell of the seed-1 map
+    # fixed-point equation on rows 1, 65, 129, ... of every 16th field (fp64, the reference's two additions)
+    near = torch.zeros_like(occ_t)
+    near[1:, :] |= occ_t[:-1, :]
+    near[:-1, :] |= occ_t[1:, :]
+    near[:, 1:] |= occ_t[:, :-1]
+    near[:, :-1] |= occ_t[:, 1:]
+    rows = torch.arange(1, side - 1, 64, device="cuda")
+    for f in range(0, F, 16):
+        c = cost[f]
+        best = torch.full((len(rows), side - 2), float("inf"), dtype=torch.float64, device="cuda")
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dx == 0 and dy == 0:
+                    continue
+                w = 1.0 if (dx == 0 or dy == 0) else 1.414
+                wv = torch.where(near[rows, 1:-1], torch.tensor(w + 5.0, dtype=torch.float64, device="cuda"),
+                                 torch.tensor(w, dtype=torch.float64, device="cuda"))
+                best = torch.minimum(best, c[rows + dy][:, 1 + dx:side - 1 + dx] + wv)
+        cur = c[rows, 1:-1]
+        free = ~occ_t[rows, 1:-1]
+        gx, gy = (int(v) for v in goals[f])
+        isgoal = (rows[:, None] == gy) & (torch.arange(1, side - 1, device="cuda")[None, :] == gx)
+        sel = free & ~isgoal
+        assert bool((cur[sel] == best[sel]).all()), f"field {f}: fixed-point equation violated"
+    m.close()
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_heuristic_batch_host_chunks(ctx, variant):
     """hpp_heuristic_batch: 70 goal cells in one call (>= 64 fields are solved in two overlapped chunks), every field
