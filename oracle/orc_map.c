@@ -29,10 +29,16 @@ int orc_in_collision(const orc_map *m, int x, int y) {
 /*
  * cv::distanceTransform(src, dst, DIST_L2, DIST_MASK_PRECISE) as published in OpenCV's
  * imgproc/src/distransform.cpp (trueDistTrans: Felzenszwalb-Huttenlocher, column pass in
- * integers through a squares table, row pass with the lower envelope in float32).
+ * integers through a squares table, row pass with the lower envelope of parabolas).
  * OpenCV is an un-vendored dependency of the reference (find_package(OpenCV), no version pin;
  * ROS Humble => 4.5.4); this restatement is pinned against cv2 4.13 with IPP disabled
- * (tests/golden/edt_*.npz, tests/test_oracle_golden.py).
+ * (tests/golden/edt_*.npz, tests/test_cpu_oracle_golden.py, and -- where cv2 is importable -- the
+ * 8192-wide cfg4 map in tests/test_cpu_oracle_vs_ref.py).
+ * The parabola intersections are evaluated in DOUBLE here: a float32 evaluation (q*q + f[q] with q > 4096 is
+ * not representable in 24 bits) puts 11 % of the cells of the 8192^2 cfg4 map on the wrong parabola, while
+ * cv2 4.13 returns the exact transform there (= scipy's exact EDT, 0 of 67 M cells differ); with doubles every
+ * intersection of integer parabolas is ordered exactly, so this pass returns sqrtf of the exact squared
+ * distance like cv2 4.13 does.  What OpenCV 4.5.4 itself returns on images wider than 4096 px is unpinned.
  * src is an m-row x n-col 8-bit image (row-major, step n); non-zero = free.
  */
 static void true_dist_trans(const uint8_t *src, int m, int n, float *dst) {
@@ -40,7 +46,7 @@ static void true_dist_trans(const uint8_t *src, int m, int n, float *dst) {
    * same result whenever the image has at least one zero pixel; 2^32 reproduces what cv2 4.13 returns for an
    * image with none (the constant 65536). */
   const float inf_col = 4294967296.0f;
-  const float inf = 1e15f;              /* envelope sentinels of the row pass */
+  const double inf = 1e15;              /* envelope sentinels of the row pass */
   float *sqr_tab = (float *)malloc(sizeof(float) * (size_t)(2 * (m > n ? m : n) + 2));
   int *d = (int *)malloc(sizeof(int) * (size_t)m);
   int i, j, k;
@@ -61,17 +67,13 @@ static void true_dist_trans(const uint8_t *src, int m, int n, float *dst) {
     }
   }
   free(d);
-  /* stage 2: lower envelope of parabolas along each row, float32 arithmetic */
+  /* stage 2: lower envelope of parabolas along each row */
   {
-    float *inv_tab = (float *)malloc(sizeof(float) * (size_t)(n + 1));
     float *f = (float *)malloc(sizeof(float) * (size_t)(n + 1));
-    float *z = (float *)malloc(sizeof(float) * (size_t)(n + 2));
+    double *z = (double *)malloc(sizeof(double) * (size_t)(n + 2));
     int *v = (int *)malloc(sizeof(int) * (size_t)(n + 1));
-    inv_tab[0] = sqr_tab[0] = 0.f;
-    for (i = 1; i < n; i++) {
-      inv_tab[i] = (float)(0.5 / i);
-      sqr_tab[i] = (float)(i * i);
-    }
+    sqr_tab[0] = 0.f;
+    for (i = 1; i < n; i++) sqr_tab[i] = (float)(i * i); /* used below only for |q - p|, where it is exact */
     for (i = 0; i < m; i++) {
       float *row = dst + (size_t)i * n;
       int p, q;
@@ -83,9 +85,9 @@ static void true_dist_trans(const uint8_t *src, int m, int n, float *dst) {
         float fq = row[q];
         f[q] = fq;
         for (;; k--) {
-          float s;
+          double s;
           p = v[k];
-          s = (fq + sqr_tab[q] - row[p] - sqr_tab[p]) * inv_tab[q - p];
+          s = (((double)fq + (double)q * q) - ((double)row[p] + (double)p * p)) / (2.0 * (q - p));
           if (s > z[k]) {
             k++;
             v[k] = q;
@@ -101,7 +103,6 @@ static void true_dist_trans(const uint8_t *src, int m, int n, float *dst) {
         row[q] = sqrtf(sqr_tab[abs(q - p)] + f[p]);
       }
     }
-    free(inv_tab);
     free(f);
     free(z);
     free(v);

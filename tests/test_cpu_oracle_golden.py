@@ -152,3 +152,22 @@ def test_image_to_occupancy_convention():
         want[255 - (j * 16 + i)] = np.int8(int(val))
     assert bits_equal(got.reshape(-1), want)
     assert got.reshape(-1)[255] == 100 and got.reshape(-1)[0] == 0
+
+
+def test_edt_layers_wide_maps_against_live_cv2():
+    """Maps wider than 4096 cells: a float32 evaluation of the parabola intersections (q*q + f[q] beyond 24 bits) puts
+    cells on the wrong parabola; cv2 4.13 (IPP off) returns the exact transform there and so must the oracle (the
+    8192^2 cfg4 map differs in 11 % of its cells otherwise).  cv2 is part of the image, here and on the GPU box."""
+    cv2 = pytest.importorskip("cv2")
+    from tests.common import cfg3_map
+    rng = np.random.default_rng(3)
+    sparse = np.zeros((40, 9000), np.int8)
+    for _ in range(25):
+        y, x = rng.integers(0, 38), rng.integers(0, 8990)
+        sparse[y:y + 2, x:x + 3] = 100
+    tall = np.ascontiguousarray(sparse.T)
+    strip = cfg3_map(8192, seed=2)[0][4000:4096]          # 96 rows of the cfg4 map, full width
+    for occ in (sparse, tall, strip):
+        ob, di = O.edt_layers(occ, np.float32(0.2))
+        ob2, di2 = O.cv2_layers(occ, 0.2)
+        assert bits_equal(ob, ob2) and bits_equal(di, di2), f"{(di != di2).sum()} cells differ"
