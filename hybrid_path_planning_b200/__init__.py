@@ -6,6 +6,8 @@ shells under ``host/`` that keep the reference's class API.  This Python package
 binding of the C ABI used by the tests and by bench.py.  There is no CPU fallback: importing works anywhere,
 but every call needs the shared library and a B200.
 """
-from .capi import (Context, Map, HppError, lib, lib_path, DEFAULT_PARAMS, VARIANT_RS, VARIANT_DUBINS)  # noqa: F401
+from .capi import (Context, Map, Comm, HppError, lib, lib_path, plan_batch_multi, comm_unique_id, shard_range,  # noqa: F401
+                   DEFAULT_PARAMS, VARIANT_RS, VARIANT_DUBINS)
 
-__all__ = ["Context", "Map", "HppError", "lib", "lib_path", "DEFAULT_PARAMS", "VARIANT_RS", "VARIANT_DUBINS"]
+__all__ = ["Context", "Map", "Comm", "HppError", "lib", "lib_path", "plan_batch_multi", "comm_unique_id", "shard_range",
+           "DEFAULT_PARAMS", "VARIANT_RS", "VARIANT_DUBINS"]

@@ -25,6 +25,11 @@ class QuirkReport(C.Structure):
                 ("h2_bucket_clamp", C.c_int32), ("rounds", C.c_uint32), ("tile_visits", C.c_uint32)]
 
 
+class BandReport(C.Structure):
+    _fields_ = [("rounds", C.c_uint32), ("halo_rows", C.c_uint32), ("gathered_all", C.c_uint32), ("pad_", C.c_uint32),
+                ("halo_bytes_sent", C.c_uint64)]
+
+
 class Node(C.Structure):
     _fields_ = [("x", C.c_double), ("y", C.c_double), ("heading", C.c_double), ("cost", C.c_double),
                 ("steer", C.c_double), ("direction", C.c_int32), ("pad_", C.c_int32)]
@@ -103,6 +108,13 @@ def lib():
             "hpp_test_heap_ops": [vp, vp, vp, sz, vp, vp],
             "hpp_dubins_path": [vp, vp, vp, dbl, dbl, vp, vp, vp, vp, sz],
             "hpp_plan_batch": [vp, C.c_int, vp, vp, sz, vp, vp, sz, C.POINTER(sz)],
+            "hpp_plan_batch_multi": [vp, sz, vp, C.c_int, vp, vp, sz, vp, vp, sz, C.POINTER(sz)],
+            "hpp_comm_unique_id": [vp],
+            "hpp_comm_create": [vp, vp, C.c_int, C.c_int, C.POINTER(vp)],
+            "hpp_plan_batch_sharded": [vp, vp, sz, vp, C.c_int, vp, vp, sz, vp, vp, sz, C.POINTER(sz), C.POINTER(sz),
+                                       C.POINTER(sz)],
+            "hpp_collide_circles_sharded": [vp, vp, vp, sz, vp],
+            "hpp_distance_layer_sharded": [vp, vp, u32, u32, C.c_float, u32, vp, vp, C.POINTER(BandReport)],
         }
         for name, args in sigs.items():
             if hasattr(L, name):
@@ -116,6 +128,12 @@ def lib():
         L.hpp_ctx_launch_count.argtypes = [vp]
         L.hpp_ctx_launch_count.restype = u64
         L.hpp_version.restype = C.c_char_p
+        L.hpp_comm_destroy.argtypes = [vp]
+        L.hpp_comm_destroy.restype = None
+        L.hpp_comm_rank.argtypes = L.hpp_comm_size.argtypes = [vp]
+        L.hpp_comm_rank.restype = L.hpp_comm_size.restype = C.c_int
+        L.hpp_shard_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+        L.hpp_shard_range.restype = None
         L.hpp_num_commands.argtypes = [C.POINTER(Params), C.c_int]
         L.hpp_num_commands.restype = i32
         _lib = L
@@ -387,6 +405,95 @@ class Map:
             self.close()
         except Exception:
             pass
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """128-byte NCCL id made by rank 0; ship it to the other ranks by any means (bench.py: torch.distributed)"""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    st = lib().hpp_comm_unique_id(C.cast(buf, C.c_void_p))
+    if st != 0:
+        raise HppError(f"hpp_comm_unique_id failed with status {st} (is libnccl.so.2 loadable?)")
+    return bytes(buf)
+
+
+def shard_range(n, world, rank):
+    lo, hi = C.c_size_t(0), C.c_size_t(0)
+    lib().hpp_shard_range(n, world, rank, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+class Comm:
+    """hpp_comm: this rank's NCCL communicator inside the C library (one process per GPU)"""
+
+    def __init__(self, ctx, unique_id, rank, world):
+        self.L = lib()
+        self.ctx = ctx
+        self.rank, self.world = rank, world
+        h = C.c_void_p()
+        idb = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        ctx.check(self.L.hpp_comm_create(ctx.h, C.cast(idb, C.c_void_p), rank, world, C.byref(h)))
+        self.h = h
+
+    def plan_batch_sharded(self, maps, map_of_query, variant, starts, goals, traj_cap=1 << 22):
+        """all ranks pass the whole query list; returns (plan headers of ALL queries, this rank's trajectories, (lo, hi))"""
+        starts = np.ascontiguousarray(starts, np.float64).reshape(-1, 3)
+        goals = np.ascontiguousarray(goals, np.float64).reshape(-1, 3)
+        moq = None if map_of_query is None else np.ascontiguousarray(map_of_query, np.uint32).reshape(-1)
+        handles = (C.c_void_p * len(maps))(*[m.h for m in maps])
+        plans = np.zeros(len(starts), PLAN_DTYPE)
+        traj = np.empty((traj_cap, 5))
+        used, lo, hi = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self.ctx.check(self.L.hpp_plan_batch_sharded(self.h, C.cast(handles, C.c_void_p), len(maps),
+                                                     moq.ctypes.data if moq is not None else None, variant,
+                                                     starts.ctypes.data, goals.ctypes.data, len(starts),
+                                                     plans.ctypes.data, traj.ctypes.data, traj_cap, C.byref(used),
+                                                     C.byref(lo), C.byref(hi)))
+        return plans, traj[:used.value], (lo.value, hi.value)
+
+    def collide_circles_sharded(self, m, xyh):
+        xyh = np.ascontiguousarray(xyh, np.float64).reshape(-1, 3)
+        out = np.empty(len(xyh), np.uint8)
+        self.ctx.check(self.L.hpp_collide_circles_sharded(self.h, m.h, xyh.ctypes.data, len(xyh), out.ctypes.data))
+        return out
+
+    def distance_layer_sharded(self, occ_band_dev, W, total_rows, resolution, band_out_dev, full_out_dev=None, halo=0):
+        """occ_band_dev: this rank's rows [lo, hi) of the occupancy (device); band_out_dev: (hi-lo) x W floats (device)"""
+        rep = BandReport()
+        self.ctx.check(self.L.hpp_distance_layer_sharded(self.h, _ptr(occ_band_dev), W, total_rows,
+                                                         C.c_float(float(np.float32(resolution))), halo,
+                                                         _ptr(band_out_dev), _ptr(full_out_dev), C.byref(rep)))
+        return rep
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hpp_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def plan_batch_multi(maps, map_of_query, variant, starts, goals, traj_cap=1 << 22, traj_out=None):
+    """hpp_plan_batch_multi: query q runs on maps[map_of_query[q]] (all maps of one context); one call, no host threads"""
+    starts = np.ascontiguousarray(starts, np.float64).reshape(-1, 3)
+    goals = np.ascontiguousarray(goals, np.float64).reshape(-1, 3)
+    moq = np.ascontiguousarray(map_of_query, np.uint32).reshape(-1)
+    assert len(moq) == len(starts) == len(goals) and len(maps) > 0
+    handles = (C.c_void_p * len(maps))(*[m.h for m in maps])
+    plans = np.zeros(len(starts), PLAN_DTYPE)
+    traj = traj_out if traj_out is not None else np.empty((traj_cap, 5))
+    used = C.c_size_t(0)
+    ctx = maps[0].ctx
+    ctx.check(maps[0].L.hpp_plan_batch_multi(C.cast(handles, C.c_void_p), len(maps), moq.ctypes.data, variant,
+                                             starts.ctypes.data, goals.ctypes.data, len(starts), plans.ctypes.data,
+                                             traj.ctypes.data, len(traj), C.byref(used)))
+    return plans, traj[:used.value]
 
 
 def make_nodes(xyh, cost=0.0, steer=0.0, direction=1):

@@ -6,7 +6,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 ${HPP_NVCC_EXTRA:-}"
-SRCS="map.cu edt.cu inflate.cu collide.cu heuristic.cu $(ls expand.cu shots.cu planner.cu 2>/dev/null || true)"
+SRCS="map.cu edt.cu inflate.cu collide.cu heuristic.cu expand.cu shots.cu planner.cu mgpu.cu"
 mkdir -p build
 pids=()
 for f in $SRCS; do
@@ -18,5 +18,5 @@ for f in $SRCS; do
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 OBJS=$(for f in $SRCS; do echo "build/${f%.cu}.o"; done)
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libhpp_b200.so $OBJS -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libhpp_b200.so $OBJS -lcudart -ldl
 echo "built hybrid_path_planning_b200/libhpp_b200.so"

@@ -129,14 +129,26 @@ __global__ void __launch_bounds__(EDT_ROW_WARPS * 32) edt_row_kernel(const int8_
 }
 
 // pass 2.  64 columns x 128 rows of output per CTA, +-32 rows of halo in shared memory (1.5x read amplification of g).
+// The kernel works on any window of rows of a g buffer: the whole map (hpp_edt_build: flipped grid_map layout out), or
+// one rank's row band inside a band + halo buffer (hpp_edt_band_cols, multi-GPU: plain row-major metres out, and a flag
+// when some distance reaches past the rows the buffer holds, so the caller can widen the halo).
 #define EDT_TX 64
 #define EDT_TY 128
 #define EDT_R 32
+struct edt_band {
+  int y_begin, y_count;   // output rows [y_begin, y_begin + y_count) of the g buffer
+  int more_above;         // map rows exist above row 0 of the buffer (not held by it)
+  int more_below;         // map rows exist below row H-1 of the buffer
+  uint32_t *unresolved;   // set to 1 when a result could be beaten by an obstacle outside the buffer
+};
+
+template <bool BAND>
 __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict__ g, int W, int H, float res_f,
                                                       float *__restrict__ distance,
-                                                      const uint32_t *__restrict__ any_obstacle) {
+                                                      const uint32_t *__restrict__ any_obstacle, edt_band bd) {
   __shared__ __align__(16) uint16_t gs[EDT_TY + 2 * EDT_R][EDT_TX];
-  const int x0 = blockIdx.x * EDT_TX, y0 = blockIdx.y * EDT_TY;
+  const int x0 = blockIdx.x * EDT_TX, y0 = (BAND ? bd.y_begin : 0) + blockIdx.y * EDT_TY;
+  const int y_end = BAND ? bd.y_begin + bd.y_count : H;
   const int tx = threadIdx.x & (EDT_TX - 1), tyb = threadIdx.x / EDT_TX;  // 4 row groups
   const int x = x0 + tx;
   const size_t n = (size_t)W * H;
@@ -159,10 +171,11 @@ __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict
   }
   __syncthreads();
   if (x >= W) return;
-  const bool empty_map = (*any_obstacle == 0u);
+  const bool empty_map = !BAND && (*any_obstacle == 0u);
+  bool open_result = false;
   for (int ry = tyb; ry < EDT_TY; ry += 256 / EDT_TX) {
     const int y = y0 + ry;
-    if (y >= H) break;
+    if (y >= y_end) break;
     const int sr = ry + EDT_R;  // row of (x,y) inside gs
     unsigned own = gs[sr][tx];
     unsigned best = (own == EDT_INF16) ? EDT_INF32 : own * own;
@@ -188,8 +201,18 @@ __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict
     }
     // cv2 returns the constant 65536 for an image without any zero pixel
     float d = (best == EDT_INF32) ? 65536.0f : __fsqrt_rn((float)best);
-    distance[n - 1 - ((size_t)y * W + x)] = __fmul_rn(d, res_f);
+    if (BAND) {
+      // the nearest obstacle outside the buffer is at least `lim` rows away: the result stands iff best <= lim^2
+      unsigned long long lim = ~0ull;
+      if (bd.more_above) lim = (unsigned long long)(y + 1);
+      if (bd.more_below) lim = min(lim, (unsigned long long)(H - y));
+      if (lim != ~0ull && (best == EDT_INF32 || (unsigned long long)best > lim * lim)) open_result = true;
+      distance[(size_t)(y - bd.y_begin) * W + x] = __fmul_rn(d, res_f);
+    } else {
+      distance[n - 1 - ((size_t)y * W + x)] = __fmul_rn(d, res_f);
+    }
   }
+  if (BAND && open_result) *bd.unresolved = 1u;
 }
 
 static const pred_lut *edt_lut_dev(hpp_ctx *c) { return (const pred_lut *)(c->d_flags + 32); }
@@ -224,7 +247,38 @@ hpp_status hpp_edt_build(hpp_map *m) {
   hpp_status s = hpp_row_dist_launch(c, m->d_occ, W, H, edt_lut_dev(c), m->d_g, m->d_obstacle, c->d_flags + 40);
   if (s != HPP_OK) return s;
   dim3 grid(hpp_div_up(W, EDT_TX), hpp_div_up(H, EDT_TY));
-  edt_col_kernel<<<grid, 256, 0, c->stream>>>(m->d_g, W, H, m->g.res_f, m->d_distance, c->d_flags + 40);
+  edt_band none;
+  memset(&none, 0, sizeof none);
+  edt_col_kernel<false><<<grid, 256, 0, c->stream>>>(m->d_g, W, H, m->g.res_f, m->d_distance, c->d_flags + 40, none);
+  HPP_LAUNCHED(c);
+  return HPP_OK;
+}
+
+// ---- row bands (multi-GPU, mgpu.cu): pass 1 of a band of rows, pass 2 of a band inside a band + halo buffer
+hpp_status hpp_edt_band_rows(hpp_ctx *c, const int8_t *occ_band_dev, int W, int rows, uint16_t *g_band) {
+  pred_lut lut;
+  memset(&lut, 0, sizeof lut);
+  for (int v = -128; v < 128; v++)
+    if (v > 20 || v < 0) lut.w[((uint8_t)v) >> 5] |= 1u << (((uint8_t)v) & 31);
+  uint32_t *h = c->h_flags + 32;
+  HPP_CUDA(c, cudaStreamSynchronize(c->stream));  // the pinned staging words may still be in flight
+  memcpy(h, &lut, sizeof lut);
+  HPP_CUDA(c, cudaMemcpyAsync(c->d_flags + 32, h, sizeof lut, cudaMemcpyHostToDevice, c->stream));
+  HPP_CUDA(c, cudaMemsetAsync(c->d_flags + 40, 0, sizeof(uint32_t), c->stream));
+  return hpp_row_dist_launch(c, occ_band_dev, W, rows, edt_lut_dev(c), g_band, nullptr, c->d_flags + 40);
+}
+
+hpp_status hpp_edt_band_cols(hpp_ctx *c, const uint16_t *g_ext, int W, int rows_ext, int y_begin, int y_count,
+                             int more_above, int more_below, float res_f, float *distance_band, uint32_t *unresolved) {
+  if (y_count <= 0) return HPP_OK;
+  edt_band bd;
+  bd.y_begin = y_begin;
+  bd.y_count = y_count;
+  bd.more_above = more_above;
+  bd.more_below = more_below;
+  bd.unresolved = unresolved;
+  dim3 grid(hpp_div_up(W, EDT_TX), hpp_div_up(y_count, EDT_TY));
+  edt_col_kernel<true><<<grid, 256, 0, c->stream>>>(g_ext, W, rows_ext, res_f, distance_band, c->d_flags + 40, bd);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }

@@ -107,6 +107,9 @@ hpp_status hpp_pinned(hpp_ctx *ctx, int slot, size_t bytes, void **out);
 
 // internal launchers (device pointers, enqueue only)
 hpp_status hpp_edt_build(hpp_map *m);                                   // edt.cu
+hpp_status hpp_edt_band_rows(hpp_ctx *c, const int8_t *occ_band_dev, int W, int rows, uint16_t *g_band);
+hpp_status hpp_edt_band_cols(hpp_ctx *c, const uint16_t *g_ext, int W, int rows_ext, int y_begin, int y_count,
+                             int more_above, int more_below, float res_f, float *distance_band, uint32_t *unresolved);
 hpp_status hpp_build_cls(hpp_map *m);                                   // map.cu
 hpp_status hpp_inflate_launch(hpp_ctx *ctx, const int8_t *occ_dev, uint32_t W, uint32_t H, double resolution,
                               double inflation_radius, int8_t *out_dev); // inflate.cu

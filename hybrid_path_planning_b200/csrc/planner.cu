@@ -40,6 +40,13 @@ struct pnode {
   short pad;
 };
 
+// per-map device pointers of a launch (all maps of one launch have the same geometry and vehicle)
+struct plan_map_desc {
+  const float *dist;      // grid_map "distance" layer
+  const uint32_t *bits;   // bit-packed occupancy rows
+  int pitch, pad_;
+};
+
 struct plan_consts {
   hpp_geom g;
   expand_consts ec;
@@ -286,8 +293,8 @@ __device__ __forceinline__ int plan_formula_of(int wid, int lane) {
 }
 
 template <int VARIANT, int PLAN_WARPS>
-__global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, const float *__restrict__ dist,
-                                                            const uint32_t *__restrict__ bits, int pitch,
+__global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, const plan_map_desc *__restrict__ descs,
+                                                            const int *__restrict__ map_of_query,
                                                             const double *__restrict__ starts,
                                                             const double *__restrict__ goals,
                                                             const int *__restrict__ query_ids, int n_queries,
@@ -331,6 +338,11 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
     if (qi >= n_queries) break;
     const int q = query_ids[qi];
     const double *hmap = fields + (size_t)field_of_query[qi] * map_size;
+    // the query's map (maps of one launch share their geometry and vehicle, hpp_plan_batch_multi)
+    const plan_map_desc md = descs[map_of_query ? map_of_query[q] : 0];
+    const float *__restrict__ dist = md.dist;
+    const uint32_t *__restrict__ bits = md.bits;
+    const int pitch = md.pitch;
     const double sx = starts[3 * q], sy = starts[3 * q + 1], sh = starts[3 * q + 2];
     const double gx = goals[3 * q], gy = goals[3 * q + 1], gh = goals[3 * q + 2];
     const int s_cx = (int)(hpp_div_res(g, sx - g.ox)), s_cy = (int)(hpp_div_res(g, sy - g.oy));
@@ -720,13 +732,21 @@ extern "C" hpp_status hpp_test_heap_ops(hpp_ctx *c, const double *keys, const in
   return HPP_OK;
 }
 
-extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *starts, const double *goals, size_t n,
-                                     hpp_plan *plans, double *traj, size_t traj_cap, size_t *traj_used) {
-  if (!m || variant < 0 || variant > 1 || (n && (!starts || !goals || !plans)) || (traj_cap && !traj)) return HPP_ERR_ARG;
+// Whole queries on one or several maps of one context.  Queries are grouped by (map, goal cell): one heuristic field
+// per distinct pair; maps that share geometry and vehicle parameters are planned by ONE plan_kernel launch (the kernel
+// takes the per-map layer pointers from a descriptor table), maps that differ are planned group after group.
+static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uint32_t *map_of_query, int variant,
+                                  const double *starts, const double *goals, size_t n, hpp_plan *plans, double *traj,
+                                  size_t traj_cap, size_t *traj_used) {
+  if (!maps || n_maps == 0 || variant < 0 || variant > 1 || (n && (!starts || !goals || !plans)) || (traj_cap && !traj))
+    return HPP_ERR_ARG;
+  for (size_t k = 0; k < n_maps; k++)
+    if (!maps[k] || maps[k]->ctx != maps[0]->ctx) return HPP_ERR_ARG;
+  if (n_maps > 1 && !map_of_query) return HPP_ERR_ARG;
   if (traj_used) *traj_used = 0;
   if (n == 0) return HPP_OK;
-  if (n > 0x7fffffff) return HPP_ERR_ARG;
-  hpp_ctx *c = m->ctx;
+  if (n > 0x7fffffff || n_maps > 0x7fffffff) return HPP_ERR_ARG;
+  hpp_ctx *c = maps[0]->ctx;
   const bool timing = getenv("HPP_PLAN_TIMING") != nullptr;
   auto t_now = [] { return std::chrono::steady_clock::now(); };
   auto t_us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -734,130 +754,174 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   };
   const auto t0 = t_now();
   HPP_CUDA(c, cudaSetDevice(c->device));
-  const int W = m->g.W, H = m->g.H;
 
-  // group the queries by goal cell: one heuristic field per distinct cell
+  // maps with the same geometry and vehicle form a group (one launch per group)
+  std::vector<int> grp_of_map(n_maps, -1), grp_first;
+  for (size_t k = 0; k < n_maps; k++) {
+    for (size_t gi = 0; gi < grp_first.size() && grp_of_map[k] < 0; gi++) {
+      const hpp_map *a = maps[grp_first[gi]], *b = maps[k];
+      if (a->g.W == b->g.W && a->g.H == b->g.H && a->g.res_f == b->g.res_f && a->g.ox == b->g.ox && a->g.oy == b->g.oy &&
+          memcmp(&a->car.p, &b->car.p, sizeof a->car.p) == 0)
+        grp_of_map[k] = (int)gi;
+    }
+    if (grp_of_map[k] < 0) {
+      grp_of_map[k] = (int)grp_first.size();
+      grp_first.push_back((int)k);
+    }
+  }
+
+  // one heuristic field per distinct (map, goal cell): sort the queries by (group, map, cell)
   std::vector<long> cell(n);
+  std::vector<int> mq(n);
   for (size_t q = 0; q < n; q++) {
+    const uint32_t k = map_of_query ? map_of_query[q] : 0u;
+    if (k >= n_maps) HPP_FAIL(c, HPP_ERR_ARG, "query %zu names map %u of %zu", q, k, n_maps);
+    const hpp_map *m = maps[k];
     const int gx = (int)((goals[3 * q] - m->g.ox) / m->g.res), gy = (int)((goals[3 * q + 1] - m->g.oy) / m->g.res);
-    if (gx < 0 || gx >= W || gy < 0 || gy >= H)
+    if (gx < 0 || gx >= m->g.W || gy < 0 || gy >= m->g.H)
       HPP_FAIL(c, HPP_ERR_ARG, "goal of query %zu lies outside the map (cell %d,%d)", q, gx, gy);
-    cell[q] = (long)gy * W + gx;
+    cell[q] = (long)gy * m->g.W + gx;
+    mq[q] = (int)k;
   }
   std::vector<int> order(n);
   for (size_t q = 0; q < n; q++) order[q] = (int)q;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cell[a] < cell[b]; });
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (grp_of_map[mq[a]] != grp_of_map[mq[b]]) return grp_of_map[mq[a]] < grp_of_map[mq[b]];
+    if (mq[a] != mq[b]) return mq[a] < mq[b];
+    return cell[a] < cell[b];
+  });
 
-  plan_consts pc;
-  memset(&pc, 0, sizeof pc);
-  pc.g = m->g;
-  hpp_make_expand_consts(m, variant, &pc.ec);
-  for (int k = 0; k < 4; k++) {
-    pc.cc.cx[k] = m->car.cx[k];
-    pc.cc.cy[k] = m->car.cy[k];
-  }
-  pc.cc.cr = m->car.cr;
-  for (int k = 0; k < 5; k++) {
-    pc.rx[k] = m->car.rx[k];
-    pc.ry[k] = m->car.ry[k];
-  }
-  pc.maxc = m->car.maxc;
-  pc.max_steer = m->car.p.max_steer;
-  pc.max_nodes = PLAN_ITER_CAP * pc.ec.n_cmd + 2;
-  int slots = 1;
-  while (slots < 2 * pc.max_nodes) slots <<= 1;
-  pc.table_mask = slots - 1;
-
-  // device buffers: inputs, per-warp pools, outputs, heuristic fields for a chunk of goal cells
-  // free device memory bounds the pools and the field chunk; small batches reuse the answer of the last large one
+  // device buffers shared by all groups: inputs, outputs, map descriptors
   size_t free_b = c->plan_free_bytes, total_b = 0;
   if (free_b == 0 || n > 64) {
     HPP_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
     c->plan_free_bytes = free_b;
   }
-  const size_t per_warp = (size_t)pc.max_nodes * (sizeof(pnode) + 12) + (size_t)slots * 4;
-  // kernel shape: eight warps per query while the batch leaves SMs free anyway, four otherwise (HPP_PLAN_WARPS forces one)
-  int plan_warps = n <= (size_t)c->sm_count ? PLAN_WARPS_LONE : PLAN_WARPS_BATCH;
-  if (const char *e = getenv("HPP_PLAN_WARPS")) {
-    const int v = atoi(e);
-    if (v == PLAN_WARPS_LONE || v == PLAN_WARPS_BATCH) plan_warps = v;
-  }
-  const void *kern = variant == HPP_VARIANT_RS
-                         ? (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_LONE>
-                                                          : (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_BATCH>)
-                         : (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_LONE>
-                                                          : (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_BATCH>);
-  const int occ_slot = variant * 2 + (plan_warps == PLAN_WARPS_LONE ? 1 : 0);
-  int occ_blocks = c->plan_occ_blocks[occ_slot];
-  if (occ_blocks == 0) {
-    HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, kern, plan_warps * 32, 0));
-    c->plan_occ_blocks[occ_slot] = occ_blocks;
-  }
-  if (occ_blocks < 1) occ_blocks = 1;
-  size_t max_warps = (size_t)c->sm_count * occ_blocks;  // CTAs (= queries in flight): one resident wave, persistent
-  if (max_warps > n) max_warps = n;
-  const size_t field_bytes = m->n * sizeof(double);
-  const size_t budget = free_b > ((size_t)2 << 30) ? free_b - ((size_t)1 << 30) : free_b / 2;
-  while (max_warps > 1 && max_warps * per_warp > budget / 2) max_warps /= 2;
-  size_t fields_cap = (budget - max_warps * per_warp - n * 64 - traj_cap * 40) / field_bytes;
-  if (fields_cap < 1) HPP_FAIL(c, HPP_ERR_NOMEM, "not enough device memory for one heuristic field");
-  if (fields_cap > 4096) fields_cap = 4096;
-  const int grid = (int)max_warps;
-  const size_t n_warps = (size_t)grid;  // one node pool / heap / table per CTA
-
   const auto t1 = t_now();
-  char *d_pool = nullptr, *d_io = nullptr;
-  double *d_fields = nullptr;
-  const size_t io_bytes = n * 48 + n * 8 + n * sizeof(hpp_plan) + traj_cap * 40 + 64;
-  // buffers come from the context's grow-only scratch: a per-call cudaMalloc/cudaFree would synchronise the whole
-  // device and serialise plan_batch calls that other contexts (threads) run concurrently on the same GPU
-  cudaError_t e = cudaSuccess;
-  hpp_status st = hpp_scratch(c, 1, n_warps * per_warp + 256, (void **)&d_pool);
-  if (st == HPP_OK) st = hpp_scratch(c, 0, io_bytes, (void **)&d_io);
+  char *d_io = nullptr;
+  const size_t io_bytes = n * 48 + n * 12 + n * sizeof(hpp_plan) + n_maps * sizeof(plan_map_desc) + traj_cap * 40 + 64;
+  hpp_status st = hpp_scratch(c, 0, io_bytes, (void **)&d_io);
   if (st != HPP_OK) {
-    st = HPP_ERR_NOMEM;
     c->plan_free_bytes = 0;  // the cached figure was stale: ask again next time
+    return HPP_ERR_NOMEM;
   }
-  double *d_starts = nullptr, *d_goals = nullptr, *d_traj = nullptr;
-  int *d_qids = nullptr, *d_fq = nullptr;
-  hpp_plan *d_plans = nullptr;
-  unsigned long long *d_cursor = nullptr;
+  double *d_starts = (double *)d_io, *d_goals = d_starts + 3 * n;
+  int *d_qids = (int *)(d_goals + 3 * n), *d_fq = d_qids + n, *d_mq = d_fq + n;
+  hpp_plan *d_plans = (hpp_plan *)(d_mq + n + (n & 1));
+  unsigned long long *d_cursor = (unsigned long long *)(d_plans + n);
+  plan_map_desc *d_descs = (plan_map_desc *)(d_cursor + 2);
+  double *d_traj = (double *)(d_descs + n_maps);
+  std::vector<plan_map_desc> descs(n_maps);
+  for (size_t k = 0; k < n_maps; k++) {
+    descs[k].dist = maps[k]->d_distance;
+    descs[k].bits = maps[k]->d_occ_bits;
+    descs[k].pitch = maps[k]->bits_pitch;
+    descs[k].pad_ = 0;
+  }
+  cudaMemcpyAsync(d_starts, starts, n * 24, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(d_goals, goals, n * 24, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(d_qids, order.data(), n * 4, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(d_mq, mq.data(), n * 4, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(d_descs, descs.data(), n_maps * sizeof(plan_map_desc), cudaMemcpyHostToDevice, c->stream);
+  cudaMemsetAsync(d_cursor, 0, 16, c->stream);
+  unsigned long long *d_prof = nullptr;
+#ifdef HPP_PLAN_PROF
+  if (hpp_scratch(c, 5, 64, (void **)&d_prof) == HPP_OK) cudaMemsetAsync(d_prof, 0, 64, c->stream);
+#endif
   std::vector<int> fq(n);
   std::vector<int32_t> chunk_goals;
-  size_t fields_alloc = 0;
-  if (st == HPP_OK) {
-    d_starts = (double *)d_io;
-    d_goals = d_starts + 3 * n;
-    d_qids = (int *)(d_goals + 3 * n);
-    d_fq = d_qids + n;
-    d_plans = (hpp_plan *)(d_fq + n);
-    d_cursor = (unsigned long long *)(d_plans + n);
-    d_traj = (double *)(d_cursor + 2);
+  cudaError_t e = cudaSuccess;
+
+  size_t q0 = 0;
+  while (q0 < n && st == HPP_OK) {
+    // ---- one group of maps: queries [q0, g1) of the sorted order
+    const int grp = grp_of_map[mq[order[q0]]];
+    size_t g1 = q0;
+    while (g1 < n && grp_of_map[mq[order[g1]]] == grp) g1++;
+    hpp_map *m0 = maps[grp_first[grp]];
+    const int W = m0->g.W;
+    const size_t ng = g1 - q0;
+    plan_consts pc;
+    memset(&pc, 0, sizeof pc);
+    pc.g = m0->g;
+    hpp_make_expand_consts(m0, variant, &pc.ec);
+    for (int k = 0; k < 4; k++) {
+      pc.cc.cx[k] = m0->car.cx[k];
+      pc.cc.cy[k] = m0->car.cy[k];
+    }
+    pc.cc.cr = m0->car.cr;
+    for (int k = 0; k < 5; k++) {
+      pc.rx[k] = m0->car.rx[k];
+      pc.ry[k] = m0->car.ry[k];
+    }
+    pc.maxc = m0->car.maxc;
+    pc.max_steer = m0->car.p.max_steer;
+    pc.max_nodes = PLAN_ITER_CAP * pc.ec.n_cmd + 2;
+    int slots = 1;
+    while (slots < 2 * pc.max_nodes) slots <<= 1;
+    pc.table_mask = slots - 1;
+    const size_t per_warp = (size_t)pc.max_nodes * (sizeof(pnode) + 12) + (size_t)slots * 4;
+    // kernel shape: eight warps per query while the batch leaves SMs free anyway, four otherwise (HPP_PLAN_WARPS forces one)
+    int plan_warps = ng <= (size_t)c->sm_count ? PLAN_WARPS_LONE : PLAN_WARPS_BATCH;
+    if (const char *ev = getenv("HPP_PLAN_WARPS")) {
+      const int v = atoi(ev);
+      if (v == PLAN_WARPS_LONE || v == PLAN_WARPS_BATCH) plan_warps = v;
+    }
+    const void *kern = variant == HPP_VARIANT_RS
+                           ? (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_LONE>
+                                                            : (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_BATCH>)
+                           : (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_LONE>
+                                                            : (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_BATCH>);
+    const int occ_slot = variant * 2 + (plan_warps == PLAN_WARPS_LONE ? 1 : 0);
+    int occ_blocks = c->plan_occ_blocks[occ_slot];
+    if (occ_blocks == 0) {
+      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, kern, plan_warps * 32, 0));
+      c->plan_occ_blocks[occ_slot] = occ_blocks;
+    }
+    if (occ_blocks < 1) occ_blocks = 1;
+    size_t max_warps = (size_t)c->sm_count * occ_blocks;  // CTAs (= queries in flight): one resident wave, persistent
+    if (max_warps > ng) max_warps = ng;
+    const size_t field_bytes = m0->n * sizeof(double);
+    const size_t budget = free_b > ((size_t)2 << 30) ? free_b - ((size_t)1 << 30) : free_b / 2;
+    while (max_warps > 1 && max_warps * per_warp > budget / 2) max_warps /= 2;
+    const size_t fixed_bytes = max_warps * per_warp + io_bytes;
+    if (fixed_bytes + field_bytes > budget)
+      HPP_FAIL(c, HPP_ERR_NOMEM, "plan_batch: pools (%zu B) + query/trajectory buffers (%zu B) + one heuristic field (%zu B) "
+               "exceed the device memory budget (%zu B): lower traj_cap or the batch size", max_warps * per_warp, io_bytes,
+               field_bytes, budget);
+    size_t fields_cap = (budget - fixed_bytes) / field_bytes;
+    if (fields_cap > 4096) fields_cap = 4096;
+    const int grid = (int)max_warps;
+    const size_t n_warps = (size_t)grid;  // one node pool / heap / table per CTA
+    char *d_pool = nullptr;
+    if (hpp_scratch(c, 1, n_warps * per_warp + 256, (void **)&d_pool) != HPP_OK) {
+      c->plan_free_bytes = 0;
+      return HPP_ERR_NOMEM;
+    }
     pnode *d_nodes = (pnode *)d_pool;
     double *d_keys = (double *)(d_nodes + n_warps * pc.max_nodes);
     int *d_idx = (int *)(d_keys + n_warps * pc.max_nodes);
     int *d_table = d_idx + n_warps * pc.max_nodes;
-    cudaMemcpyAsync(d_starts, starts, n * 24, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(d_goals, goals, n * 24, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(d_qids, order.data(), n * 4, cudaMemcpyHostToDevice, c->stream);
-    cudaMemsetAsync(d_cursor, 0, 16, c->stream);
-    unsigned long long *d_prof = nullptr;
-#ifdef HPP_PLAN_PROF
-    if (hpp_scratch(c, 5, 64, (void **)&d_prof) == HPP_OK) cudaMemsetAsync(d_prof, 0, 64, c->stream);
-#endif
-    // chunks of distinct goal cells
-    size_t q0 = 0;
-    while (q0 < n && st == HPP_OK) {
+    double *d_fields = nullptr;
+    size_t fields_alloc = 0;
+
+    // ---- chunks of distinct (map, goal cell) pairs of this group
+    while (q0 < g1 && st == HPP_OK) {
       chunk_goals.clear();
+      std::vector<std::pair<int, size_t>> runs;  // (map, first field of the map's run) inside the chunk
       size_t q1 = q0;
-      long last = -1;
-      while (q1 < n) {
+      long last_cell = -1;
+      int last_map = -1;
+      while (q1 < g1) {
         const long cl = cell[order[q1]];
-        if (cl != last) {
+        const int mk = mq[order[q1]];
+        if (cl != last_cell || mk != last_map) {
           if (chunk_goals.size() / 2 >= fields_cap) break;
+          if (mk != last_map) runs.push_back({mk, chunk_goals.size() / 2});
           chunk_goals.push_back((int32_t)(cl % W));
           chunk_goals.push_back((int32_t)(cl / W));
-          last = cl;
+          last_cell = cl;
+          last_map = mk;
         }
         fq[q1] = (int)(chunk_goals.size() / 2 - 1);
         q1++;
@@ -867,13 +931,16 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
         if (hpp_scratch(c, 3, nf * field_bytes, (void **)&d_fields) != HPP_OK) {
           st = HPP_ERR_NOMEM;
           c->plan_free_bytes = 0;
-          d_fields = nullptr;
           break;
         }
         fields_alloc = nf;
       }
       const auto t2 = t_now();
-      st = hpp_heuristic_batch_dev(m, variant, chunk_goals.data(), nf, d_fields, nullptr);
+      for (size_t r = 0; r < runs.size() && st == HPP_OK; r++) {
+        const size_t f0 = runs[r].second, f1 = r + 1 < runs.size() ? runs[r + 1].second : nf;
+        st = hpp_heuristic_batch_dev(maps[runs[r].first], variant, chunk_goals.data() + 2 * f0, f1 - f0,
+                                     d_fields + f0 * m0->n, nullptr);
+      }
       if (st != HPP_OK) break;
       const auto t3 = t_now();
       if (timing) fprintf(stderr, "[plan timing] setup %.0f us, alloc+h2d %.0f us, heuristic (returns after the kernel) %.0f us\n",
@@ -881,16 +948,15 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
       cudaMemcpyAsync(d_fq + q0, fq.data() + q0, (q1 - q0) * 4, cudaMemcpyHostToDevice, c->stream);
       cudaMemsetAsync(d_cursor + 1, 0, 8, c->stream);  // the kernel's query counter
       {
-        const float *a_dist = m->d_distance;
-        const uint32_t *a_bits = m->d_occ_bits;
-        int a_pitch = m->bits_pitch;
+        const plan_map_desc *a_descs = d_descs;
+        const int *a_mq = n_maps > 1 ? d_mq : nullptr;
         const double *a_starts = d_starts, *a_goals = d_goals, *a_fields = d_fields;
         const int *a_qids = d_qids + q0, *a_fq = d_fq + q0;
         int a_nq = (int)(q1 - q0);
         unsigned long long a_cap = traj_cap;
-        void *params[] = {&pc,      &a_dist, &a_bits,  &a_pitch, &a_starts, &a_goals,  &a_qids, &a_nq,     &a_fq,
-                          &a_fields, &d_nodes, &d_keys, &d_idx,   &d_table,  &d_plans, &d_traj, &a_cap,    &d_cursor,
-                          &d_prof};
+        void *params[] = {&pc,       &a_descs, &a_mq,   &a_starts, &a_goals, &a_qids,  &a_nq,   &a_fq,
+                          &a_fields, &d_nodes, &d_keys, &d_idx,    &d_table, &d_plans, &d_traj, &a_cap,
+                          &d_cursor, &d_prof};
         cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, 0, c->stream);
       }
       c->launches++;
@@ -941,4 +1007,17 @@ extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *star
   cudaStreamSynchronize(c->stream);
   if (timing) fprintf(stderr, "[plan timing] total %.0f us\n", t_us(t0, t_now()));
   return st;
+}
+
+extern "C" hpp_status hpp_plan_batch(hpp_map *m, int variant, const double *starts, const double *goals, size_t n,
+                                     hpp_plan *plans, double *traj, size_t traj_cap, size_t *traj_used) {
+  if (!m) return HPP_ERR_ARG;
+  hpp_map *one[1] = {m};
+  return plan_batch_impl(one, 1, nullptr, variant, starts, goals, n, plans, traj, traj_cap, traj_used);
+}
+
+extern "C" hpp_status hpp_plan_batch_multi(hpp_map *const *maps, size_t n_maps, const uint32_t *map_of_query, int variant,
+                                           const double *starts, const double *goals, size_t n, hpp_plan *plans,
+                                           double *traj, size_t traj_cap, size_t *traj_used) {
+  return plan_batch_impl(maps, n_maps, map_of_query, variant, starts, goals, n, plans, traj, traj_cap, traj_used);
 }

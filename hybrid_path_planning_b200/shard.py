@@ -57,6 +57,8 @@ def sharded_map(units: np.ndarray, compute, device="cpu", group=None) -> np.ndar
     world, rank = _world(group)
     lo, hi = shard_range(len(units), world, rank)
     out = np.asarray(compute(units[lo:hi]))
+    if out.shape[0] != hi - lo:
+        raise ValueError(f"compute returned {out.shape[0]} rows for {hi - lo} units")
     t = torch.from_numpy(np.ascontiguousarray(out)).to(device)
     return gather_slices(t, len(units), group).cpu().numpy()
 
@@ -67,19 +69,23 @@ def sharded_queries(starts: np.ndarray, goals: np.ndarray, plan, device="cpu", g
     world, rank = _world(group)
     lo, hi = shard_range(len(starts), world, rank)
     plans, traj = plan(starts[lo:hi], goals[lo:hi])
-    raw = torch.from_numpy(np.ascontiguousarray(plans).view(np.uint8).reshape(len(plans), -1).copy()).to(device)
+    # explicit item size: a rank whose slice is empty (fewer queries than ranks) still takes part in the gather
+    raw = torch.from_numpy(np.ascontiguousarray(plans).view(np.uint8).reshape(len(plans), plans.dtype.itemsize).copy()).to(device)
     allp = gather_slices(raw, len(starts), group).cpu().numpy()
     return allp.reshape(-1).view(plans.dtype), (lo, hi, traj)
 
 
 # ------------------------------------------------------------------------------------------- distance-layer row bands
-def band_with_halo(occ_band: torch.Tensor, halo: int, group=None) -> tuple[torch.Tensor, int, int]:
+def band_with_halo(occ_band: torch.Tensor, halo: int, group=None, min_rows: int | None = None) -> tuple[torch.Tensor, int, int]:
     """occ_band: this rank's rows [rows, W] int8 (device tensor for NCCL, CPU tensor for gloo).  Exchanges `halo` rows
     with the ranks above and below and returns (band + halo rows, rows received from below-index neighbour, rows
-    received from above-index neighbour).  Rank r holds rows after rank r-1 (y grows with the rank)."""
+    received from above-index neighbour).  Rank r holds rows after rank r-1 (y grows with the rank).
+    The halo is clamped with min_rows = total_rows // world, the SAME number on every rank (bands of a shard_range
+    split differ by one row when total_rows % world != 0: a clamp with the local height would make neighbours post
+    sends and receives of different sizes)."""
     world, rank = _world(group)
     rows = occ_band.shape[0]
-    h = min(halo, rows)
+    h = min(halo, rows if min_rows is None else min_rows)
     if world == 1:
         return occ_band, 0, 0
     ops, lo_buf, hi_buf = [], None, None
@@ -110,7 +116,7 @@ def sharded_distance_band(occ_band: torch.Tensor, total_rows: int, resolution: f
     res = float(np.float32(resolution))
     min_rows = total_rows // max(world, 1)
     while True:
-        ext, below, above = band_with_halo(occ_band, halo, group)
+        ext, below, above = band_with_halo(occ_band, halo, group, min_rows)
         band = edt_cells(ext)[below:below + rows]
         idx = torch.arange(rows, device=band.device, dtype=torch.float32)
         limit = torch.full((rows,), float("inf"), device=band.device)

@@ -242,7 +242,9 @@ typedef struct {
   int32_t n_states;      /* trajectory length; 1 = failure */
   int32_t iterations;
   int32_t via_shot;      /* ended by an analytic shot */
-  int32_t status;        /* 0 ok, 1 = node pool exhausted (query aborted as failure) */
+  int32_t status;        /* 0 ok, 1 = node pool exhausted (query aborted as failure), 2 = the start pose's cell index
+                          * lies outside [0, W*H): the reference indexes its heuristic vector out of range there
+                          * (RS/src/HybridAstar.cpp:597, undefined behaviour); reported as a failure (1-state trajectory) */
   double cost;           /* Cost_path of the terminating node (0 on failure) */
   uint64_t traj_offset;  /* first state in traj[] (states of 5 doubles: x,y,heading,gridx,gridy) */
 } hpp_plan;
@@ -250,6 +252,62 @@ typedef struct {
 hpp_status hpp_plan_batch(hpp_map *map, int variant, const double *starts_xyh, const double *goals_xyh,
                           size_t n, hpp_plan *plans, double *traj /* cap x 5 */, size_t traj_cap,
                           size_t *traj_used);
+
+/* The same for queries on SEVERAL maps of one context (a fleet planning on different lots, cfg5): query q runs on
+ * maps[map_of_query[q]].  One heuristic field per distinct (map, goal cell); maps that share geometry (W, H,
+ * resolution, origin) and vehicle parameters are planned by ONE kernel launch with no host threads, maps that differ
+ * are planned group after group.  Results are identical to one hpp_plan_batch call per map. */
+hpp_status hpp_plan_batch_multi(hpp_map *const *maps, size_t n_maps, const uint32_t *map_of_query /* n */, int variant,
+                                const double *starts_xyh, const double *goals_xyh, size_t n, hpp_plan *plans,
+                                double *traj /* cap x 5 */, size_t traj_cap, size_t *traj_used);
+
+/* ---------------------------------------------------------------- multi-GPU (one process per GPU, NCCL over NVLink)
+ * only independent units are partitioned -- batches of queries, pose batches, and row bands of a large
+ * map for the distance layer; a single heuristic field does not shard (replicas only).  NCCL is loaded at run time
+ * (dlopen of libnccl.so.2; HPP_ERR_UNSUPPORTED when it is absent) and used only for the halo exchange of the row-band
+ * distance transform and for the result gathers.  The reference has no multi-process path: these entry points are what
+ * a multi-GPU deployment of HybridAstar::run (RS/src/HybridAstar.cpp:553-729), Grid_map::isSingleStateCollisionFree
+ * (RS/src/Grid_map.cpp:222-284) and the Grid_map constructor's layers (RS/src/Grid_map.cpp:22-74) calls instead of
+ * the single-GPU ones; every rank makes the same call with the same arguments. */
+typedef struct hpp_comm hpp_comm;
+#define HPP_COMM_ID_BYTES 128
+/* rank 0 makes the id; the caller ships the bytes to the other ranks (MPI, a file, torch.distributed ...) */
+hpp_status hpp_comm_unique_id(uint8_t id[HPP_COMM_ID_BYTES]);
+hpp_status hpp_comm_create(hpp_ctx *ctx, const uint8_t id[HPP_COMM_ID_BYTES], int rank, int world, hpp_comm **out);
+void hpp_comm_destroy(hpp_comm *comm);
+int hpp_comm_rank(const hpp_comm *comm);
+int hpp_comm_size(const hpp_comm *comm);
+/* contiguous split of n units: rank r owns [lo, hi); sizes differ by at most one (the first n % world are larger) */
+void hpp_shard_range(size_t n, int world, int rank, size_t *lo, size_t *hi);
+
+/* cfg5: queries [lo, hi) of the list are planned on this rank (maps replicated: every rank holds all maps); the plan
+ * headers of ALL n_total queries are returned to every rank by one ncclAllGather; trajectories stay on the rank that
+ * produced them (traj_local; hpp_plan.traj_offset of a foreign query refers to its own rank's buffer).  Arguments as
+ * hpp_plan_batch_multi, all arrays of n_total entries. */
+hpp_status hpp_plan_batch_sharded(hpp_comm *comm, hpp_map *const *maps, size_t n_maps, const uint32_t *map_of_query,
+                                  int variant, const double *starts_xyh, const double *goals_xyh, size_t n_total,
+                                  hpp_plan *plans_all, double *traj_local, size_t traj_cap, size_t *traj_used,
+                                  size_t *lo, size_t *hi);
+/* cfg4: poses [lo, hi) checked on this rank (distance layer replicated), all n_total verdicts gathered to every rank */
+hpp_status hpp_collide_circles_sharded(hpp_comm *comm, hpp_map *map, const double *xyh, size_t n_total,
+                                       uint8_t *verdict_all);
+
+/* large-map distance layer in row bands: this rank holds rows [lo, hi) (hpp_shard_range of total_rows) of the
+ * occupancy in device memory.  Pass 1 (row distances) is local; the bands then exchange halo_rows rows (0 = 64) of
+ * the pass-1 result with their neighbours (ncclSend/ncclRecv) and run pass 2; when a distance reaches past the halo
+ * the ranks agree to double it, and finally to gather all rows.  distance_band_dev: (hi-lo) x W floats, metres,
+ * row-major in MAP orientation (not flipped).  distance_full_dev (may be NULL): the whole layer W*total_rows in the
+ * reference's grid_map layout (distance[k] = edt[n-1-k]*res, RS/src/Grid_map.cpp:67-74), gathered to every rank. */
+typedef struct {
+  uint32_t rounds;          /* pass-2 rounds (1 = the first halo was enough) */
+  uint32_t halo_rows;       /* halo of the last round */
+  uint32_t gathered_all;    /* 1 = fell back to gathering all rows */
+  uint32_t pad_;
+  uint64_t halo_bytes_sent; /* bytes this rank sent in halo exchanges (and the fall-back gather) */
+} hpp_band_report;
+hpp_status hpp_distance_layer_sharded(hpp_comm *comm, const int8_t *occ_band_dev, uint32_t W, uint32_t total_rows,
+                                      float resolution, uint32_t halo_rows, float *distance_band_dev,
+                                      float *distance_full_dev, hpp_band_report *report /* may be NULL */);
 
 #ifdef __cplusplus
 }

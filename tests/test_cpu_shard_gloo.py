@@ -71,6 +71,16 @@ def _worker(rank, world, port, q):
         band = torch.from_numpy(big[lo:hi].copy())
         out["band"] = shard.sharded_distance_band(band, big.shape[0], 0.2, _edt_cells_oracle, halo=4).numpy()
         out["band_span"] = (lo, hi)
+        # uneven split (201 rows over 2 ranks: bands of 101 and 100 rows) with a halo that has to grow past the
+        # shorter band: the clamp must be the same on both ranks or the exchange sizes disagree
+        odd = block_map(96, 201, 0.0015, 2, seed=12)
+        lo, hi = shard.shard_range(odd.shape[0], world, rank)
+        out["band_odd"] = shard.sharded_distance_band(torch.from_numpy(odd[lo:hi].copy()), odd.shape[0], 0.2,
+                                                      _edt_cells_oracle, halo=4).numpy()
+        # fewer queries than ranks: the rank with the empty slice still takes part in the gather
+        one, (lo1, hi1, _) = shard.sharded_queries(starts[:1], goals[:1], plan)
+        out["one_plan"] = one
+        out["one_span"] = (lo1, hi1)
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -110,3 +120,11 @@ def test_sharded_paths_world2():
     assert full.max() > 4 * 0.2 * 3, "the test map must have distances well past the initial halo"
     got = np.concatenate([res[r]["band"] for r in range(world)], 0)
     assert got.dtype == np.float32 and np.array_equal(got, full.astype(np.float32))
+    odd = block_map(96, 201, 0.0015, 2, seed=12)
+    full = _edt_cells_oracle(torch.from_numpy(odd)).numpy() * float(np.float32(0.2))
+    assert full.max() > 0.2 * 64, "the odd-split map needs a halo past 64 rows: the next doubling (128) hits the clamp"
+    got = np.concatenate([res[r]["band_odd"] for r in range(world)], 0)
+    assert got.shape == (201, 96) and np.array_equal(got, full.astype(np.float32))
+    assert res[0]["one_span"] == (0, 1) and res[1]["one_span"] == (1, 1)
+    for r in range(world):
+        assert len(res[r]["one_plan"]) == 1 and res[r]["one_plan"][0] == res[r]["plans"][0]
