@@ -400,30 +400,33 @@ def ours_arm(args):
     t_max = float(t_all.item())
     value = F * n * args.steps * world / t_max / 1e6
 
-    # ---- e2e: the call a user of the reference API makes, host buffers in pinned memory
+    # ---- e2e: the path a user of the planner runs, through the host-buffer C ABI.  Per step: one map message (occupancy
+    # from pinned host memory: H2D + K1) and F start/goal queries on it -- hpp_plan_batch computes the F goal fields
+    # (K3a, the same F cells as the device-timed step), keeps them ON THE DEVICE where the search consumes them, runs the
+    # device-resident Hybrid A* and returns plan headers + trajectories to host memory.  Goal poses = centres of the F
+    # goal cells, start poses = collision-free poses of this rank's map.
+    res = float(np.float32(RES))
+    org = -side * res / 2.0
+    q_goals = np.stack([org + (goals[:, 0] + 0.5) * res, org + (goals[:, 1] + 0.5) * res, np.zeros(F)], 1)
+    cand = random_poses(64 * F + 4000, side, side, margin=20.0, seed=5 + rank)
+    q_starts = cand[m.collide_circles(cand) == 0][:F]
+    assert len(q_starts) == F, "not enough collision-free start poses on the map"
     occ_pin = torch.from_numpy(occ).pin_memory()
-    # host output buffer: all F fields at once when the host has the memory (one hpp_heuristic_batch call per step, its
-    # chunks overlap copy and compute); otherwise F/4 fields at a time through a smaller buffer (no overlap across calls)
-    import psutil
-    need = F * n * 8
-    ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    whole = psutil.virtual_memory().available / max(1, ranks_here) > 2.5 * need
-    Fe = F if whole else max(1, (F + 3) // 4)
-    try:
-        cost_pin = torch.empty(Fe * n, dtype=torch.float64, pin_memory=True)
-    except RuntimeError:                                       # not enough lockable host memory: pageable buffer
-        cost_pin = torch.empty(Fe * n, dtype=torch.float64)
-    occ_h, cost_h = occ_pin.numpy(), cost_pin.numpy().reshape(Fe, side, side)
+    plans_pin = torch.zeros(F * hpp.capi.PLAN_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(hpp.capi.PLAN_DTYPE)
+    traj_pin = torch.zeros((1 << 18, 5), dtype=torch.float64).pin_memory().numpy()
+    occ_h = occ_pin.numpy()
+    e2e_out = {}
 
     def e2e_step():
         m.update(occ_h)                                       # H2D occupancy + K1 + sync
-        for f0 in range(0, F, Fe):                            # K3a + D2H of the cost fields + sync
-            m.heuristic_batch(hpp.VARIANT_RS, goals[f0:f0 + Fe], out=cost_h[:len(goals[f0:f0 + Fe])])
+        p, t = m.plan_batch(hpp.VARIANT_RS, q_starts, q_goals, plans_out=plans_pin, traj_out=traj_pin)  # fields + A* + D2H
+        e2e_out["traj_rows"] = len(t)
 
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
         e2e_step()
     barrier()
+    launches_e0 = ctx.launches
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         flush.fill_(1)
@@ -431,14 +434,47 @@ def ours_arm(args):
     torch.cuda.synchronize()
     barrier()
     t_e2e = time.perf_counter() - t0
+    launches_e2e = (ctx.launches - launches_e0) // e2e_steps
     t_all = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     e2e_value = F * n * e2e_steps * world / float(t_all.item()) / 1e6
-    last0 = (F - 1) // Fe * Fe                                  # first field of the chunk left in the buffer
-    checksum = float(sum(np.nan_to_num(cost_h[f - last0, goals[f][1], :], posinf=0.0).sum() for f in range(last0, F)))
+    e2e_h2d = int(n + 2 * F * 24)
+    e2e_d2h = int(F * hpp.capi.PLAN_DTYPE.itemsize + e2e_out["traj_rows"] * 40 + 8)
+    e2e_solved = int((plans_pin["n_states"] > 1).sum())
+    e2e_iters = [float(plans_pin["iterations"].mean()), int(plans_pin["iterations"].max())]
+    # sub-figure (rank 0 of a 1-GPU run): holonomicCostsWithObstacles_planning through host buffers -- the F fp64 fields
+    # copied to pinned host memory (19.9 GB per step: PCIe-bound; the planner above never needs them on the host)
+    fields_to_host = None
+    cost_h = None
+    if world == 1:
+        import psutil
+        whole = psutil.virtual_memory().available > 2.5 * F * n * 8
+        Fe = F if whole else max(1, (F + 3) // 4)
+        try:
+            cost_pin = torch.empty(Fe * n, dtype=torch.float64, pin_memory=True)
+        except RuntimeError:                                   # not enough lockable host memory: pageable buffer
+            cost_pin = torch.empty(Fe * n, dtype=torch.float64)
+        cost_h = cost_pin.numpy().reshape(Fe, side, side)
+
+        def fields_step():
+            m.update(occ_h)
+            for f0 in range(0, F, Fe):
+                m.heuristic_batch(hpp.VARIANT_RS, goals[f0:f0 + Fe], out=cost_h[:len(goals[f0:f0 + Fe])])
+        fields_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            flush.fill_(1)
+            fields_step()
+        torch.cuda.synchronize()
+        t_f = (time.perf_counter() - t0) / 2
+        fields_to_host = {"value": F * n / t_f / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n),
+                          "d2h_bytes_per_step": int(8 * n * F), "fields_per_call": Fe,
+                          "api": "hpp_map_update + hpp_heuristic_batch (host buffers, pinned)"}
     # latency of one field through the reference-shaped call (hpp_heuristic_rs = holonomicCostsWithObstacles_planning)
-    m.heuristic_rs(goal, (0, 0), out=cost_h[0])
+    one_h = cost_h[0] if cost_h is not None else torch.empty(n, dtype=torch.float64).pin_memory().numpy().reshape(side, side)
+    m.heuristic_rs(goal, (0, 0), out=one_h)
     ts1 = []
     for _ in range(3):
         flush.fill_(2)
@@ -448,8 +484,9 @@ def ours_arm(args):
         ctx.sync()
         ts1.append(time.perf_counter() - t0)
     t0 = time.perf_counter()
-    m.heuristic_rs(goal, (0, 0), out=cost_h[0])
+    m.heuristic_rs(goal, (0, 0), out=one_h)
     t_single_e2e = time.perf_counter() - t0
+    del cost_h, one_h
 
     # goal-row sums of the first fields of the device-resident batch: compared with the reference arm's (cpu_baseline)
     m.heuristic_batch_dev(hpp.VARIANT_RS, goals, cost_dev)
@@ -474,10 +511,13 @@ def ours_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": bench_config(side, F),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(8 * n * F),
-                "steps": e2e_steps, "api": "hpp_map_update + hpp_heuristic_batch (host buffers, pinned)",
-                "fields_per_call": Fe,
-                "checksum": checksum},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
+                "steps": e2e_steps,
+                "api": "hpp_map_update (occupancy from pinned host memory) + hpp_plan_batch (F start/goal queries: the F "
+                       "goal fields stay on the device, device-resident Hybrid A*, plan headers + trajectories to host)",
+                "queries_per_step": F, "solved": e2e_solved, "iterations_mean_max": e2e_iters,
+                "gpu_launches_per_step": int(launches_e2e),
+                "fields_to_host": fields_to_host},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"heur_warp_kernel (one persistent launch, {F} fields, one CTA of 20 warps per field, one warp per 32x32 tile, compacted sweeps)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -490,9 +530,11 @@ def ours_arm(args):
 
     line["extra"] = {"single_field": {"ms_device": min(ts1) * 1e3, "mcells_per_s_device": n / min(ts1) / 1e6,
                                       "ms_e2e": t_single_e2e * 1e3, "api": "hpp_heuristic_rs (host buffer, D2H inside)"}}
+    if not args.no_sharded:
+        line["sharded"] = sharded_section(ctx, torch, hpp, rank, world, dist if world > 1 else None, not args.quick)
     if rank == 0 and world == 1 and not args.no_extras:
         cpu_x = cpu_extras_child(args)
-        line["extra"].update(extras(ctx, torch, hpp, stream, cpu_x))
+        line["extra"].update(extras(ctx, torch, hpp, stream, cpu_x, line.get("sharded", {}).get("cfg5")))
         cb = cpu_baseline(args)
         ref_sums = cb.pop("field_row_sums_first_wave", None) if isinstance(cb, dict) else None
         if ref_sums:
@@ -506,6 +548,93 @@ def ours_arm(args):
         dist.destroy_process_group()
 
 
+def sharded_section(ctx, torch, hpp, rank, world, dist, full):
+    """The partitioning the north_star names, through the C ABI's multi-GPU layer (hpp_comm: NCCL inside the library),
+    at every N (N = 1 is the base of the scaling figures):
+      cfg5      8192 RS queries = 8 parking maps x 1024 pairs, STRONG scaling: the query list is split contiguously
+                over the ranks (maps replicated), every rank plans its slice with one hpp_plan_batch_multi call and the
+                plan headers are gathered to every rank by one ncclAllGather (hpp_plan_batch_sharded);
+                queries/s = 8192 / max-over-ranks wall time, warm-up pass first, best of 3.
+      edt_band  distance layer of an 8192^2 and a 16384^2 map in row bands: pass 1 local, halo rows of the pass-1
+                result exchanged with the neighbours (ncclSend/Recv), pass 2 (hpp_distance_layer_sharded); wall time
+                with the exchange inside, max over ranks, best of 3."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    idt = torch.zeros(hpp.capi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(hpp.comm_unique_id()), dtype=torch.uint8))
+    if world > 1:
+        dist.broadcast(idt, 0)
+    comm = hpp.Comm(ctx, idt.cpu().numpy().tobytes(), rank, world)
+
+    def timed(fn, reps=3):
+        best = float("inf")
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            fn()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, float(t.item()))
+        return best
+    out = {}
+    # ---- cfg5
+    nmaps, npairs = 8, 1024
+    maps = {}
+
+    def dev_collide(k, pm, cand):                    # device verdicts (bit-exact with the oracle: tests)
+        maps[k] = hpp.Map(ctx, pm, RES)
+        return maps[k].collide_circles(cand)
+    jobs = cfg5_jobs(nmaps, npairs, dev_collide)
+    mlist = [maps[k] for k in range(nmaps)]
+    starts = np.vstack([j["starts"] for j in jobs])
+    goals = np.vstack([j["goals"] for j in jobs])
+    moq = np.repeat(np.arange(nmaps, dtype=np.uint32), npairs)
+    res = {}
+
+    def run5():
+        res["plans"], _, res["span"] = comm.plan_batch_sharded(mlist, moq, hpp.VARIANT_RS, starts, goals, traj_cap=1 << 21)
+    run5()                                           # warm-up: device scratch grows once
+    l0 = ctx.launches
+    t5 = timed(run5)
+    plans = res["plans"]
+    out["cfg5"] = {"queries_per_s": nmaps * npairs / t5, "ms": t5 * 1e3, "queries": nmaps * npairs,
+                   "solved": int((plans["n_states"] > 1).sum()), "scaling": "strong",
+                   "queries_on_rank0": int(res["span"][1] - res["span"][0]),
+                   "iterations_max": int(plans["iterations"].max()),
+                   "gpu_launches_per_pass": int((ctx.launches - l0) // 3),
+                   "api": "hpp_plan_batch_sharded (hpp_plan_batch_multi on the rank's slice of the query list: one call, "
+                          "no host threads; ncclAllGather of the plan headers)"}
+    for mm in mlist:
+        mm.close()
+    # ---- distance layer in row bands
+    out["edt_band"] = {}
+    for side in ((8192, 16384) if full else (8192,)):
+        lo, hi = hpp.shard_range(side, world, rank)
+        rng = np.random.default_rng(77)              # the same map on every rank, synthesised band by band
+        b = rng.random((side // 8, side // 8)) < 0.30
+        band_occ = torch.from_numpy(np.ascontiguousarray(
+            (np.kron(b[lo // 8:(hi + 7) // 8], np.ones((8, 8), np.int8)) * 100).astype(np.int8)[lo - lo // 8 * 8:][:hi - lo])).to(dev)
+        band = torch.empty((hi - lo) * side, dtype=torch.float32, device=dev)
+        rep = {}
+
+        def run_band():
+            rep["r"] = comm.distance_layer_sharded(band_occ, side, side, RES, band, None, halo=64)
+        run_band()
+        tb = timed(run_band)
+        r = rep["r"]
+        out["edt_band"][f"{side}x{side}"] = {"ms": tb * 1e3, "rows_per_rank": int(hi - lo), "halo_rows": int(r.halo_rows),
+                                             "rounds": int(r.rounds), "gathered_all": int(r.gathered_all),
+                                             "halo_bytes_sent_rank0": int(r.halo_bytes_sent),
+                                             "gcells_per_s": side * side / tb / 1e9,
+                                             "band_checksum_rank0": float(band.double().sum().item())}
+        del band_occ, band
+    comm.close()
+    return out
+
+
 def k4_traffic():
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k4_collide_circles"]
@@ -514,7 +643,7 @@ def k4_traffic():
         return None
 
 
-def extras(ctx, torch, hpp, stream, cpu_x):
+def extras(ctx, torch, hpp, stream, cpu_x, cfg5_dev):
     """cfg4 (collision checks/s) and cfg5 (queries/s): device numbers, with the all-core CPU figures of cpu_x beside."""
     from oracle import pyorc as O
     out = {}
@@ -562,49 +691,16 @@ def extras(ctx, torch, hpp, stream, cpu_x):
         "cpu": cpu4}
     m.close()
     del poses, verd, d_occ
-    # ---- cfg5: 8192 RS queries = 8 synthetic parking maps x 1024 start/goal pairs.  A query is one warp from start to
-    # finish and one map's batch does not fill the GPU, so the maps are planned concurrently, one context (= one stream)
-    # per map, from host threads (the C ABI is re-entrant across contexts; ctypes releases the GIL during the calls).
-    import threading
-    nmaps, npairs = 8, 1024
-    cxs, mms = {}, {}
-
-    def dev_collide(k, pm, cand):                    # device verdicts (bit-exact with the oracle: tests)
-        cxs[k] = hpp.Context(torch.cuda.current_device())
-        mms[k] = hpp.Map(cxs[k], pm, RES)
-        return mms[k].collide_circles(cand)
-    jobs = cfg5_jobs(nmaps, npairs, dev_collide)
-    for k, j in enumerate(jobs):
-        j.update(ctx=cxs[k], map=mms[k])
-    for j in jobs:                                   # warm-up: every context grows its device scratch once
-        j["map"].plan_batch(hpp.VARIANT_RS, j["starts"], j["goals"])
-
-    def work(j):
-        j["plans"], _ = j["map"].plan_batch(hpp.VARIANT_RS, j["starts"], j["goals"])
-    t_gpu = float("inf")
-    for _ in range(3):                               # best of three (host thread start-up jitters the first pass)
-        th = [threading.Thread(target=work, args=(j,)) for j in jobs]
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        t_gpu = min(t_gpu, time.perf_counter() - t0)
-    solved = int(sum((j["plans"]["n_states"] > 1).sum() for j in jobs))
-    for j in jobs:
-        j["map"].close()
-        j["ctx"].close()
     try:
         out["cfg1_cfg2_latency"] = fixture_latency(ctx, hpp, O)
     except Exception as e:  # pragma: no cover  (never let an extra sink the headline line)
         out["cfg1_cfg2_latency"] = {"error": str(e)[-200:]}
-    nq = nmaps * npairs
-    out["cfg5_queries"] = {"queries_per_s": nq / t_gpu, "queries": nq, "solved": solved, "maps_in_flight": nmaps,
-                           "api": "hpp_plan_batch per map (host buffers; heuristic fields + device-resident A*), one "
-                                  "context per map, maps planned concurrently from host threads; best of 3 passes",
-                           "cpu": cpu_x.get("cfg5", {"error": cpu_x.get("error", "no CPU leg")})}
-    if "solved" in out["cfg5_queries"]["cpu"]:
-        out["cfg5_queries"]["cpu"]["device_solved_count_matches"] = bool(out["cfg5_queries"]["cpu"]["solved"] == solved)
+    # ---- cfg5: the 1-GPU figure of the sharded section (one hpp_plan_batch_multi call for the 8 maps), CPU beside it
+    out["cfg5_queries"] = dict(cfg5_dev or {"error": "sharded section skipped"})
+    out["cfg5_queries"]["cpu"] = cpu_x.get("cfg5", {"error": cpu_x.get("error", "no CPU leg")})
+    if "solved" in out["cfg5_queries"]["cpu"] and "solved" in out["cfg5_queries"]:
+        out["cfg5_queries"]["cpu"]["device_solved_count_matches"] = bool(
+            out["cfg5_queries"]["cpu"]["solved"] == out["cfg5_queries"]["solved"])
     return out
 
 
@@ -659,7 +755,23 @@ def fixture_latency(ctx, hpp, O):
             tc.append(time.perf_counter() - t0)
             if time.perf_counter() - t_begin > 10.0:
                 break
+        quirk = None
+        if variant == 0 and W * H > 70000:
+            # the reference's progress-check quirk H1 (RS/src/HybridAstar.cpp:452-472) fires on maps of more than 70 000
+            # cells: count the heuristic cells on which the reference (oracle, quirks on) differs from the exact fixed
+            # point the device returns, for the last query, next to what hpp_quirk_report says
+            om_q = O.Map(occ, res, with_layers=False)
+            st, gl = O._state(om_q, *starts[-1]), O._state(om_q, *goals[-1])
+            gcell, scell = (int(gl.gridx), int(gl.gridy)), (int(st.gridx), int(st.gridy))
+            hq, q = O.heuristic_rs(occ, gcell, scell, quirks=True)
+            got, rep = m.heuristic_rs(gcell, scell)
+            fin = np.isfinite(hq) & np.isfinite(got) & (got > 0)
+            quirk = {"h1_fired_in_reference": bool(q.h1_fired), "cells_differing_from_reference": int((hq != got).sum()),
+                     "max_rel_diff": float(np.max(np.abs(hq[fin] - got[fin]) / got[fin])) if fin.any() else 0.0,
+                     "hpp_quirk_report_h1": int(rep.h1_progress_break),
+                     "plans_equal_reference": "asserted in tests/test_gpu_baseline_configs.py::test_cfg1_rs_on_gridmap"}
         out[name] = {"cells": int(W * H), "queries": len(starts), "solved": ok, "iterations_mean": float(np.mean(its)),
+                     "reference_quirk_h1": quirk,
                      "iterations_max": int(max(its)), "map_build_ms": t_map * 1e3,
                      "ms_per_query": 1e3 * float(np.mean(ts)), "ms_per_query_max": 1e3 * float(max(ts)),
                      "cpu": {"ms_per_query": 1e3 * float(np.mean(tc)), "ms_per_query_max": 1e3 * float(max(tc)),
@@ -706,6 +818,8 @@ def main():
     ap.add_argument("--fields", type=int, default=148, help="goal fields (queries) per step; default = one per SM of a B200")
     ap.add_argument("--ref-cores", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the cfg5 / EDT-band section")
+    ap.add_argument("--quick", action="store_true", help="skip the 16384^2 band case")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -90,6 +90,8 @@ def lib():
             "hpp_map_cells": [vp, vp, sz, vp, vp],
             "hpp_inflate": [vp, vp, u32, u32, dbl, dbl, vp],
             "hpp_inflate_dev": [vp, vp, u32, u32, dbl, dbl, vp],
+            "hpp_cv_threshold_otsu": [vp, vp, u32, u32, vp, C.POINTER(dbl)],
+            "hpp_cv_dilate_ellipse": [vp, vp, u32, u32, i32, i32, vp],
             "hpp_image_to_occupancy": [vp, vp, u32, u32, vp],
             "hpp_image_to_occupancy_dev": [vp, vp, u32, u32, vp],
             "hpp_collide_circles": [vp, vp, sz, vp],
@@ -104,7 +106,7 @@ def lib():
             "hpp_expand_dev": [vp, C.c_int, vp, sz, vp],
             "hpp_rs_shot": [vp, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)],
             "hpp_dubins_shot": [vp, vp, sz, vp, sz, vp, vp, sz, C.POINTER(sz)],
-            "hpp_rs_all_paths": [vp, vp, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, sz],
+            "hpp_rs_all_paths": [vp, vp, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp],
             "hpp_test_heap_ops": [vp, vp, vp, sz, vp, vp],
             "hpp_dubins_path": [vp, vp, vp, dbl, dbl, vp, vp, vp, vp, sz],
             "hpp_plan_batch": [vp, C.c_int, vp, vp, sz, vp, vp, sz, C.POINTER(sz)],
@@ -184,6 +186,25 @@ class Context:
         self.check(self.L.hpp_inflate(self.h, occ.ctypes.data, W, H, float(resolution), float(radius), out.ctypes.data))
         return out
 
+    def cv_threshold_otsu(self, gray):
+        """cv2.threshold(gray, 0, 255, THRESH_BINARY | THRESH_OTSU) -> (threshold, binary image)"""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        H, W = gray.shape
+        out = np.empty_like(gray)
+        thr = C.c_double(0)
+        self.check(self.L.hpp_cv_threshold_otsu(self.h, gray.ctypes.data, W, H, out.ctypes.data, C.byref(thr)))
+        return thr.value, out
+
+    def cv_dilate_ellipse(self, binary, r, complemented=False):
+        """cv2.dilate(binary, getStructuringElement(MORPH_ELLIPSE, (2r+1, 2r+1), (r, r))) for a 0 / non-zero image;
+        complemented=True: `binary` holds the complement of the image to dilate (a folded cv2.bitwise_not)"""
+        binary = np.ascontiguousarray(binary, np.uint8)
+        H, W = binary.shape
+        out = np.empty_like(binary)
+        self.check(self.L.hpp_cv_dilate_ellipse(self.h, binary.ctypes.data, W, H, int(r), int(bool(complemented)),
+                                                out.ctypes.data))
+        return out
+
     def image_to_occupancy(self, img):
         """8-bit gray image [rows, cols] -> occupancy [H = cols, W = rows] (grid_map_publisher's conversion)"""
         img = np.ascontiguousarray(img, np.uint8)
@@ -216,15 +237,16 @@ class Context:
         tl = np.zeros(max_paths)
         ns = np.zeros(max_paths, np.int32)
         samples = np.zeros((samples_cap, 3))
+        dirs = np.zeros(samples_cap, np.int32)
         self.check(self.L.hpp_rs_all_paths(self.h, s3, g3, maxc, step, max_paths, C.byref(n_paths), n_seg.ctypes.data,
                                            lengths.ctypes.data, types.ctypes.data, tl.ctypes.data, ns.ctypes.data,
-                                           samples.ctypes.data, samples_cap))
+                                           samples.ctypes.data, samples_cap, dirs.ctypes.data))
         out, off = [], 0
         for k in range(n_paths.value):
             m = int(ns[k])
             out.append(dict(lengths=lengths[k, :n_seg[k]].copy(), types=bytes(types[k, :n_seg[k]]).decode(), L=tl[k],
                             x=samples[off:off + m, 0].copy(), y=samples[off:off + m, 1].copy(),
-                            yaw=samples[off:off + m, 2].copy()))
+                            yaw=samples[off:off + m, 2].copy(), dir=dirs[off:off + m].copy()))
             off += m
         return out
 
@@ -385,14 +407,16 @@ class Map:
     def dubins_shot(self, starts, goals, samples_cap=1 << 20):
         return self._shot(self.L.hpp_dubins_shot, starts, goals, samples_cap)
 
-    def plan_batch(self, variant, starts, goals, traj_cap=1 << 22):
+    def plan_batch(self, variant, starts, goals, traj_cap=1 << 22, plans_out=None, traj_out=None):
+        """plans_out / traj_out: caller-owned result buffers (e.g. pinned), otherwise fresh arrays"""
         starts = np.ascontiguousarray(starts, np.float64).reshape(-1, 3)
         goals = np.ascontiguousarray(goals, np.float64).reshape(-1, 3)
-        plans = np.zeros(len(starts), PLAN_DTYPE)
-        traj = np.zeros((traj_cap, 5))
+        plans = plans_out if plans_out is not None else np.zeros(len(starts), PLAN_DTYPE)
+        traj = traj_out if traj_out is not None else np.empty((traj_cap, 5))
+        assert len(plans) == len(starts) and plans.dtype == PLAN_DTYPE and traj.dtype == np.float64
         used = C.c_size_t(0)
         self.ctx.check(self.L.hpp_plan_batch(self.h, variant, starts.ctypes.data, goals.ctypes.data, len(starts),
-                                             plans.ctypes.data, traj.ctypes.data, traj_cap, C.byref(used)))
+                                             plans.ctypes.data, traj.ctypes.data, len(traj), C.byref(used)))
         return plans, traj[:used.value]
 
     def close(self):

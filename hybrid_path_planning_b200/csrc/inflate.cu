@@ -29,8 +29,12 @@ __global__ void __launch_bounds__(256) occ_hist_kernel(const int8_t *__restrict_
   h[threadIdx.x] = 0;
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t n16 = n / 16;
-  const int4 *p = (const int4 *)occ;
+  // the caller's pointer may be any byte address (a view into a larger buffer): bytes up to the first 16-byte
+  // boundary and after the last whole 16-byte group are read one by one, the rest with 16-byte loads
+  size_t head = (size_t)((16 - ((uintptr_t)occ & 15)) & 15);
+  if (head > n) head = n;
+  const size_t n16 = (n - head) / 16;
+  const int4 *p = (const int4 *)(occ + head);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
     int4 v = __ldg(p + i);
     uint8_t b[16];
@@ -38,7 +42,8 @@ __global__ void __launch_bounds__(256) occ_hist_kernel(const int8_t *__restrict_
 #pragma unroll
     for (int k = 0; k < 16; k++) atomicAdd(&h[b[k]], 1u);
   }
-  for (size_t i = n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < head; i += stride) atomicAdd(&h[(uint8_t)occ[i]], 1u);
+  for (size_t i = head + n16 * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     atomicAdd(&h[(uint8_t)occ[i]], 1u);
   __syncthreads();
   if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
@@ -93,7 +98,7 @@ struct ellipse_rows {
 
 __global__ void __launch_bounds__(256) inflate_col_kernel(const uint16_t *__restrict__ g, int W, int H,
                                                           const ellipse_rows *__restrict__ el_dev,
-                                                          int8_t *__restrict__ out) {
+                                                          int8_t *__restrict__ out, int8_t hit_value) {
   __shared__ uint16_t dxs[2 * INF_MAX_R + 1];
   const int r = el_dev->r;
   for (int i = threadIdx.x; i < 2 * r + 1; i += blockDim.x) dxs[i] = el_dev->dx[i];
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) inflate_col_kernel(const uint16_t *__rest
   const int lo = max(0, y - r), hi = min(H - 1, y + r);  // dilate border: outside pixels never win
   for (int yy = lo; yy <= hi && !hit; yy++) hit = g[(size_t)yy * W + x] <= dxs[yy - y + r];
   // dilated 255 -> inverted 0 -> occ' = 100 - round(0) = 100; else 100 - round(255*100/255) = 0  (:151-157)
-  out[(size_t)y * W + x] = hit ? 100 : 0;
+  out[(size_t)y * W + x] = hit ? hit_value : (int8_t)0;  // hit_value: 100 (occupancy out) or -1 = 255 (cv::dilate out)
 }
 
 hpp_status hpp_inflate_launch(hpp_ctx *c, const int8_t *occ_dev, uint32_t W, uint32_t H, double resolution,
@@ -153,7 +158,7 @@ hpp_status hpp_inflate_launch(hpp_ctx *c, const int8_t *occ_dev, uint32_t W, uin
   s = hpp_row_dist_launch(c, occ_dev, (int)W, (int)H, d_lut, d_g, nullptr, d_any);
   if (s != HPP_OK) return s;
   dim3 cgrid(hpp_div_up(W, 256), H);
-  inflate_col_kernel<<<cgrid, 256, 0, c->stream>>>(d_g, (int)W, (int)H, d_el, out_dev);
+  inflate_col_kernel<<<cgrid, 256, 0, c->stream>>>(d_g, (int)W, (int)H, d_el, out_dev, (int8_t)100);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
@@ -179,6 +184,120 @@ extern "C" hpp_status hpp_inflate(hpp_ctx *c, const int8_t *occ, uint32_t W, uin
   s = hpp_inflate_launch(c, (const int8_t *)d_in, W, H, resolution, inflation_radius, (int8_t *)d_out);
   if (s != HPP_OK) return s;
   HPP_CUDA(c, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, c->stream));
+  HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HPP_OK;
+}
+
+// ------------------------------------------------------------------ the two OpenCV calls of InflateMap, as such
+// MI/src/map_inflate_node.cpp:115-139 is `threshold(OTSU) -> bitwise_not -> dilate(ellipse) -> bitwise_not` on a gray
+// cv::Mat.  host/dropin/mi/opencv2/opencv.hpp maps exactly those calls onto the two entry points below, so the node's
+// source compiles and runs unmodified with the image work on the device (same kernels as hpp_inflate).
+__global__ void __launch_bounds__(256) lut_binarize_kernel(const uint8_t *__restrict__ src, size_t n,
+                                                           const pred_lut *__restrict__ lut, uint8_t *__restrict__ dst) {
+  __shared__ pred_lut l;
+  if (threadIdx.x < 8) l.w[threadIdx.x] = lut->w[threadIdx.x];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned v = src[i];
+    dst[i] = ((l.w[v >> 5] >> (v & 31)) & 1u) ? 0 : 255;  // lut = "gray <= threshold"
+  }
+}
+
+__global__ void otsu_threshold_out_kernel(const pred_lut *__restrict__ lut, uint32_t *__restrict__ thr_out) {
+  // the predicate table is "v <= thr" for the identity gray table: thr = number of set bits - 1
+  int cnt = 0;
+  for (int k = 0; k < 8; k++) cnt += __popc(lut->w[k]);
+  *thr_out = (uint32_t)(cnt - 1);
+}
+
+// cv::threshold(src, dst, 0, 255, THRESH_BINARY | THRESH_OTSU) on an 8-bit single-channel image (host buffers)
+extern "C" hpp_status hpp_cv_threshold_otsu(hpp_ctx *c, const uint8_t *src, uint32_t W, uint32_t H, uint8_t *dst,
+                                            double *threshold_out) {
+  if (!c || !src || !dst || W == 0 || H == 0) return HPP_ERR_ARG;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)W * H;
+  void *d_in, *d_out, *scr;
+  hpp_status s = hpp_scratch(c, 0, n, &d_in);
+  if (s != HPP_OK) return s;
+  s = hpp_scratch(c, 1, n, &d_out);
+  if (s != HPP_OK) return s;
+  s = hpp_scratch(c, 2, 1024 + 256 + 64, &scr);
+  if (s != HPP_OK) return s;
+  unsigned int *d_hist = (unsigned int *)scr;
+  pred_lut *d_lut = (pred_lut *)((uint8_t *)scr + 1024);
+  uint32_t *d_thr = (uint32_t *)((uint8_t *)scr + 1024 + 64);
+  gray_table gt;
+  for (int v = 0; v < 256; v++) gt.g[v] = (uint8_t)v;  // the image already holds gray values
+  HPP_CUDA(c, cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, c->stream));
+  HPP_CUDA(c, cudaMemsetAsync(d_hist, 0, 1024 + 256 + 64, c->stream));
+  int grid = (int)((n / 4096 + 1) < (size_t)c->sm_count * 8 ? (n / 4096 + 1) : (size_t)c->sm_count * 8);
+  occ_hist_kernel<<<grid, 256, 0, c->stream>>>((const int8_t *)d_in, n, d_hist);
+  HPP_LAUNCHED(c);
+  otsu_kernel<<<1, 32, 0, c->stream>>>(d_hist, gt, (double)W * (double)H, d_lut);
+  HPP_LAUNCHED(c);
+  lut_binarize_kernel<<<grid, 256, 0, c->stream>>>((const uint8_t *)d_in, n, d_lut, (uint8_t *)d_out);
+  HPP_LAUNCHED(c);
+  otsu_threshold_out_kernel<<<1, 1, 0, c->stream>>>(d_lut, d_thr);
+  HPP_LAUNCHED(c);
+  HPP_CUDA(c, cudaMemcpyAsync(dst, d_out, n, cudaMemcpyDeviceToHost, c->stream));
+  HPP_CUDA(c, cudaMemcpyAsync(c->h_flags + 52, d_thr, 4, cudaMemcpyDeviceToHost, c->stream));
+  HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (threshold_out) *threshold_out = (double)c->h_flags[52];
+  return HPP_OK;
+}
+
+// cv::dilate(src, dst, getStructuringElement(MORPH_ELLIPSE, Size(2r+1, 2r+1), Point(r, r))) on a BINARY 8-bit image
+// (pixels are 0 or non-zero, as cv::threshold leaves them; non-zero pixels come out as 255): host buffers
+extern "C" hpp_status hpp_cv_dilate_ellipse(hpp_ctx *c, const uint8_t *src, uint32_t W, uint32_t H, int32_t r,
+                                            int32_t src_complemented, uint8_t *dst) {
+  if (!c || !src || !dst || W == 0 || H == 0 || r < 0) return HPP_ERR_ARG;
+  // dilating the set pixels by the ellipse = inflating "occupied" cells: the inflate pipeline with a predicate table
+  // that marks every non-zero byte, and 100/0 mapped to 255/0 on the way out
+  if (r > INF_MAX_R) HPP_FAIL(c, HPP_ERR_UNSUPPORTED, "structuring element radius %d > %d", r, INF_MAX_R);
+  if (W >= 65535u) HPP_FAIL(c, HPP_ERR_UNSUPPORTED, "dilate supports W < 65535");
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)W * H;
+  void *d_in, *d_out, *scr;
+  hpp_status s = hpp_scratch(c, 0, n, &d_in);
+  if (s != HPP_OK) return s;
+  s = hpp_scratch(c, 1, n, &d_out);
+  if (s != HPP_OK) return s;
+  const size_t g_bytes = (n * 2 + 255) & ~(size_t)255;
+  s = hpp_scratch(c, 2, g_bytes + 1024 + 256 + sizeof(ellipse_rows) + 256, &scr);
+  if (s != HPP_OK) return s;
+  uint16_t *d_g = (uint16_t *)scr;
+  pred_lut *d_lut = (pred_lut *)((uint8_t *)scr + g_bytes + 1024);
+  uint32_t *d_any = (uint32_t *)((uint8_t *)scr + g_bytes + 1024 + 64);
+  ellipse_rows *d_el = (ellipse_rows *)((uint8_t *)scr + g_bytes + 1024 + 256);
+  void *hp;
+  s = hpp_pinned(c, 1, sizeof(ellipse_rows) + sizeof(pred_lut), &hp);
+  if (s != HPP_OK) return s;
+  HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  ellipse_rows *el = (ellipse_rows *)hp;
+  pred_lut *lut = (pred_lut *)(el + 1);
+  el->r = r;
+  const double inv_r2 = r ? 1. / ((double)r * r) : 0.;
+  for (int i = 0; i < 2 * r + 1; i++) {
+    int dy = i - r;
+    el->dx[i] = (uint16_t)(int)nearbyint(r * sqrt((r * r - dy * dy) * inv_r2));
+  }
+  if (src_complemented) {  // the bytes are the complement of the image (a cv::bitwise_not not yet applied): 255 = unset
+    for (int k = 0; k < 8; k++) lut->w[k] = 0xffffffffu;
+    lut->w[7] &= ~(1u << 31);
+  } else {                 // every byte but 0 is a set pixel
+    for (int k = 0; k < 8; k++) lut->w[k] = 0xffffffffu;
+    lut->w[0] &= ~1u;
+  }
+  HPP_CUDA(c, cudaMemcpyAsync(d_el, el, sizeof(ellipse_rows), cudaMemcpyHostToDevice, c->stream));
+  HPP_CUDA(c, cudaMemcpyAsync(d_lut, lut, sizeof(pred_lut), cudaMemcpyHostToDevice, c->stream));
+  HPP_CUDA(c, cudaMemsetAsync(d_any, 0, 4, c->stream));
+  HPP_CUDA(c, cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, c->stream));
+  s = hpp_row_dist_launch(c, (const int8_t *)d_in, (int)W, (int)H, d_lut, d_g, nullptr, d_any);
+  if (s != HPP_OK) return s;
+  dim3 cgrid(hpp_div_up(W, 256), H);
+  inflate_col_kernel<<<cgrid, 256, 0, c->stream>>>(d_g, (int)W, (int)H, d_el, (int8_t *)d_out, (int8_t)-1);
+  HPP_LAUNCHED(c);
+  HPP_CUDA(c, cudaMemcpyAsync(dst, d_out, n, cudaMemcpyDeviceToHost, c->stream));
   HPP_CUDA(c, cudaStreamSynchronize(c->stream));
   return HPP_OK;
 }

@@ -190,6 +190,7 @@ struct all_paths_hdr {
   double lengths[RS_NCAND][5];
   double total[RS_NCAND];
   char types[RS_NCAND][5];
+  int seg_samples[RS_NCAND][5];  // interior samples per segment (the end sample of the last segment comes on top)
   unsigned long long samples_needed;
 };
 
@@ -207,7 +208,11 @@ __global__ void __launch_bounds__(32) rs_all_paths_kernel(double sx, double sy, 
     sv.out = samples;
     sv.cap = cap;
     sv.base = base;
-    int n_keep = warp_sample_path<false>(S.len[k], S.typ[k], S.nseg[k], maxc, step_size * maxc, sx, sy, syaw, sv);
+    if (lane == 0)
+      for (int i = 0; i < 5; i++) hdr->seg_samples[e][i] = 0;
+    __syncwarp();
+    int n_keep = warp_sample_path<false>(S.len[k], S.typ[k], S.nseg[k], maxc, step_size * maxc, sx, sy, syaw, sv, true,
+                                         hdr->seg_samples[e]);
     if (lane == 0) {
       hdr->n_seg[e] = S.nseg[k];
       hdr->n_samples[e] = n_keep;
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(32) rs_all_paths_kernel(double sx, double sy, 
 extern "C" hpp_status hpp_rs_all_paths(hpp_ctx *c, const double start[3], const double goal[3], double maxc,
                                        double step_size, int32_t max_paths, int32_t *n_paths, int32_t *n_seg,
                                        double *lengths, char *types, double *total_len, int32_t *n_samples,
-                                       double *samples, size_t samples_cap) {
+                                       double *samples, size_t samples_cap, int32_t *directions) {
   if (!c || !start || !goal || !n_paths || !n_seg || !lengths || !types || !total_len || !n_samples || max_paths < 1)
     return HPP_ERR_ARG;
   HPP_CUDA(c, cudaSetDevice(c->device));
@@ -261,6 +266,22 @@ extern "C" hpp_status hpp_rs_all_paths(hpp_ctx *c, const double start[3], const 
   if (h->samples_needed && samples) {
     HPP_CUDA(c, cudaMemcpyAsync(samples, d_samples, h->samples_needed * 24, cudaMemcpyDeviceToHost, c->stream));
     HPP_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  if (directions) {
+    // PATH::directions (RS/src/reeds_shepp_path.cpp:697, :714-721 via interpolate): slot 0 carries the sign of the first
+    // segment, every later slot the sign of the segment that wrote it; trimmed like the samples
+    size_t o = 0;
+    for (int e = 0; e < h->n_paths; e++) {
+      const int keep = h->n_samples[e];
+      int j = 0;
+      if (keep > 0) directions[o + j++] = h->lengths[e][0] > 0.0 ? 1 : -1;
+      for (int i = 0; i < h->n_seg[e]; i++) {
+        const int dsign = h->lengths[e][i] > 0.0 ? 1 : -1;
+        const int cnt = h->seg_samples[e][i] + (i == h->n_seg[e] - 1 ? 1 : 0);
+        for (int q = 0; q < cnt && j < keep; q++) directions[o + j++] = dsign;
+      }
+      o += (size_t)keep;
+    }
   }
   return HPP_OK;
 }

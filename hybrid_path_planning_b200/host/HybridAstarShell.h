@@ -10,7 +10,10 @@
 #include <memory>
 #include <vector>
 
+#include <type_traits>
+
 #include "GridMapShell.h"
+#include "PathShells.h"
 
 template <int VARIANT>
 class HybridAstarT {
@@ -20,8 +23,15 @@ class HybridAstarT {
   std::vector<State> run(State start_state, State goal_state);
   std::vector<std::vector<State>> run_batch(const std::vector<State> &starts, const std::vector<State> &goals);
 
+  // RS/include/HybridAstar.h:51 / DB/include/HybridAstar.h:40: the reference fills its private command list here
+  // (RS/src/HybridAstar.cpp:14-23); the commands of the shell live with the map on the device (hpp_map_set_params)
+  // and this call fetches a host copy of them: {steering angle, direction} per command, in the reference's order
+  void motionCommands();
+  const std::vector<std::vector<double>> &commands() const { return motionCommand; }
   // RS/include/HybridAstar.h:52-53 / DB/include/HybridAstar.h:41-42
   std::vector<std::shared_ptr<planner::Node>> GetnextNeighbours(const std::shared_ptr<planner::Node> &current_node);
+  // RS/src/HybridAstar.cpp:80-107: Cost_path of the child that motionCommand = {steering angle, direction} produces
+  double PathCost(const std::shared_ptr<planner::Node> &current_node, const std::vector<double> &motionCommand);
   // RS/include/HybridAstar.h:56 (reeds_shepp_Path) / DB/include/HybridAstar.h:47 (dubins_Path): nullptr = no shot
   std::shared_ptr<planner::Node> analyticShot(const std::shared_ptr<planner::Node> &current_Node,
                                               const std::shared_ptr<planner::Node> &goal_Node);
@@ -33,9 +43,15 @@ class HybridAstarT {
                                              const std::shared_ptr<planner::Node> &g) {
     return analyticShot(c, g);
   }
-  // RS/include/HybridAstar.h:62: cost per cell, row-major [y*W + x], +inf (RS) / 1000 (Dubins) where unreachable
-  std::vector<double> holonomicCostsWithObstacles_planning(const std::shared_ptr<planner::Node> &GoalNode);
-  // DB/include/HybridAstar.h:51 form: one HolonomicNode per cell (only ->cost is meaningful, as in the caller)
+  // The heuristic under the reference's name and with the reference's return type of each package:
+  //   RS/include/HybridAstar.h:62  std::vector<double>, cost per cell, row-major [y*W + x], +inf where unreachable
+  //   DB/include/HybridAstar.h:51  std::vector<std::shared_ptr<planner::HolonomicNode>>, one node per cell (->cost 1000
+  //                                where unreachable; only ->cost and the cell of ->Current_state are meaningful)
+  using HeuristicResult = typename std::conditional<VARIANT == HPP_VARIANT_RS, std::vector<double>,
+                                                    std::vector<std::shared_ptr<planner::HolonomicNode>>>::type;
+  HeuristicResult holonomicCostsWithObstacles_planning(const std::shared_ptr<planner::Node> &GoalNode);
+  // both forms for either planner
+  std::vector<double> holonomicCosts(const std::shared_ptr<planner::Node> &GoalNode);
   std::vector<std::shared_ptr<planner::HolonomicNode>> holonomicCostsWithObstacles_nodes(
       const std::shared_ptr<planner::Node> &GoalNode);
   // set when the last heuristic call hit an input on which the reference's sequential quirks (H1/H2) may fire
@@ -47,6 +63,7 @@ class HybridAstarT {
   CarData car_data_;
   double simulationLength, step_car;
   State start_state_;
+  std::vector<std::vector<double>> motionCommand;
   hpp_quirk_report report_{};
 };
 

@@ -27,3 +27,11 @@ if [ -f "$REF/reeds_shepp_hybrid_astar/src/main_path_planning.cpp" ] && [ -d "$M
     echo "built hybrid_path_planning_b200/ref_node_$tag (reference node source, unmodified, on the shells)"
   done
 fi
+
+# map_inflate: the reference's UNMODIFIED node source (it has no header: the harness includes the .cpp) against the cv shim
+# of dropin/mi (opencv2/opencv.hpp -> hpp_cv_threshold_otsu / hpp_cv_dilate_ellipse) inside the stand-in ROS
+if [ -f "$REF/map_inflate/src/map_inflate_node.cpp" ] && [ -d "$MOCK" ]; then
+  $CXX $CXXFLAGS -Dmain=reference_node_main -Idropin/mi -I"$MOCK/include" -I. -I../../include -I"$REF/map_inflate/src" \
+    "$MOCK/mi_node_harness.cpp" -L.. -l:libhpp_host.so -l:libhpp_b200.so -Wl,-rpath,'$ORIGIN' -o ../ref_node_mi
+  echo "built hybrid_path_planning_b200/ref_node_mi (reference map_inflate node source, unmodified, on the cv shim)"
+fi

@@ -2,6 +2,7 @@
 // (RS/src/main_path_planning.cpp:63-69 gridMapdata, :283-300 the query) and prints the results as text.
 // Built and run by tests/test_gpu_host_shells.py, which compares the output with the oracle.
 //   shell_demo <occ.raw> <W> <H> <variant 0|1> <sx> <sy> <sh> <gx> <gy> <gh>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -24,6 +25,15 @@ struct OccupancyGridLike {
   std::vector<int8_t> data;
 };
 
+static std::vector<double> costs_of(const std::vector<double> &h) { return h; }
+static std::vector<double> costs_of(const std::vector<std::shared_ptr<planner::HolonomicNode>> &nodes) {
+  std::vector<double> h;
+  for (const auto &n : nodes) h.push_back(n->cost);
+  return h;
+}
+
+static void drive_paths(const State &start, const State &goal);
+
 template <class Planner>
 static int drive(Grid_map &grid, const CarData &car, const State &start, const State &goal) {
   Planner planner(grid, car, 4.0, 1.0);  // pathLength, step_car defaults of the node parameters
@@ -36,7 +46,10 @@ static int drive(Grid_map &grid, const CarData &car, const State &start, const S
   g.gridx = gx;
   g.gridy = gy;
   auto goal_node = std::make_shared<planner::Node>(g, std::vector<State>{g}, 0.0, 0.0, 1, std::weak_ptr<planner::Node>());
-  const std::vector<double> h = planner.holonomicCostsWithObstacles_planning(goal_node);
+  // the reference's method name with the reference's return type of the package: vector<double> (RS) or one
+  // HolonomicNode per cell (Dubins)
+  const auto hres = planner.holonomicCostsWithObstacles_planning(goal_node);
+  const std::vector<double> h = costs_of(hres);
   double sum = 0;
   std::size_t finite = 0;
   for (double v : h)
@@ -55,7 +68,35 @@ static int drive(Grid_map &grid, const CarData &car, const State &start, const S
   const auto shot = planner.analyticShot(start_node, goal_node);
   if (shot) std::printf("shot 1 %.17g %zu\n", shot->Cost_path, shot->Trajectory.size());
   else std::printf("shot 0\n");
+  // motionCommands / PathCost (RS/include/HybridAstar.h:51-53): every command's cost from the start node
+  planner.motionCommands();
+  std::printf("commands %zu\n", planner.commands().size());
+  for (const auto &cmd : planner.commands())
+    std::printf("%.17g %.0f %.17g\n", cmd[0], cmd[1], planner.PathCost(start_node, cmd));
   return 0;
+}
+
+// the analytic path classes of the public interface (RS/include/reeds_shepp_path.h, DB/include/dubins_path.h)
+static void drive_paths(const State &start, const State &goal) {
+  const double maxc = std::tan(0.6) / 2.75;
+  reeds_shepp_path rs;
+  const std::vector<PATH> all = rs.calc_all_paths(start.x, start.y, start.heading, goal.x, goal.y, goal.heading, maxc, 1.0);
+  std::printf("rs_paths %zu\n", all.size());
+  for (const PATH &p : all) {
+    std::string t;
+    for (const auto &c : p.ctypes) t += c;
+    double sx = 0, sy = 0;
+    long sd = 0;
+    for (std::size_t i = 0; i < p.x.size(); i++) sx += p.x[i], sy += p.y[i], sd += p.directions[i];
+    std::printf("%s %.17g %zu %.17g %.17g %ld\n", t.c_str(), p.L, p.x.size(), sx, sy, sd);
+  }
+  const PATH best = rs.calc_optimal_path(start.x, start.y, start.heading, goal.x, goal.y, goal.heading, maxc, 1.0);
+  std::printf("rs_optimal %.17g %zu\n", best.L, best.x.size());
+  dubins_path db;
+  const Path d = db.calc_dubins_path(start.x, start.y, start.heading, goal.x, goal.y, goal.heading, maxc, 0.1);
+  std::string m;
+  for (const auto &c : d.mode) m += c;
+  std::printf("dubins %s %.17g %zu %.17g\n", m.c_str(), d.length, d.x.size(), db.mod2pi(-1.0));
 }
 
 int main(int argc, char **argv) {
@@ -81,7 +122,9 @@ int main(int argc, char **argv) {
     long occupied = 0;
     for (int8_t v : infl) occupied += v > 0;
     std::printf("inflated %ld\n", occupied);
-    return variant == 0 ? drive<HybridAstar>(grid, car, start, goal) : drive<HybridAstarDubins>(grid, car, start, goal);
+    const int rc = variant == 0 ? drive<HybridAstar>(grid, car, start, goal) : drive<HybridAstarDubins>(grid, car, start, goal);
+    drive_paths(start, goal);
+    return rc;
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -1,6 +1,7 @@
 // shells.cpp -- bodies of the host shells (GridMapShell.h, HybridAstarShell.h): marshalling only, every computation
 // is a C-ABI call into libhpp_b200.so.  Errors of the library become std::runtime_error (the reference's own
 // conventions -- nullptr shot, 1-state failure path -- are kept as return values).
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -210,7 +211,48 @@ std::shared_ptr<planner::Node> HybridAstarT<V>::analyticShot(const std::shared_p
 }
 
 template <int V>
-std::vector<double> HybridAstarT<V>::holonomicCostsWithObstacles_planning(const std::shared_ptr<planner::Node> &goal) {
+void HybridAstarT<V>::motionCommands() {
+  // one expansion of a free-standing node returns every command's {steering angle, direction} in command order
+  hpp_node in;
+  std::memset(&in, 0, sizeof in);
+  in.direction = 1;
+  const hpp_params p = car_data_.params(simulationLength, step_car);
+  const int nc = hpp_num_commands(&p, V);
+  std::vector<hpp_child> kids((std::size_t)nc);
+  check(grid_map_.ctx(), hpp_expand(grid_map_.handle(), V, &in, 1, kids.data()), "hpp_expand");
+  motionCommand.clear();
+  for (const hpp_child &k : kids) motionCommand.push_back({k.steer, (double)k.direction});
+}
+
+template <int V>
+double HybridAstarT<V>::PathCost(const std::shared_ptr<planner::Node> &cur, const std::vector<double> &cmd) {
+  if (cmd.size() < 2) throw std::runtime_error("PathCost: a motion command is {steering angle, direction}");
+  hpp_node in;
+  std::memset(&in, 0, sizeof in);
+  in.x = cur->Current_state.x;
+  in.y = cur->Current_state.y;
+  in.heading = cur->Current_state.heading;
+  in.cost = cur->Cost_path;
+  in.steer = cur->steeringAngle;
+  in.direction = cur->direction;
+  const hpp_params p = car_data_.params(simulationLength, step_car);
+  const int nc = hpp_num_commands(&p, V);
+  std::vector<hpp_child> kids((std::size_t)nc);
+  check(grid_map_.ctx(), hpp_expand(grid_map_.handle(), V, &in, 1, kids.data()), "hpp_expand");
+  for (const hpp_child &k : kids)  // the cost is filled for every command, colliding rollouts included
+    if (k.steer == cmd[0] && (double)k.direction == cmd[1]) return k.cost;
+  throw std::runtime_error("PathCost: not one of the planner's motion commands");
+}
+
+template <int V>
+typename HybridAstarT<V>::HeuristicResult HybridAstarT<V>::holonomicCostsWithObstacles_planning(
+    const std::shared_ptr<planner::Node> &goal) {
+  if constexpr (V == HPP_VARIANT_RS) return holonomicCosts(goal);
+  else return holonomicCostsWithObstacles_nodes(goal);
+}
+
+template <int V>
+std::vector<double> HybridAstarT<V>::holonomicCosts(const std::shared_ptr<planner::Node> &goal) {
   const State gs = withCell(goal->Current_state);
   std::vector<double> cost((std::size_t)grid_map_.getWidth() * grid_map_.getHeight());
   const hpp_status st =
@@ -225,7 +267,7 @@ std::vector<double> HybridAstarT<V>::holonomicCostsWithObstacles_planning(const 
 template <int V>
 std::vector<std::shared_ptr<planner::HolonomicNode>> HybridAstarT<V>::holonomicCostsWithObstacles_nodes(
     const std::shared_ptr<planner::Node> &goal) {
-  const std::vector<double> cost = holonomicCostsWithObstacles_planning(goal);
+  const std::vector<double> cost = holonomicCosts(goal);
   std::vector<std::shared_ptr<planner::HolonomicNode>> out(cost.size());
   const int W = (int)grid_map_.getWidth();
   for (std::size_t i = 0; i < cost.size(); i++) {
@@ -239,6 +281,104 @@ std::vector<std::shared_ptr<planner::HolonomicNode>> HybridAstarT<V>::holonomicC
 
 template class HybridAstarT<HPP_VARIANT_RS>;
 template class HybridAstarT<HPP_VARIANT_DUBINS>;
+
+// ---------------------------------------------------------------------------------------------- analytic path classes
+static double wrap_pi(double theta) {  // RS/src/reeds_shepp_path.cpp pi_2_pi / DB/src/dubins_path.cpp pi_2_pi
+  while (theta > M_PI) theta -= 2.0 * M_PI;
+  while (theta < -M_PI) theta += 2.0 * M_PI;
+  return theta;
+}
+double reeds_shepp_path::pi_2_pi(double theta) { return wrap_pi(theta); }
+double dubins_path::pi_2_pi(double theta) { return wrap_pi(theta); }
+double dubins_path::mod2pi(double theta) { return theta - 2.0 * M_PI * std::floor(theta / M_PI / 2.0); }  // DB :26-29
+
+std::vector<PATH> reeds_shepp_path::calc_all_paths(double sx, double sy, double syaw, double gx, double gy, double gyaw,
+                                                   double maxc, double step_size) {
+  hpp_ctx *ctx = hpp_host::thread_ctx();
+  const double s[3] = {sx, sy, syaw}, g[3] = {gx, gy, gyaw};
+  const int max_paths = 48;
+  int32_t n_paths = 0, n_seg[48], n_samples[48];
+  double lengths[48 * 5], total[48];
+  char types[48 * 5];
+  std::vector<double> samples;
+  std::vector<int32_t> dirs;
+  std::size_t cap = 1 << 16;
+  for (;;) {
+    samples.resize(cap * 3);
+    dirs.resize(cap);
+    const hpp_status st = hpp_rs_all_paths(ctx, s, g, maxc, step_size, max_paths, &n_paths, n_seg, lengths, types, total,
+                                           n_samples, samples.data(), cap, dirs.data());
+    if (st == HPP_ERR_CAPACITY && cap < ((std::size_t)1 << 26)) {
+      cap *= 4;
+      continue;
+    }
+    check(ctx, st, "hpp_rs_all_paths");
+    break;
+  }
+  std::vector<PATH> out;
+  std::size_t off = 0;
+  for (int e = 0; e < n_paths; e++) {
+    PATH p;
+    for (int i = 0; i < n_seg[e]; i++) {
+      p.lengths.push_back(lengths[e * 5 + i]);
+      p.ctypes.push_back(std::string(1, types[e * 5 + i]));
+    }
+    p.L = total[e];
+    for (int j = 0; j < n_samples[e]; j++) {
+      p.x.push_back(samples[3 * (off + j)]);
+      p.y.push_back(samples[3 * (off + j) + 1]);
+      p.yaw.push_back(samples[3 * (off + j) + 2]);
+      p.directions.push_back(dirs[off + j]);
+    }
+    off += (std::size_t)n_samples[e];
+    out.push_back(std::move(p));
+  }
+  return out;
+}
+
+PATH reeds_shepp_path::calc_optimal_path(double sx, double sy, double syaw, double gx, double gy, double gyaw, double maxc,
+                                         double step_size) {
+  std::vector<PATH> paths = calc_all_paths(sx, sy, syaw, gx, gy, gyaw, maxc, step_size);
+  if (paths.empty()) throw std::runtime_error("calc_optimal_path: no path (the reference indexes paths[0] here)");
+  std::size_t mini = 0;  // RS/src/reeds_shepp_path.cpp:24-35: `<=`, so the last one among equals
+  double minL = paths[0].L;
+  for (std::size_t i = 0; i < paths.size(); ++i)
+    if (paths[i].L <= minL) {
+      minL = paths[i].L;
+      mini = i;
+    }
+  return paths[mini];
+}
+
+Path dubins_path::calc_dubins_path(double sx, double sy, double syaw, double gx, double gy, double gyaw, double curv,
+                                   double step_size) {
+  hpp_ctx *ctx = hpp_host::thread_ctx();
+  const double s[3] = {sx, sy, syaw}, g[3] = {gx, gy, gyaw};
+  double length = 0;
+  char mode[4] = {0, 0, 0, 0};
+  int32_t n = 0;
+  std::vector<double> samples;
+  std::size_t cap = 1 << 14;
+  for (;;) {
+    samples.resize(cap * 3);
+    const hpp_status st = hpp_dubins_path(ctx, s, g, curv, step_size, &length, mode, &n, samples.data(), cap);
+    if (st == HPP_ERR_CAPACITY && cap < ((std::size_t)1 << 26)) {
+      cap *= 4;
+      continue;
+    }
+    check(ctx, st, "hpp_dubins_path");
+    break;
+  }
+  Path p;
+  p.length = length;
+  for (int i = 0; i < 3 && mode[i]; i++) p.mode.push_back(std::string(1, mode[i]));
+  for (int j = 0; j < n; j++) {
+    p.x.push_back(samples[3 * j]);
+    p.y.push_back(samples[3 * j + 1]);
+    p.yaw.push_back(samples[3 * j + 2]);
+  }
+  return p;
+}
 
 // ---------------------------------------------------------------------------------------------- map_inflate
 std::vector<int8_t> InflateOccupancy(const std::vector<int8_t> &occ, uint32_t width, uint32_t height, double resolution,

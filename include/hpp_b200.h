@@ -219,7 +219,8 @@ hpp_status hpp_dubins_shot(hpp_map *map, const hpp_node *starts, size_t n, const
 hpp_status hpp_rs_all_paths(hpp_ctx *ctx, const double start_xyh[3], const double goal_xyh[3], double maxc,
                             double step_size, int32_t max_paths, int32_t *n_paths, int32_t *n_seg,
                             double *lengths, char *types, double *total_len, int32_t *n_samples,
-                            double *samples_xyyaw, size_t samples_cap);
+                            double *samples_xyyaw, size_t samples_cap,
+                            int32_t *directions /* may be NULL: PATH::directions, one per sample (+1 / -1) */);
 /* idem for dubins_path::calc_dubins_path (a11): best word + samples */
 hpp_status hpp_dubins_path(hpp_ctx *ctx, const double start_xyh[3], const double goal_xyh[3], double curv,
                            double step_size, double *length, char mode[3], int32_t *n_samples,
@@ -260,6 +261,20 @@ hpp_status hpp_plan_batch(hpp_map *map, int variant, const double *starts_xyh, c
 hpp_status hpp_plan_batch_multi(hpp_map *const *maps, size_t n_maps, const uint32_t *map_of_query /* n */, int variant,
                                 const double *starts_xyh, const double *goals_xyh, size_t n, hpp_plan *plans,
                                 double *traj /* cap x 5 */, size_t traj_cap, size_t *traj_used);
+
+/* ---------------------------------------------------------------- the OpenCV calls of map_inflate_node::InflateMap
+ * MI/src/map_inflate_node.cpp:115-139 works on a gray cv::Mat: cv::threshold(0, 255, THRESH_BINARY | THRESH_OTSU) (:127),
+ * cv::bitwise_not (:131), cv::dilate with getStructuringElement(MORPH_ELLIPSE, (2r+1)^2, (r,r)) (:134-135),
+ * cv::bitwise_not (:138).  These two entry points replace the two image operations; the header
+ * hybrid_path_planning_b200/host/dropin/mi/opencv2/opencv.hpp maps the node's cv:: calls onto them, so the node source
+ * compiles and runs unmodified.  8-bit single-channel images, row-major, host buffers. */
+hpp_status hpp_cv_threshold_otsu(hpp_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, uint8_t *dst /* 0 | 255 */,
+                                 double *threshold_out /* may be NULL: the Otsu threshold, cv::threshold's return value */);
+/* src is a binary image (0 / non-zero, what cv::threshold returns); set pixels of dst are 255.  r = element radius.
+ * src_complemented != 0: the bytes of src are the COMPLEMENT of the image to dilate (the cv::bitwise_not in front of
+ * the dilation folded into the call: 255 = unset pixel). */
+hpp_status hpp_cv_dilate_ellipse(hpp_ctx *ctx, const uint8_t *src, uint32_t W, uint32_t H, int32_t r,
+                                 int32_t src_complemented, uint8_t *dst);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU, NCCL over NVLink)
  * only independent units are partitioned -- batches of queries, pose batches, and row bands of a large

@@ -70,6 +70,7 @@ def _cmp_paths(got, want):
         np.testing.assert_allclose(a["x"], b["x"], rtol=0, atol=TOL)
         np.testing.assert_allclose(a["y"], b["y"], rtol=0, atol=TOL)
         np.testing.assert_allclose(a["yaw"], b["yaw"], rtol=0, atol=TOL)
+        assert np.array_equal(a["dir"], b["dir"])          # PATH::directions
 
 
 def test_rs_all_paths_matches_oracle(ctx):

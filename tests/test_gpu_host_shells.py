@@ -66,3 +66,32 @@ def test_host_shells_against_oracle(tmp_path, variant):
     assert int(f[1]) == int(shot["found"])
     if shot["found"]:
         assert float(f[2]) == pytest.approx(shot["cost"], rel=1e-9) and int(f[3]) == len(shot["traj"])
+    i += 1
+    # motionCommands / PathCost: the reference's own GetnextNeighbours cost for every command (colliding ones included:
+    # the oracle's expansion carries the cost of every command)
+    every = O.expand(om, variant, start, 0.0, 0.0, 1)
+    steer, direction = O.motion_commands(variant)
+    assert out[i] == f"commands {len(steer)}"
+    rows = np.array([[float(v) for v in ln.split()] for ln in out[i + 1:i + 1 + len(steer)]])
+    i += 1 + len(steer)
+    assert np.array_equal(rows[:, 0], steer) and np.array_equal(rows[:, 1], direction)
+    for r, k in zip(rows, every):
+        assert r[2] == pytest.approx(k["cost"], rel=1e-12)
+    # reeds_shepp_path / dubins_path class shells
+    maxc = np.tan(0.6) / 2.75
+    want_all = O.rs_all_paths(start, goal, maxc, 1.0)
+    assert out[i] == f"rs_paths {len(want_all)}"
+    for ln, w in zip(out[i + 1:i + 1 + len(want_all)], want_all):
+        f = ln.split()
+        assert f[0] == w["types"] and float(f[1]) == pytest.approx(w["L"], abs=1e-9) and int(f[2]) == len(w["x"])
+        assert float(f[3]) == pytest.approx(w["x"].sum(), abs=1e-7) and float(f[4]) == pytest.approx(w["y"].sum(), abs=1e-7)
+        assert int(f[5]) == int(w["dir"].sum())
+    i += 1 + len(want_all)
+    best = min(reversed(want_all), key=lambda w: w["L"])       # `<=` in the reference: the last among equals
+    f = out[i].split()
+    assert f[0] == "rs_optimal" and float(f[1]) == pytest.approx(best["L"], abs=1e-9) and int(f[2]) == len(best["x"])
+    i += 1
+    d = O.dubins_path(start, goal, maxc, 0.1)
+    f = out[i].split()
+    assert f[0] == "dubins" and f[1] == d["mode"] and float(f[2]) == pytest.approx(d["length"], abs=1e-9)
+    assert int(f[3]) == len(d["x"]) and float(f[4]) == pytest.approx(-1.0 + 2 * np.pi, abs=1e-15)
