@@ -98,6 +98,8 @@ def lib():
             "hpp_collide_circles_dev": [vp, vp, sz, vp],
             "hpp_collide_sat": [vp, vp, sz, vp],
             "hpp_collide_sat_dev": [vp, vp, sz, vp],
+            "hpp_collide_improved": [vp, vp, sz, vp],
+            "hpp_collide_improved_dev": [vp, vp, sz, vp],
             "hpp_heuristic_rs": [vp, i32, i32, i32, i32, vp, C.POINTER(QuirkReport)],
             "hpp_heuristic_dubins": [vp, i32, i32, vp, C.POINTER(QuirkReport)],
             "hpp_heuristic_batch_dev": [vp, C.c_int, vp, sz, vp, vp],
@@ -338,6 +340,13 @@ class Map:
         v = np.empty(len(xyh), np.uint8)
         self.ctx.check(self.L.hpp_collide_sat(self.h, xyh.ctypes.data, len(xyh), v.ctypes.data))
         return v
+
+    def collide_improved(self, xyh):
+        """Grid_map::isSingleStateCollisionFreeImproved, with the reference's own return convention (see the header)"""
+        xyh = np.ascontiguousarray(xyh, np.float64).reshape(-1, 3)
+        out = np.empty(len(xyh), np.uint8)
+        self.ctx.check(self.L.hpp_collide_improved(self.h, xyh.ctypes.data, len(xyh), out.ctypes.data))
+        return out
 
     def collide_circles_dev(self, xyh_dev, n, verdict_dev):
         self.ctx.check(self.L.hpp_collide_circles_dev(self.h, _ptr(xyh_dev), n, _ptr(verdict_dev)))

@@ -5,6 +5,9 @@
 //     3 doubles (24 B), the verdict streams out as 1 byte; the up-to-16 float taps are gathers into the
 //     distance layer served by L2/HBM.  Algorithmic bytes: 24 + 1 + 4*4*4 = 89 B per pose.
 // K5: one warp per pose (window rows across lanes, bit-packed occupancy), 8 poses per CTA.
+#include <math.h>
+#include <stdlib.h>
+
 #include "collide.cuh"
 
 __global__ void __launch_bounds__(256) collide_circles_kernel(hpp_geom g, circ_consts cc,
@@ -15,6 +18,60 @@ __global__ void __launch_bounds__(256) collide_circles_kernel(hpp_geom g, circ_c
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const double x = xyh[3 * i], y = xyh[3 * i + 1], h = xyh[3 * i + 2];
     verdict[i] = (uint8_t)circles_collide(g, cc, dist, x, y, h);
+  }
+}
+
+// K4 over the compact layer: the same verdicts from a quarter of the bytes (the 8192^2 layer is 67 MB and stays in L2;
+// a 2x2 tap window costs 1.4 sectors on average instead of 2.25)
+__global__ void __launch_bounds__(256) collide_circles_u8_kernel(hpp_geom g, circ_consts cc,
+                                                                 const uint8_t *__restrict__ d2, int tiles_x,
+                                                                 const double *__restrict__ xyh, size_t n,
+                                                                 uint8_t *__restrict__ verdict) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fmul_rn(__fsqrt_rn((float)threadIdx.x), g.res_f);  // what edt_col_kernel stores for d2 = v
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double x = xyh[3 * i], y = xyh[3 * i + 1], h = xyh[3 * i + 2];
+    double s, c;
+    sincos(h, &s, &c);
+    int hit = 0;
+#pragma unroll
+    for (int k = 0; k < 4 && !hit; k++) {
+      const double px = cc.cx[k] * c - cc.cy[k] * s + x;
+      const double py = cc.cx[k] * s + cc.cy[k] * c + y;
+      hit = circle_hits_u8(g, d2, tiles_x, lut, px, py, cc.cr);
+    }
+    verdict[i] = (uint8_t)hit;
+  }
+}
+
+// Grid_map::isSingleStateCollisionFreeImproved (RS/src/Grid_map.cpp:286-317), statement by statement, including its
+// return convention (which is NOT the one of isSingleStateCollisionFree: `true` when the bounding circle is clear,
+// `false` when its centre is outside the map, and the detailed check's "true = collision" in between)
+__global__ void __launch_bounds__(256) collide_improved_kernel(hpp_geom g, circ_consts cc, bound_consts bc,
+                                                               const float *__restrict__ dist,
+                                                               const double *__restrict__ xyh, size_t n,
+                                                               uint8_t *__restrict__ result) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double x = xyh[3 * i], y = xyh[3 * i + 1], h = xyh[3 * i + 2];
+    // CarData::getBoundingCircle -> local2Global(state, (bx, 0))  (RS/src/CarData.cpp:112-124)
+    double sn, cs;
+    sincos(h, &sn, &cs);
+    const double bpx = bc.bx * cs - 0.0 * sn + x;
+    const double bpy = bc.bx * sn + 0.0 * cs + y;
+    circle_taps t;
+    circle_prep(g, bpx, bpy, t);
+    int r;
+    if (t.mode == 0) {
+      r = 0;                                               // :313-316 out of bounds -> false
+    } else if (circle_hits(g, dist, bpx, bpy, bc.br)) {    // :301 clearance < bounding radius
+      r = circles_collide(g, cc, dist, x, y, h);           // :304 detailed check (true = collision)
+    } else {
+      r = 1;                                               // :309 -> true
+    }
+    result[i] = (uint8_t)r;
   }
 }
 
@@ -61,7 +118,30 @@ extern "C" hpp_status hpp_collide_circles_dev(hpp_map *m, const double *xyh_dev,
   // grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
   long long want = hpp_div_up((long long)n, 256);
   int grid = (int)(want < (long long)c->sm_count * 8 ? want : (long long)c->sm_count * 8);
-  collide_circles_kernel<<<grid, 256, 0, c->stream>>>(m->g, make_cc(m), m->d_distance, xyh_dev, n, verdict_dev);
+  // compact layer whenever the circle radius is safely below the clamp distance (see circle_hits_u8); HPP_K4_FLOAT=1
+  // forces the float layer (same verdicts, for comparison)
+  static const bool force_float = getenv("HPP_K4_FLOAT") != nullptr;
+  if (!force_float && m->car.cr < 14.0 * m->g.res)
+    collide_circles_u8_kernel<<<grid, 256, 0, c->stream>>>(m->g, make_cc(m), m->d_d2u8, m->d2_tiles_x, xyh_dev, n,
+                                                           verdict_dev);
+  else
+    collide_circles_kernel<<<grid, 256, 0, c->stream>>>(m->g, make_cc(m), m->d_distance, xyh_dev, n, verdict_dev);
+  HPP_LAUNCHED(c);
+  return HPP_OK;
+}
+
+extern "C" hpp_status hpp_collide_improved_dev(hpp_map *m, const double *xyh_dev, size_t n, uint8_t *result_dev) {
+  if (!m || (n && (!xyh_dev || !result_dev))) return HPP_ERR_ARG;
+  if (n == 0) return HPP_OK;
+  hpp_ctx *c = m->ctx;
+  HPP_CUDA(c, cudaSetDevice(c->device));
+  long long want = hpp_div_up((long long)n, 256);
+  int grid = (int)(want < (long long)c->sm_count * 8 ? want : (long long)c->sm_count * 8);
+  bound_consts bc;
+  const hpp_params &p = m->car.p;
+  bc.bx = (p.axle_to_front - p.axle_to_back) / 2.0;                                        // RS/src/CarData.cpp:79
+  bc.br = sqrt(pow((p.axle_to_front + p.axle_to_back) / 2.0, 2) + pow(p.width / 2.0, 2));  // :81
+  collide_improved_kernel<<<grid, 256, 0, c->stream>>>(m->g, make_cc(m), bc, m->d_distance, xyh_dev, n, result_dev);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
@@ -110,4 +190,7 @@ extern "C" hpp_status hpp_collide_circles(hpp_map *m, const double *xyh, size_t 
 }
 extern "C" hpp_status hpp_collide_sat(hpp_map *m, const double *xyh, size_t n, uint8_t *verdict) {
   return collide_host(m, xyh, n, verdict, hpp_collide_sat_dev);
+}
+extern "C" hpp_status hpp_collide_improved(hpp_map *m, const double *xyh, size_t n, uint8_t *result) {
+  return collide_host(m, xyh, n, result, hpp_collide_improved_dev);
 }

@@ -15,6 +15,10 @@
 struct circ_consts {
   double cx[4], cy[4], cr;
 };
+// CarData::setCircles' bounding circle (RS/src/CarData.cpp:78-81), for isSingleStateCollisionFreeImproved
+struct bound_consts {
+  double bx, br;
+};
 
 // grid_map::getIndexFromPosition: ((p - 0.5*len) - pos) / res, truncated after negation
 __device__ __forceinline__ void gm_index(const hpp_geom &g, double px, double py, int &i, int &j) {
@@ -37,6 +41,7 @@ struct circle_taps {
   int mode;           // 0 = outside the map (collision), 1 = INTER_NEAREST fallback (tap l[0]), 2 = bilinear
   long l[4];
   double rx, ry;
+  int ia, ib, ja, jb; // cell indices of the taps: l[0] = (ia, ja), l[1] = (ib, ja), l[2] = (ia, jb), l[3] = (ib, jb)
 };
 
 __device__ __forceinline__ void circle_prep(const hpp_geom &g, double px, double py, circle_taps &t) {
@@ -46,6 +51,7 @@ __device__ __forceinline__ void circle_prep(const hpp_geom &g, double px, double
   t.mode = 0;
   t.l[0] = t.l[1] = t.l[2] = t.l[3] = 0;
   t.rx = t.ry = 0.0;
+  t.ia = t.ib = t.ja = t.jb = 0;
   if (!(tx >= 0.0 && ty >= 0.0 && tx < g.lenx && ty < g.leny)) return;
   // atPositionLinearInterpolated
   int i0, j0;
@@ -63,9 +69,12 @@ __device__ __forceinline__ void circle_prep(const hpp_geom &g, double px, double
   if (l0 < 0 || l0 >= nn || l1 < 0 || l1 >= nn || l2 < 0 || l2 >= nn || l3 < 0 || l3 >= nn) {
     t.mode = 1;  // INTER_NEAREST fallback
     t.l[0] = t.l[1] = t.l[2] = t.l[3] = (long)j0 * W + i0;
+    t.ia = t.ib = i0;
+    t.ja = t.jb = j0;
   } else {
     t.mode = 2;
     t.l[0] = l0; t.l[1] = l1; t.l[2] = l2; t.l[3] = l3;
+    t.ia = ia; t.ib = ib; t.ja = ja; t.jb = jb;
     double bx = cx, by = cy;
     gm_position(g, ia, ja, bx, by);
     t.rx = hpp_div_res(g, px - bx);
@@ -95,6 +104,40 @@ __device__ __forceinline__ int circle_hits(const hpp_geom &g, const float *__res
     f1 = __ldg(dist + t.l[1]);
     f2 = __ldg(dist + t.l[2]);
     f3 = __ldg(dist + t.l[3]);
+  }
+  return circle_finish(t, f0, f1, f2, f3, r);
+}
+
+// The same circle over the COMPACT layer (hpp_map::d_d2u8: squared cell distance clamped to 255, one byte per cell in
+// 8 x 4 micro-tiles; lut[v] = sqrtf((float)v) * res_f, the float the distance layer holds for that cell).
+// Why the clamp cannot change a verdict: the Euclidean distance transform is 1-Lipschitz, and the four taps lie within
+// sqrt(2) cells of each other.  If a tap is clamped (true distance >= sqrt(255) = 15.97 cells) every tap -- clamped or
+// not -- is at least 14.55 cells, so the interpolated clearance is at least 14.55 * res either way, and the caller only
+// uses this path for circle radii below 14 cells: "no collision" with and without the clamp.  If no tap is clamped the
+// values are the layer's, bit for bit.
+__device__ __forceinline__ int circle_hits_u8(const hpp_geom &g, const uint8_t *__restrict__ d2, int tiles_x,
+                                              const float *lut, double px, double py, double r) {
+  circle_taps t;
+  circle_prep(g, px, py, t);
+  if (t.mode == 0) return 1;
+  size_t a0, a1, a2, a3;
+  if ((unsigned)t.ia < (unsigned)g.W && (unsigned)t.ib < (unsigned)g.W) {  // then ja, jb are rows of the map too
+    a0 = hpp_d2_addr(t.ia, t.ja, tiles_x);
+    a1 = hpp_d2_addr(t.ib, t.ja, tiles_x);
+    a2 = hpp_d2_addr(t.ia, t.jb, tiles_x);
+    a3 = hpp_d2_addr(t.ib, t.jb, tiles_x);
+  } else {  // grid_map's linear index aliases a column index of -1 / W into the neighbouring row: follow it
+    a0 = hpp_d2_addr((int)(t.l[0] % g.W), (int)(t.l[0] / g.W), tiles_x);
+    a1 = hpp_d2_addr((int)(t.l[1] % g.W), (int)(t.l[1] / g.W), tiles_x);
+    a2 = hpp_d2_addr((int)(t.l[2] % g.W), (int)(t.l[2] / g.W), tiles_x);
+    a3 = hpp_d2_addr((int)(t.l[3] % g.W), (int)(t.l[3] / g.W), tiles_x);
+  }
+  const float f0 = lut[__ldg(d2 + a0)];
+  float f1 = f0, f2 = f0, f3 = f0;
+  if (t.mode == 2) {
+    f1 = lut[__ldg(d2 + a1)];
+    f2 = lut[__ldg(d2 + a2)];
+    f3 = lut[__ldg(d2 + a3)];
   }
   return circle_finish(t, f0, f1, f2, f3, r);
 }

@@ -145,7 +145,8 @@ struct edt_band {
 template <bool BAND>
 __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict__ g, int W, int H, float res_f,
                                                       float *__restrict__ distance,
-                                                      const uint32_t *__restrict__ any_obstacle, edt_band bd) {
+                                                      const uint32_t *__restrict__ any_obstacle, edt_band bd,
+                                                      uint8_t *__restrict__ d2u8, int d2_tiles_x) {
   __shared__ __align__(16) uint16_t gs[EDT_TY + 2 * EDT_R][EDT_TX];
   const int x0 = blockIdx.x * EDT_TX, y0 = (BAND ? bd.y_begin : 0) + blockIdx.y * EDT_TY;
   const int y_end = BAND ? bd.y_begin + bd.y_count : H;
@@ -210,6 +211,8 @@ __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict
       distance[(size_t)(y - bd.y_begin) * W + x] = __fmul_rn(d, res_f);
     } else {
       distance[n - 1 - ((size_t)y * W + x)] = __fmul_rn(d, res_f);
+      // compact copy for K4: squared cell distance clamped to 255, at the same (flipped) cell (i, j) = (W-1-x, H-1-y)
+      if (d2u8) d2u8[hpp_d2_addr(W - 1 - x, H - 1 - y, d2_tiles_x)] = (uint8_t)min(best, 255u);
     }
   }
   if (BAND && open_result) *bd.unresolved = 1u;
@@ -249,7 +252,8 @@ hpp_status hpp_edt_build(hpp_map *m) {
   dim3 grid(hpp_div_up(W, EDT_TX), hpp_div_up(H, EDT_TY));
   edt_band none;
   memset(&none, 0, sizeof none);
-  edt_col_kernel<false><<<grid, 256, 0, c->stream>>>(m->d_g, W, H, m->g.res_f, m->d_distance, c->d_flags + 40, none);
+  edt_col_kernel<false><<<grid, 256, 0, c->stream>>>(m->d_g, W, H, m->g.res_f, m->d_distance, c->d_flags + 40, none,
+                                                     m->d_d2u8, m->d2_tiles_x);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
@@ -278,7 +282,8 @@ hpp_status hpp_edt_band_cols(hpp_ctx *c, const uint16_t *g_ext, int W, int rows_
   bd.more_below = more_below;
   bd.unresolved = unresolved;
   dim3 grid(hpp_div_up(W, EDT_TX), hpp_div_up(y_count, EDT_TY));
-  edt_col_kernel<true><<<grid, 256, 0, c->stream>>>(g_ext, W, rows_ext, res_f, distance_band, c->d_flags + 40, bd);
+  edt_col_kernel<true><<<grid, 256, 0, c->stream>>>(g_ext, W, rows_ext, res_f, distance_band, c->d_flags + 40, bd,
+                                                    nullptr, 0);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }

@@ -72,7 +72,18 @@ struct hpp_map {
   uint16_t *d_g;        // pass-1 row distances of the EDT (scratch, kept for reuse)
   float *d_obstacle;    // [x + y*W]
   float *d_distance;    // [x + y*W] (already flipped: distance[k] = edt[n-1-k]*res)
+  // compact copy of the distance layer for the footprint check (K4): the squared cell distance clamped to 255, one byte
+  // per cell, in micro-tiles of 8 (i) x 4 (j) cells = one 32-byte sector, same (flipped) cell order as d_distance.
+  // distance == sqrtf((float)d2) * res_f exactly for d2 < 255; see collide.cu for why the clamp keeps the verdicts.
+  uint8_t *d_d2u8;
+  int d2_tiles_x;       // micro-tiles per row: ceil(W / 8)
 };
+
+#define HPP_D2_TILE_W 8
+#define HPP_D2_TILE_H 4
+static inline __host__ __device__ size_t hpp_d2_addr(int i, int j, int tiles_x) {
+  return ((size_t)(j >> 2) * (size_t)tiles_x + (size_t)(i >> 3)) * 32u + (size_t)(((j & 3) << 3) + (i & 7));
+}
 
 #define HPP_CUDA(ctx, call)                                                                       \
   do {                                                                                            \

@@ -289,6 +289,8 @@ static hpp_status map_alloc(hpp_ctx *c, uint32_t W, uint32_t H, float resolution
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_g, m->n * sizeof(uint16_t));
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_obstacle, m->n * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_distance, m->n * sizeof(float));
+  m->d2_tiles_x = hpp_div_up(W, HPP_D2_TILE_W);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_d2u8, (size_t)m->d2_tiles_x * hpp_div_up(H, HPP_D2_TILE_H) * 32);
   if (e != cudaSuccess) {
     snprintf(c->err, sizeof(c->err), "map allocation failed: %s", cudaGetErrorString(e));
     hpp_map_destroy(m);
@@ -367,6 +369,7 @@ extern "C" hpp_status hpp_map_destroy(hpp_map *m) {
   cudaFree(m->d_g);
   cudaFree(m->d_obstacle);
   cudaFree(m->d_distance);
+  cudaFree(m->d_d2u8);
   free(m);
   return HPP_OK;
 }

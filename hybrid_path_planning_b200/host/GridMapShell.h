@@ -58,6 +58,8 @@ class Grid_map {
   void setPlannerParams(const CarData &car_data, double pathLength, double step_car);
   // RS/src/Grid_map.cpp:239-284: true = collision or outside the map (hazard H5: the name says the opposite)
   bool isSingleStateCollisionFree(const State &current);
+  // RS/src/Grid_map.cpp:286-317 (bounding-circle pre-filter; the reference's own, different, return convention)
+  bool isSingleStateCollisionFreeImproved(const State &current);
   // DB/src/Grid_map.cpp:50-95 (the polygon argument is recomputed from the state on the device: it is a pure function
   // of the state and the car, DB/src/CarData.cpp:39-59)
   template <class Polygon>

@@ -71,6 +71,13 @@ bool Grid_map::isSingleStateCollisionFree(const State &s) {
   return v != 0;
 }
 
+bool Grid_map::isSingleStateCollisionFreeImproved(const State &s) {
+  const double xyh[3] = {s.x, s.y, s.heading};
+  uint8_t v = 0;
+  check(h_->ctx, hpp_collide_improved(h_->map, xyh, 1, &v), "hpp_collide_improved");
+  return v != 0;
+}
+
 bool Grid_map::checkCollisionSat(const State &s) {
   const double xyh[3] = {s.x, s.y, s.heading};
   uint8_t v = 1;

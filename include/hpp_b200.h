@@ -129,6 +129,14 @@ hpp_status hpp_collide_circles(hpp_map *map, const double *xyh, size_t n, uint8_
 hpp_status hpp_collide_circles_dev(hpp_map *map, const double *xyh_dev, size_t n, uint8_t *verdict_dev);
 hpp_status hpp_collide_sat(hpp_map *map, const double *xyh, size_t n, uint8_t *verdict);
 hpp_status hpp_collide_sat_dev(hpp_map *map, const double *xyh_dev, size_t n, uint8_t *verdict_dev);
+/* Grid_map::isSingleStateCollisionFreeImproved (RS/include/Grid_map.h:103, RS/src/Grid_map.cpp:286-317): the bounding
+ * circle of CarData::getBoundingCircle (RS/src/CarData.cpp:78-81, :112-116) as a pre-filter of the four-circle check.
+ * result[i] is the method's return value AS THE REFERENCE RETURNS IT, which is not the convention of
+ * isSingleStateCollisionFree: 1 when the bounding circle is clear of obstacles, 0 when its centre lies outside the map,
+ * and isSingleStateCollisionFree's value (1 = collision) when the bounding circle touches an obstacle.  The reference
+ * never calls the method; it is provided so that code written against the class finds it. */
+hpp_status hpp_collide_improved(hpp_map *map, const double *xyh, size_t n, uint8_t *result);
+hpp_status hpp_collide_improved_dev(hpp_map *map, const double *xyh_dev, size_t n, uint8_t *result_dev);
 
 /* ---------------------------------------------------------------- holonomic-with-obstacles heuristic
  * Replaces HybridAstar::holonomicCostsWithObstacles_planning (RS/include/HybridAstar.h:62,

@@ -68,6 +68,7 @@ void orc_ellipse_halfwidths(int r, int *dx /* 2r+1 entries, -1 = empty row */);
 /* returns 1 = collision or out of map (reference polarity, hazard H5) */
 int orc_collide_circles(const orc_map *m, const orc_car *car, double x, double y, double heading);
 void orc_car_circles(const orc_car *car, double cx[4], double cy[4], double *r);
+int orc_collide_circles_improved(const orc_map *m, const orc_car *car, double x, double y, double heading);
 void orc_collide_circles_batch(const orc_map *m, const orc_car *car, const double *xyh, size_t n, uint8_t *verdict);
 
 /* ---- a9: SAT footprint collision (DB/src/Grid_map.cpp:50-123, DB/src/sat_collision_checker.cc:12-161) ---- */

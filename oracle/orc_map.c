@@ -387,6 +387,26 @@ int orc_collide_circles(const orc_map *m, const orc_car *car, double x, double y
   return 0;
 }
 
+/* RS/src/Grid_map.cpp:286-317 isSingleStateCollisionFreeImproved with CarData::getBoundingCircle
+ * (RS/src/CarData.cpp:78-81, :112-124); returns the method's value as the reference returns it */
+int orc_collide_circles_improved(const orc_map *m, const orc_car *car, double x, double y, double heading) {
+  gm_geom g;
+  double bx = (car->axle_to_front - car->axle_to_back) / 2.0;
+  double br = sqrt(pow((car->axle_to_front + car->axle_to_back) / 2.0, 2) + pow(car->width / 2.0, 2));
+  double px = bx * cos(heading) - 0.0 * sin(heading) + x;
+  double py = bx * sin(heading) + 0.0 * cos(heading) + y;
+  float value;
+  gm_setup(m, &g);
+  if (!gm_is_inside(&g, px, py)) return 0;
+  if (!gm_at_linear(&g, m->distance, px, py, &value)) {
+    int i, j;
+    gm_index(&g, px, py, &i, &j);
+    value = m->distance[(size_t)j * g.W + i];
+  }
+  if ((double)value < br) return orc_collide_circles(m, car, x, y, heading);
+  return 1;
+}
+
 /* the same check over n poses (xyh: n x 3), one call per pose exactly as above: the loop the CPU baselines time */
 void orc_collide_circles_batch(const orc_map *m, const orc_car *car, const double *xyh, size_t n, uint8_t *verdict) {
   size_t i;

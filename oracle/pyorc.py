@@ -210,6 +210,15 @@ def collide_circles(m, poses, car=DEFAULT_CAR):
     return out
 
 
+def collide_improved(m, poses, car=DEFAULT_CAR):
+    """isSingleStateCollisionFreeImproved per pose (the reference's own return convention)"""
+    cs = car_struct(car)
+    L = lib()
+    L.orc_collide_circles_improved.argtypes = [C.POINTER(OrcMap), C.POINTER(OrcCar), C.c_double, C.c_double, C.c_double]
+    poses = np.asarray(poses, np.float64).reshape(-1, 3)
+    return np.array([L.orc_collide_circles_improved(C.byref(m.c), C.byref(cs), p[0], p[1], p[2]) for p in poses], np.uint8)
+
+
 def collide_sat(m, poses, car=DEFAULT_CAR):
     cs = car_struct(car)
     poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 3)

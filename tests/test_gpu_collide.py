@@ -121,3 +121,40 @@ def test_collide_circles_cfg4_full_size(ctx):
     assert abs(got.mean() - want.mean()) < 5e-3
     assert np.array_equal(m.collide_circles(poses[:1_000_000]), got[:1_000_000])   # host-buffer path, same verdicts
     m.close()
+
+
+def test_collide_compact_layer_equals_float_layer(ctx):
+    """K4 reads the compact squared-distance layer (one byte per cell, clamped to 255, 8x4 micro-tiles) by default and
+    the float layer for circle radii >= 14 cells: the verdicts must be identical on dense and on sparse maps (clamped
+    taps), at the map border (index aliasing) and for a fine resolution where the radius is close to the limit."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    sparse = np.zeros((300, 333), np.int8)
+    sparse[150:153, 100:104] = 100
+    sparse[10, 300] = 100
+    for occ, res in ((block_map(301, 203, 0.1, 2, 3), 0.2), (sparse, 0.2), (block_map(256, 256, 0.02, 4, 2), 0.05),
+                     (np.zeros((40, 50), np.int8), 0.2)):
+        H, W = occ.shape
+        m = hpp.Map(ctx, occ, res)
+        om = O.Map(occ, res)
+        poses = random_poses(30000, W, H, res=res, margin=-2.0 * res * 10, seed=7)      # also outside the map
+        got = m.collide_circles(poses)
+        want = O.collide_circles(om, poses)
+        assert np.array_equal(got, want), f"{(got != want).sum()} verdicts differ ({W}x{H} at {res})"
+        m.close()
+
+
+def test_collide_improved_matches_oracle(ctx):
+    """Grid_map::isSingleStateCollisionFreeImproved (RS/src/Grid_map.cpp:286-317): all three outcomes occur"""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ = block_map(200, 160, 0.01, 3, 4)
+    m = hpp.Map(ctx, occ, 0.2)
+    om = O.Map(occ, 0.2)
+    poses = random_poses(20000, 200, 160, margin=-3.0, seed=9)
+    got = m.collide_improved(poses)
+    want = O.collide_improved(om, poses)
+    assert np.array_equal(got, want)
+    plain = O.collide_circles(om, poses)
+    assert (want != plain).any() and (want == 0).any() and (want == 1).any()
+    m.close()
