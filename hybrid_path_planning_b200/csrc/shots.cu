@@ -190,7 +190,7 @@ struct all_paths_hdr {
   double lengths[RS_NCAND][5];
   double total[RS_NCAND];
   char types[RS_NCAND][5];
-  int seg_samples[RS_NCAND][5];  // interior samples per segment (the end sample of the last segment comes on top)
+  int seg_samples[RS_NCAND][5];  // per segment: interior samples | (those written with pd > 0) << 16
   unsigned long long samples_needed;
 };
 
@@ -268,17 +268,24 @@ extern "C" hpp_status hpp_rs_all_paths(hpp_ctx *c, const double start[3], const 
     HPP_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   if (directions) {
-    // PATH::directions (RS/src/reeds_shepp_path.cpp:697, :714-721 via interpolate): slot 0 carries the sign of the first
-    // segment, every later slot the sign of the segment that wrote it; trimmed like the samples
+    // PATH::directions: slot 0 carries the sign of the first segment's length (RS/src/reeds_shepp_path.cpp:697); every
+    // other slot the sign of the length argument of the interpolate() call that wrote it (:791) -- the running pd for
+    // interior samples (negative for the first samples of a segment that continues in its predecessor's direction,
+    // :716-719), the segment length for the end sample of the last segment; trimmed like the samples.  pd moves
+    // monotonically by +-step inside a segment, so its positive samples are one contiguous run.
     size_t o = 0;
     for (int e = 0; e < h->n_paths; e++) {
       const int keep = h->n_samples[e];
       int j = 0;
       if (keep > 0) directions[o + j++] = h->lengths[e][0] > 0.0 ? 1 : -1;
       for (int i = 0; i < h->n_seg[e]; i++) {
-        const int dsign = h->lengths[e][i] > 0.0 ? 1 : -1;
-        const int cnt = h->seg_samples[e][i] + (i == h->n_seg[e] - 1 ? 1 : 0);
-        for (int q = 0; q < cnt && j < keep; q++) directions[o + j++] = dsign;
+        const bool fwd = h->lengths[e][i] > 0.0;  // step d > 0: pd rises, non-positive samples first
+        const int cnt = h->seg_samples[e][i] & 0xffff, npos = h->seg_samples[e][i] >> 16;
+        for (int q = 0; q < cnt && j < keep; q++) {
+          const bool positive = fwd ? q >= cnt - npos : q < npos;
+          directions[o + j++] = positive ? 1 : -1;
+        }
+        if (i == h->n_seg[e] - 1 && j < keep) directions[o + j++] = fwd ? 1 : -1;
       }
       o += (size_t)keep;
     }

@@ -353,7 +353,7 @@ static __device__ __noinline__ void rs_interpolate(double l, char m, double maxc
 //   RS:      world = (cos(-q)x + sin(-q)y + sx, -sin(-q)x + cos(-q)y + sy, pi_2_pi(yaw + q))      (:76-81)
 //   Dubins:  world = (x cos q - y sin q + sx,  x sin q + y cos q + sy,     pi_2_pi(yaw + q))       (DB :365-371)
 // visit0 = false skips the visit of sample 0 (the start pose itself, the same for every path of a shot: the caller has
-// looked at it once).  seg_counts (optional, zeroed by the caller): number of interior samples each segment contributes.
+// looked at it once).  seg_counts (optional, zeroed by the caller): per segment, interior samples | (those with pd > 0) << 16.
 template <bool DUBINS, class Visitor>
 __device__ __forceinline__ int warp_sample_path(const double *len, const unsigned char *typ, int nseg, double maxc,
                                                 double step, double sx, double sy, double syaw, Visitor &vis,
@@ -410,7 +410,11 @@ __device__ __forceinline__ int warp_sample_path(const double *len, const unsigne
       if (nz) last_nonzero = ind + (31 - __clz(nz));
       if ((cnt || (cnt < 32 && last_seg)) && vis(valid, ind + lane, X, Y, YAW, px)) return -1;
       ind += cnt;
-      if (seg_counts && lane == 0) seg_counts[i] += cnt;  // interior samples of segment i (PATH::directions, :714-721)
+      if (seg_counts) {  // PATH::directions: interpolate() stores the sign of ITS length argument (:791) -- pd for the
+                         // interior samples -- so segment i reports its interior samples and how many have pd > 0
+        const unsigned pm = __ballot_sync(0xffffffffu, lane < cnt && mine > 0.0);
+        if (lane == 0) seg_counts[i] += cnt + (__popc(pm) << 16);
+      }
       // advance pd by cnt steps (all lanes identically)
       for (int j = 0; j < cnt; j++) pd += d;
       if (cnt < 32) {

@@ -76,7 +76,13 @@ def test_host_shells_against_oracle(tmp_path, variant):
     i += 1 + len(steer)
     assert np.array_equal(rows[:, 0], steer) and np.array_equal(rows[:, 1], direction)
     for r, k in zip(rows, every):
-        assert r[2] == pytest.approx(k["cost"], rel=1e-12)
+        # RS/src/HybridAstar.cpp:80-107 for the start node (Cost_path 0, steering 0, direction 1): simulationLength 4,
+        # reverse 10, directionChange 250 (RS) / 200 (Dubins), steerAngle 15, steerAngleChange 20
+        want_cost = (4.0 if r[1] == 1 else 4.0 * 10.0) + (0.0 if r[1] == 1 else (250.0 if variant == 0 else 200.0)) + \
+            abs(r[0]) * 15.0 + abs(r[0] - 0.0) * 20.0
+        assert r[2] == pytest.approx(want_cost, rel=1e-12)
+        if k["valid"]:                       # the oracle (like the reference) prices only collision-free rollouts
+            assert r[2] == pytest.approx(k["cost"], rel=1e-12)
     # reeds_shepp_path / dubins_path class shells
     maxc = np.tan(0.6) / 2.75
     want_all = O.rs_all_paths(start, goal, maxc, 1.0)
