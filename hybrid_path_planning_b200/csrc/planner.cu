@@ -890,7 +890,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
                "exceed the device memory budget (%zu B): lower traj_cap or the batch size", max_warps * per_warp, io_bytes,
                field_bytes, budget);
     size_t fields_cap = (budget - fixed_bytes) / field_bytes;
-    if (fields_cap > 4096) fields_cap = 4096;
+    if (fields_cap > 65536) fields_cap = 65536;  // (a chunk ends with a synchronisation: as few chunks as memory allows)
     const int grid = (int)max_warps;
     const size_t n_warps = (size_t)grid;  // one node pool / heap / table per CTA
     char *d_pool = nullptr;
