@@ -142,17 +142,31 @@ struct edt_band {
   uint32_t *unresolved;   // set to 1 when a result could be beaten by an obstacle outside the buffer
 };
 
+// epilogue shared by the column kernels: sqrtf((float)d2) * (float)res at the 180-degree-rotated index, plus the compact
+// copy for K4 (squared cell distance clamped to 255) at the same flipped cell (i, j) = (W-1-x, H-1-y)
+__device__ __forceinline__ void edt_store(unsigned best, int x, int y, int W, int H, float res_f,
+                                          float *__restrict__ distance, uint8_t *__restrict__ d2u8, int d2_tiles_x) {
+  // cv2 returns the constant 65536 for an image without any zero pixel
+  const float d = (best == EDT_INF32) ? 65536.0f : __fsqrt_rn((float)best);
+  distance[(size_t)W * H - 1 - ((size_t)y * W + x)] = __fmul_rn(d, res_f);
+  if (d2u8) d2u8[hpp_d2_addr(W - 1 - x, H - 1 - y, d2_tiles_x)] = (uint8_t)min(best, 255u);
+}
+
+// far_flags (whole-map mode): one word per output tile + a global word at far_flags[-1]; far_mask: one bit per cell of a
+// tile, [tile][row][half].  A cell whose search needs rows beyond the +-32-row halo parks its best-so-far in its slot of
+// the distance layer, sets its bit and flags its tile; edt_far_kernel (block-minimum pyramid) finishes exactly those
+// cells instead of walking the rows one by one through L2 -- the cost per cell stays bounded on sparse maps.
 template <bool BAND>
 __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict__ g, int W, int H, float res_f,
                                                       float *__restrict__ distance,
                                                       const uint32_t *__restrict__ any_obstacle, edt_band bd,
-                                                      uint8_t *__restrict__ d2u8, int d2_tiles_x) {
+                                                      uint8_t *__restrict__ d2u8, int d2_tiles_x,
+                                                      uint32_t *__restrict__ far_flags, uint32_t *__restrict__ far_mask) {
   __shared__ __align__(16) uint16_t gs[EDT_TY + 2 * EDT_R][EDT_TX];
   const int x0 = blockIdx.x * EDT_TX, y0 = (BAND ? bd.y_begin : 0) + blockIdx.y * EDT_TY;
   const int y_end = BAND ? bd.y_begin + bd.y_count : H;
   const int tx = threadIdx.x & (EDT_TX - 1), tyb = threadIdx.x / EDT_TX;  // 4 row groups
   const int x = x0 + tx;
-  const size_t n = (size_t)W * H;
   if ((W & 7) == 0 && x0 + EDT_TX <= W) {
     // 16-byte loads: a tile row is 8 chunks of 8 uint16
     for (int i = threadIdx.x; i < (EDT_TY + 2 * EDT_R) * (EDT_TX / 8); i += 256) {
@@ -180,6 +194,7 @@ __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict
     const int sr = ry + EDT_R;  // row of (x,y) inside gs
     unsigned own = gs[sr][tx];
     unsigned best = (own == EDT_INF16) ? EDT_INF32 : own * own;
+    bool far = false;
     if (!empty_map) {
       const int kmax = max(y, H - 1 - y);
       for (int k = 1; k <= kmax; k++) {
@@ -189,6 +204,9 @@ __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict
         if (k <= EDT_R) {
           a = gs[sr - k][tx];
           b = gs[sr + k][tx];
+        } else if (!BAND) {
+          far = true;  // rows beyond the halo: this tile goes to edt_far_kernel
+          break;
         } else {
           a = (y - k >= 0) ? g[(size_t)(y - k) * W + x] : EDT_INF16;
           b = (y + k < H) ? g[(size_t)(y + k) * W + x] : EDT_INF16;
@@ -200,6 +218,19 @@ __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict
         }
       }
     }
+    if (!BAND) {
+      const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      const unsigned fm = __ballot_sync(__activemask(), far);  // a warp = 32 adjacent columns of one row
+      if ((threadIdx.x & 31) == 0) far_mask[(tile * EDT_TY + ry) * 2 + ((threadIdx.x >> 5) & 1)] = fm;
+      if (far) {
+        distance[(size_t)W * H - 1 - ((size_t)y * W + x)] = __uint_as_float(best);  // parked for edt_far_kernel
+        far_flags[tile] = 1u;
+        far_flags[-1] = 1u;
+      } else {
+        edt_store(best, x, y, W, H, res_f, distance, d2u8, d2_tiles_x);
+      }
+      continue;
+    }
     // cv2 returns the constant 65536 for an image without any zero pixel
     float d = (best == EDT_INF32) ? 65536.0f : __fsqrt_rn((float)best);
     if (BAND) {
@@ -209,13 +240,68 @@ __global__ void __launch_bounds__(256) edt_col_kernel(const uint16_t *__restrict
       if (bd.more_below) lim = min(lim, (unsigned long long)(H - y));
       if (lim != ~0ull && (best == EDT_INF32 || (unsigned long long)best > lim * lim)) open_result = true;
       distance[(size_t)(y - bd.y_begin) * W + x] = __fmul_rn(d, res_f);
-    } else {
-      distance[n - 1 - ((size_t)y * W + x)] = __fmul_rn(d, res_f);
-      // compact copy for K4: squared cell distance clamped to 255, at the same (flipped) cell (i, j) = (W-1-x, H-1-y)
-      if (d2u8) d2u8[hpp_d2_addr(W - 1 - x, H - 1 - y, d2_tiles_x)] = (uint8_t)min(best, 255u);
     }
   }
   if (BAND && open_result) *bd.unresolved = 1u;
+}
+
+// ---- far path (sparse maps).  bmin[b][x] = min of g(x, y) over the EDT_BLK rows of block b; a block whose lower bound
+// bmin^2 + (rows to its nearest row)^2 cannot beat the best so far is skipped as a whole.
+#define EDT_BLK 16
+__global__ void __launch_bounds__(256) edt_blockmin_kernel(const uint16_t *__restrict__ g, int W, int H,
+                                                           uint16_t *__restrict__ bmin,
+                                                           const uint32_t *__restrict__ far_flags) {
+  if (far_flags[-1] == 0u) return;  // no cell asked for the far path
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (x >= W) return;
+  unsigned m = EDT_INF16;
+  const int y1 = min(H, (b + 1) * EDT_BLK);
+  for (int y = b * EDT_BLK; y < y1; y++) m = min(m, (unsigned)g[(size_t)y * W + x]);
+  bmin[(size_t)b * W + x] = (uint16_t)m;
+}
+
+__global__ void __launch_bounds__(256) edt_far_kernel(const uint16_t *__restrict__ g, const uint16_t *__restrict__ bmin,
+                                                      int W, int H, float res_f, float *__restrict__ distance,
+                                                      uint8_t *__restrict__ d2u8, int d2_tiles_x,
+                                                      const uint32_t *__restrict__ far_flags,
+                                                      const uint32_t *__restrict__ far_mask) {
+  const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  if (far_flags[tile] == 0u) return;  // the column kernel finished this tile
+  const int tx = threadIdx.x & (EDT_TX - 1), tyb = threadIdx.x / EDT_TX;
+  const int x = blockIdx.x * EDT_TX + tx;
+  if (x >= W) return;
+  for (int ry = tyb; ry < EDT_TY; ry += 256 / EDT_TX) {
+    const int y = blockIdx.y * EDT_TY + ry;
+    if (y >= H) break;
+    const unsigned fm = far_mask[(tile * EDT_TY + ry) * 2 + ((threadIdx.x >> 5) & 1)];
+    if (!((fm >> (threadIdx.x & 31)) & 1u)) continue;  // finished by the column kernel
+    const size_t slot = (size_t)W * H - 1 - ((size_t)y * W + x);
+    const unsigned parked = __float_as_uint(distance[slot]);  // best over the rows y-32 .. y+32
+    unsigned long long best = parked == EDT_INF32 ? ~0ull : (unsigned long long)parked;
+#pragma unroll
+    for (int dir = -1; dir <= 1; dir += 2) {
+      int yy = y + dir * (EDT_R + 1);
+      while (yy >= 0 && yy < H) {
+        const unsigned long long dy = (unsigned long long)(dir > 0 ? yy - y : y - yy);
+        if (dy * dy >= best) break;
+        // entering a block at its nearest row: skip it when its minimum cannot win
+        if ((dir > 0 && (yy & (EDT_BLK - 1)) == 0) || (dir < 0 && (yy & (EDT_BLK - 1)) == EDT_BLK - 1)) {
+          const unsigned mb = bmin[(size_t)(yy / EDT_BLK) * W + x];
+          if (mb == EDT_INF16 || (unsigned long long)mb * mb + dy * dy >= best) {
+            yy += dir * EDT_BLK;
+            continue;
+          }
+        }
+        const unsigned v = g[(size_t)yy * W + x];
+        if (v != EDT_INF16) {
+          const unsigned long long cand = (unsigned long long)v * v + dy * dy;
+          best = cand < best ? cand : best;
+        }
+        yy += dir;
+      }
+    }
+    edt_store(best == ~0ull ? EDT_INF32 : (unsigned)best, x, y, W, H, res_f, distance, d2u8, d2_tiles_x);
+  }
 }
 
 static const pred_lut *edt_lut_dev(hpp_ctx *c) { return (const pred_lut *)(c->d_flags + 32); }
@@ -252,8 +338,25 @@ hpp_status hpp_edt_build(hpp_map *m) {
   dim3 grid(hpp_div_up(W, EDT_TX), hpp_div_up(H, EDT_TY));
   edt_band none;
   memset(&none, 0, sizeof none);
+  // far-path state (scratch slot 5): [global flag | one flag per tile | block minima]; the two far kernels return at
+  // once unless the column kernel flagged a tile (maps with distances beyond the 32-row halo)
+  const size_t n_tiles = (size_t)grid.x * grid.y, n_blk = (size_t)hpp_div_up(H, EDT_BLK);
+  const size_t flag_bytes = ((n_tiles + 1) * sizeof(uint32_t) + 255) & ~(size_t)255;
+  const size_t mask_bytes = n_tiles * EDT_TY * 2 * sizeof(uint32_t);  // written by the column kernel, never cleared
+  void *far = nullptr;
+  s = hpp_scratch(c, 5, flag_bytes + mask_bytes + n_blk * W * sizeof(uint16_t), &far);
+  if (s != HPP_OK) return s;
+  uint32_t *far_flags = (uint32_t *)far + 1;
+  uint32_t *far_mask = (uint32_t *)((uint8_t *)far + flag_bytes);
+  uint16_t *bmin = (uint16_t *)((uint8_t *)far + flag_bytes + mask_bytes);
+  HPP_CUDA(c, cudaMemsetAsync(far, 0, flag_bytes, c->stream));
   edt_col_kernel<false><<<grid, 256, 0, c->stream>>>(m->d_g, W, H, m->g.res_f, m->d_distance, c->d_flags + 40, none,
-                                                     m->d_d2u8, m->d2_tiles_x);
+                                                     m->d_d2u8, m->d2_tiles_x, far_flags, far_mask);
+  HPP_LAUNCHED(c);
+  edt_blockmin_kernel<<<dim3(hpp_div_up(W, 256), (unsigned)n_blk), 256, 0, c->stream>>>(m->d_g, W, H, bmin, far_flags);
+  HPP_LAUNCHED(c);
+  edt_far_kernel<<<grid, 256, 0, c->stream>>>(m->d_g, bmin, W, H, m->g.res_f, m->d_distance, m->d_d2u8, m->d2_tiles_x,
+                                              far_flags, far_mask);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }
@@ -283,7 +386,7 @@ hpp_status hpp_edt_band_cols(hpp_ctx *c, const uint16_t *g_ext, int W, int rows_
   bd.unresolved = unresolved;
   dim3 grid(hpp_div_up(W, EDT_TX), hpp_div_up(y_count, EDT_TY));
   edt_col_kernel<true><<<grid, 256, 0, c->stream>>>(g_ext, W, rows_ext, res_f, distance_band, c->d_flags + 40, bd,
-                                                    nullptr, 0);
+                                                    nullptr, 0, nullptr, nullptr);
   HPP_LAUNCHED(c);
   return HPP_OK;
 }

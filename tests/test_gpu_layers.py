@@ -116,3 +116,36 @@ def test_image_to_occupancy_bit_exact(ctx, rows, cols, seed):
     got = ctx.image_to_occupancy(img)
     assert got.shape == (cols, rows)
     assert bits_equal(got, O.image_to_occ(img))
+
+
+def test_layers_sparse_maps_far_path(ctx):
+    """Distances far beyond the column kernel's 32-row halo: the flagged tiles are finished by the block-minimum far
+    kernel.  A nearly empty map (hundreds of cells to the nearest obstacle), a map that is dense in one corner and
+    empty elsewhere (flagged and unflagged tiles side by side), a single obstacle cell in a corner, and rows without any
+    obstacle; bit-exact against the oracle (= cv2, tests/test_cpu_oracle_golden.py) and, for the compact layer K4 reads,
+    through the collision verdicts of poses all over the map."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    from tests.common import random_poses
+    rng = np.random.default_rng(3)
+    a = np.zeros((1100, 1300), np.int8)
+    for _ in range(7):
+        y, x = rng.integers(0, 1095), rng.integers(0, 1295)
+        a[y:y + 3, x:x + 4] = 100
+    b = np.zeros((900, 1000), np.int8)
+    b[:200, :256] = block_map(256, 200, 0.3, 8, 5)
+    c = np.zeros((700, 333), np.int8)
+    c[699, 0] = 100
+    d = np.zeros((300, 500), np.int8)
+    d[100, :] = 100
+    d[250, 40] = -1
+    for occ in (a, b, c, d):
+        H, W = occ.shape
+        m = hpp.Map(ctx, occ, 0.2)
+        om = O.Map(occ, 0.2)
+        obst, dist = m.layers()
+        assert bits_equal(obst, om.obstacle)
+        assert bits_equal(dist, om.distance), f"{(dist != om.distance).sum()} cells differ ({W}x{H})"
+        poses = random_poses(20000, W, H, margin=0.5, seed=1)
+        assert np.array_equal(m.collide_circles(poses), O.collide_circles(om, poses))
+        m.close()
