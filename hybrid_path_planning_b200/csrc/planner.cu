@@ -30,6 +30,9 @@
 #define PLAN_WARPS_BATCH 4
 #define PLAN_WARPS_LONE 8
 #define PLAN_ITER_CAP 3500
+#ifndef PLAN_PATH_GROUP
+#define PLAN_PATH_GROUP 8  // lanes per candidate path in the shot's footprint checks (32 = one path per warp step)
+#endif
 #define PI_ASTAR 3.14159 /* RS/include/HybridAstar.h:24 */
 
 struct pnode {
@@ -441,17 +444,9 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
         // The reference tries them in cost order and stops at the first free one (> 5 paths) or keeps the cheapest
         // free one; which path that is does not depend on how many were looked at, so the order -- a sequential
         // heap replay -- is only worked out when some path is free (once per successful query).
-        for (;;) {
-          int e = 0;
-          if (lane == 0) e = atomicAdd(&sm.next_path, 1);
-          e = __shfl_sync(0xffffffffu, e, 0);
-          if (e >= n_acc) break;
-          const int verdict = rs_check_path(S, e, g, pc.cc, dist, cn.x, cn.y, cn.h, pc.maxc, sm.hit0);
-          if (lane == 0) {
-            sm.verdict[e] = verdict;
-            if (verdict >= 0) sm.any_free = 1;
-          }
-        }
+        // (grouped: a warp walks 32 / PLAN_PATH_GROUP paths at once, one per lane group, see rs_check_paths_grouped)
+        rs_check_paths_grouped<PLAN_PATH_GROUP>(S, n_acc, &sm.next_path, sm.verdict, &sm.any_free, g, pc.cc, dist, cn.x,
+                                                cn.y, cn.h, pc.maxc, sm.hit0);
         __syncthreads();
         if (sm.any_free) {
           if (wid == 0) rs_order_paths(S, cn.cost, pc.maxc, pc.max_steer);

@@ -616,6 +616,111 @@ __device__ __forceinline__ int rs_check_path(const rs_warp_smem &S, int e, const
   return ((n_keep < 0) || (vis.hit_zero_idx < n_keep)) ? -1 : n_keep;
 }
 
+// Phase 5 for a whole shot, GROUPED: the warp checks 32 / G candidate paths at once, one per group of G lanes, each
+// group pulling its next path from *next_path.  rs_check_path walks one path segment by segment with the whole warp:
+// a segment is one dependent step whatever its length, and with 1 m between samples most segments fill a few lanes
+// (3-5 steps per path, ~10 paths per warp in the planner).  Here a step serves 32 / G paths.  The samples of a path
+// are the same whatever the group width: pd advances by the reference's repeated addition (:722-729) in both forms,
+// and the verdict of a path (-1 collides / kept sample count) does not depend on the order its samples are looked at.
+// verdict[e] receives the verdict of the e-th accepted path, *any_free is set when some path is free.  hit0: footprint
+// verdict of sample 0 (the start pose, common to all paths).  Warp-collective; every warp of a CTA may run it at once.
+template <int G>
+__device__ __forceinline__ void rs_check_paths_grouped(const rs_warp_smem &S, int n_acc, int *next_path, int *verdict,
+                                                       int *any_free, const hpp_geom &g, const circ_consts &cc,
+                                                       const float *dist, double sx, double sy, double syaw, double maxc,
+                                                       int hit0) {
+  static_assert(G == 4 || G == 8 || G == 16 || G == 32, "group width");
+  constexpr unsigned FULLM = 0xffffffffu;
+  constexpr unsigned GMASK = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+  const int lane = threadIdx.x & 31, sub = lane & (G - 1), gbase = lane & ~(G - 1);
+  const double step = maxc;  // step_size (1.0) * maxc
+  double rs_, rc_;
+  sincos(-syaw, &rs_, &rc_);
+  // per-group state (identical in the lanes of a group)
+  int e = -1, k = 0, i = 0, nseg = 0, ind = 1, last_nonzero = -1, hit_zero_idx = 0x7fffffff;
+  bool exhausted = false, seg_start = true;
+  double pd = 0.0, ll = 0.0, ox = 0.0, oy = 0.0, oyaw = 0.0, ex = 0.0, ey = 0.0, eyaw = 0.0;
+  for (;;) {
+    // groups without a path take the next one
+    const bool want = e < 0 && !exhausted;
+    int ne = -1;
+    if (want && sub == 0) ne = atomicAdd(next_path, 1);
+    ne = __shfl_sync(FULLM, ne, gbase);
+    if (want) {
+      if (ne >= n_acc) {
+        exhausted = true;
+      } else {
+        e = ne;
+        k = S.acc[e];
+        nseg = S.nseg[k];
+        i = 0;
+        ind = 1;
+        last_nonzero = -1;
+        hit_zero_idx = hit0 > 0 ? 0 : 0x7fffffff;  // sample 0 has local x == 0.0: a hit there counts if it is kept
+        ll = 0.0;
+        ex = ey = eyaw = 0.0;
+        seg_start = true;
+      }
+    }
+    if (!__any_sync(FULLM, e >= 0)) break;
+    const bool act = e >= 0 && nseg > 0;
+    // ---- one step of the group's current segment (generate_local_course, :697-735)
+    const double l = act ? S.len[k][i] : 0.0;
+    const char m = act ? (char)S.typ[k][i] : 'S';
+    const double d = (l > 0.0) ? step : -step;
+    if (act && seg_start) {
+      ox = ex; oy = ey; oyaw = eyaw;  // px[ind] read before --ind (:711)
+      pd = (i >= 1 && (S.len[k][i - 1] * l) > 0) ? -d - ll : d - ll;
+      seg_start = false;
+    }
+    double mine = pd;
+    for (int j = 0; j < sub; j++) mine += d;  // the reference's repeated addition, so the rounding matches
+    const bool in_range = act && fabs(mine) <= fabs(l);
+    const unsigned vm = (__ballot_sync(FULLM, in_range) >> gbase) & GMASK;
+    const int cnt = (vm == GMASK) ? G : (__ffs(~vm) - 1);  // the leading run of lanes: the while loop stops at the first miss
+    const bool last_seg = i == nseg - 1;
+    const bool is_end = act && cnt < G && sub == cnt;       // the end-of-segment sample (:733-735), length l
+    const bool valid = act && (sub < cnt || (is_end && last_seg));
+    double px = 0, py = 0, pyaw = 0;
+    if (act && (sub < cnt || is_end)) rs_interpolate(is_end ? l : mine, m, maxc, ox, oy, oyaw, px, py, pyaw);
+    int hit = 0;
+    if (valid) {  // world transform (:76-81) and footprint
+      const double X = rc_ * px + rs_ * py + sx, Y = -rs_ * px + rc_ * py + sy, YAW = pi_2_pi(pyaw + syaw);
+      hit = circles_collide_ilp(g, cc, dist, X, Y, YAW);
+    }
+    const unsigned nz = (__ballot_sync(FULLM, valid && px != 0.0) >> gbase) & GMASK;
+    const unsigned hard = (__ballot_sync(FULLM, hit && px != 0.0) >> gbase) & GMASK;
+    const unsigned soft = (__ballot_sync(FULLM, hit && px == 0.0) >> gbase) & GMASK;
+    if (nz) last_nonzero = ind + (31 - __clz(nz));
+    if (soft) hit_zero_idx = min(hit_zero_idx, ind + __ffs(soft) - 1);
+    ind += cnt;
+    for (int j = 0; j < cnt; j++) pd += d;
+    const bool seg_done = cnt < G;
+    const double bx = __shfl_sync(FULLM, px, gbase + (cnt < G ? cnt : 0));
+    const double by = __shfl_sync(FULLM, py, gbase + (cnt < G ? cnt : 0));
+    const double byaw = __shfl_sync(FULLM, pyaw, gbase + (cnt < G ? cnt : 0));
+    if (act && seg_done) {
+      ex = bx; ey = by; eyaw = byaw;
+      ll = l - pd - d;  // :731
+      i++;
+      seg_start = true;
+    }
+    const bool path_done = e >= 0 && (!act || hard != 0 || (seg_done && i >= nseg));
+    if (path_done) {
+      int res = -1;
+      if (!hard) {
+        const int n_keep = last_nonzero + 1;  // the trailing "px == 0.0" trim (:738-744)
+        res = (hit_zero_idx < n_keep) ? -1 : n_keep;
+      }
+      if (sub == 0) {
+        verdict[e] = res;
+        if (res >= 0) *any_free = 1;
+      }
+      e = -1;
+    }
+  }
+}
+
 // folds the verdict of the o-th path into the result; returns true when the search is over
 // (> 5 paths: first collision-free path in pop order, :226-271; else strict minimum, first wins, :188-200)
 __device__ __forceinline__ bool rs_fold_path(const rs_warp_smem &S, int o, int n_keep, rs_shot_result &R, double &best) {
