@@ -10,17 +10,14 @@
 //     Dubins:  cost[v] = min(1000, min_u fl(cost[u] + fl(hypot(dir) + 10*cnt3x3(u))))  (DB/src/HybridAstar.cpp:198-221,:286-297)
 // over free cells v, which does not depend on the relaxation order (fl(a + w) is monotone in a).
 //
-// Device algorithm: ONE persistent kernel per batch of fields -- delta-stepping over tiles.  Two tile kernels:
-//   heur_warp_kernel (default)  32x32 tiles, ONE WARP per tile (no block-level barrier inside a tile solve), 16 / 20 / 4
-//                      warps per CTA.  A tile with its halo is staged by one TMA tensor box copy (3-D tensor map over
-//                      the batch's fields; row-wise bulk copies or plain loads as fall-backs).  The frontier lives in
-//                      REGISTERS, one 32-bit "needs evaluation" mask per lane (= row).  Sweeps are COMPACTED
-//                      (sweep_compact): the rows' needed cells go into one shared-memory list, every lane takes two
-//                      entries whatever their rows, improved cells OR their push masks into their rows' words with
-//                      32-bit shared atomics.  The row-wise sweep (HPP_HEUR_COMPACT=0) is kept for comparison.
-//   heur_persist_kernel (HPP_HEUR_NB=2|4)  the earlier 64x64 / 128x128 tiles: a CTA of NB*NB warps stages one tile,
-//                      every warp owns one 32x32 block (lane = row), block-border changes are posted to the neighbouring
-//                      warp through a shared-memory mask, one __syncthreads_or per PHASE_SWEEPS sweeps.
+// Device algorithm: ONE persistent kernel per batch of fields (heur_warp_kernel) -- delta-stepping over 32x32 tiles,
+// ONE WARP per tile (no block-level barrier inside a tile solve), 16 / 20 / 4 warps per CTA.  A tile with its halo is
+// staged by one TMA tensor box copy (3-D tensor map over the batch's fields; row-wise bulk copies or plain loads where
+// the tensor map cannot be used).  The frontier lives in REGISTERS, one 32-bit "needs evaluation" mask per lane
+// (= row).  Sweeps are COMPACTED (sweep_compact): the rows' needed cells go into one shared-memory list, every lane
+// takes two entries whatever their rows, improved cells OR their push masks into their rows' words with 32-bit shared
+// atomics.  (Round 1 also carried a multi-warp-tile kernel, a row-wise sweep and an asynchronous tile-queue kernel;
+// they were slower on every measured case -- profiles/r1_summary.md -- and were removed in round 2.)
 //   * A cell is evaluated by PULL: min over its 8 neighbours, exactly the reference's additions (no FMA; min
 //     before add is legal because fl(a+w) is monotone).  An improved cell pushes only the neighbours it can still
 //     improve, so settled cells behind the front are not re-evaluated.
@@ -34,7 +31,7 @@
 //     a group of several CTAs (cooperative launch) scans the tile table in slices and meets at two group barriers per
 //     round; ONE CTA per field (plain launch, large batches) keeps the round's schedule as the list of tiles posted
 //     to during the previous round and scans the table only when the window moves.  The host launches once and
-//     never polls.  heur_async_kernel (HPP_HEUR_ASYNC=1) is an experimental barrier-free tile queue for a lone field.
+//     never polls.
 // Costs are fp64 with exactly the reference's additions (library built with -fmad=false).
 #include <cooperative_groups.h>
 #include <cuda.h>  // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
@@ -52,16 +49,12 @@
 #define HPP_COUNT(x)
 #endif
 
-#ifndef HPP_NB2_CTAS
-#define HPP_NB2_CTAS 4  // resident 64x64-tile CTAs per SM (register cap 65536 / (128 * HPP_NB2_CTAS))
-#endif
 
 namespace {
 
 constexpr int HB = 32;  // block side = one warp, lane = row
 constexpr unsigned FULL = 0xffffffffu;
 constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;
-constexpr int PHASE_SWEEPS = 8;
 
 // direction bits of the tile activity flags / out flags
 enum { DIR_N = 1, DIR_S = 2, DIR_W = 4, DIR_E = 8, DIR_NW = 16, DIR_NE = 32, DIR_SW = 64, DIR_SE = 128 };
@@ -87,13 +80,11 @@ struct heur_args {
   uint32_t *stats;                 // [n_fields][4]: rounds, tile visits, windows, sweeps of CTA rank 0
   uint32_t *lists;                 // warp-tile kernel: [grid][n_tiles] schedule of the round
   uint32_t *sched;                 // warp-tile kernel: [n_groups][4 * group_size] slice counts + minima of a round
-  uint32_t *aq;                    // async kernel: control words + tile states + ring queue (see heur_async_kernel)
   unsigned long long *prof;        // optional [grid][8] cycle counters (HPP_HEUR_DEBUG): schedule, stage, solve,
                                    // write-back, barrier wait, tiles, phases, longest single solve
   double delta;                    // width of the global cost window
   double delta_in;                 // width of the sub-windows inside a tile visit
   int group_size, n_groups;
-  int compact;                     // warp-tile kernel: 1 = compacted sweeps (sweep_compact), 0 = row-wise sweeps (sweep)
   int lpt;                         // one-CTA-per-field mode: longest-first ordering of a round's tiles
   int tmap_ok;                     // warp-tile kernel: the tensor map below is valid (tiles staged by one TMA box copy)
   alignas(64) CUtensorMap tmap;    // cost_all as a (W, H, n_fields) fp64 tensor, box 38 x 34 x 1 = a tile with its halo
@@ -145,72 +136,6 @@ struct blk_state {
   uint32_t c_heavy, c_sparse, c_on, c_imp, c_sweeps;
 };
 
-template <int NB>
-__device__ __forceinline__ void post(uint32_t *s_inc, uint32_t *s_out, int bx, int by, int dx, int dy, int row, uint32_t bits,
-                                     blk_state &st) {
-  const int nx = bx + dx, ny = by + dy;
-  if (nx < 0 || nx >= NB || ny < 0 || ny >= NB) {
-    unsigned d;
-    if (dy < 0) d = dx < 0 ? DIR_NW : (dx > 0 ? DIR_NE : DIR_N);
-    else if (dy > 0) d = dx < 0 ? DIR_SW : (dx > 0 ? DIR_SE : DIR_S);
-    else d = dx < 0 ? DIR_W : DIR_E;
-    // a diagonal step that leaves the tile through an edge only (not the tile corner) is an edge post
-    if (dx != 0 && dy != 0) {
-      const bool xin = nx >= 0 && nx < NB, yin = ny >= 0 && ny < NB;
-      if (xin) d = dy < 0 ? DIR_N : DIR_S;
-      else if (yin) d = dx < 0 ? DIR_W : DIR_E;
-    }
-    atomicOr(s_out, d);
-  } else {
-    atomicOr(&s_inc[(ny * NB + nx) * 32 + row], bits);
-    st.posted = 1;
-  }
-}
-
-// Cells that a changed cell may improve, as three row masks per lane: bit (x+1) <-> column x (bits 0 and 33 are the
-// columns just outside the block) of the row above / my row / the row below.
-struct push3 {
-  unsigned long long up, own, dn;
-};
-
-// nmask: bit 0 NW, 1 N, 2 NE, 3 W, 4 E, 5 SW, 6 S, 7 SE  (neighbours of column x of my row)
-__device__ __forceinline__ void add_push(push3 &ps, int x, uint32_t nmask) {
-  ps.up |= (unsigned long long)(nmask & 7u) << x;
-  ps.own |= (unsigned long long)(((nmask >> 3) & 1u) | ((nmask >> 2) & 4u)) << x;
-  ps.dn |= (unsigned long long)((nmask >> 5) & 7u) << x;
-}
-
-// exchange the row masks between neighbouring lanes (= rows), turn them into need bits of my block, and post
-// what leaves the block to the neighbouring warp's incoming mask or to the tile's out flags
-template <int NB>
-__device__ __forceinline__ void propagate(const push3 &ps, blk_state &st, uint32_t *s_inc, uint32_t *s_out, int bx, int by,
-                                          int lane) {
-  unsigned long long from_above = __shfl_up_sync(FULL, ps.dn, 1), from_below = __shfl_down_sync(FULL, ps.up, 1);
-  if (lane == 0) from_above = 0;
-  if (lane == 31) from_below = 0;
-  const unsigned long long tot = ps.own | from_above | from_below;
-  st.need |= (uint32_t)(tot >> 1) & st.freem;
-  const bool spill_l = tot & 1ull, spill_r = (tot >> 33) & 1ull;
-  const bool edge = spill_l || spill_r || (lane == 0 && ps.up) || (lane == 31 && ps.dn);
-  if (__any_sync(FULL, edge)) {
-    __threadfence_block();  // the cost stores of this sweep before the notifications
-    if (spill_l) post<NB>(s_inc, s_out, bx, by, -1, 0, lane, 0x80000000u, st);
-    if (spill_r) post<NB>(s_inc, s_out, bx, by, 1, 0, lane, 1u, st);
-    if (lane == 0 && ps.up) {
-      const uint32_t mid = (uint32_t)(ps.up >> 1);
-      if (mid) post<NB>(s_inc, s_out, bx, by, 0, -1, 31, mid, st);
-      if (ps.up & 1ull) post<NB>(s_inc, s_out, bx, by, -1, -1, 31, 0x80000000u, st);
-      if ((ps.up >> 33) & 1ull) post<NB>(s_inc, s_out, bx, by, 1, -1, 31, 1u, st);
-    }
-    if (lane == 31 && ps.dn) {
-      const uint32_t mid = (uint32_t)(ps.dn >> 1);
-      if (mid) post<NB>(s_inc, s_out, bx, by, 0, 1, 0, mid, st);
-      if (ps.dn & 1ull) post<NB>(s_inc, s_out, bx, by, -1, 1, 0, 0x80000000u, st);
-      if ((ps.dn >> 33) & 1ull) post<NB>(s_inc, s_out, bx, by, 1, 1, 0, 1u, st);
-    }
-  }
-}
-
 // weights held in registers (RS) / shared memory (Dubins table)
 struct eval_w {
   double c0, d0;          // RS: cheapest cardinal / diagonal edge (the push filter's lower bound)
@@ -253,447 +178,6 @@ __device__ __forceinline__ double eval_cell(const volatile double *cs, const vol
   nmask = (t2 < nw ? 1u : 0u) | (t1 < n ? 2u : 0u) | (t2 < ne ? 4u : 0u) | (t1 < w ? 8u : 0u) | (t1 < ea ? 16u : 0u) |
           (t2 < sw ? 32u : 0u) | (t1 < s ? 64u : 0u) | (t2 < se ? 128u : 0u);
   return best;
-}
-
-// one sweep of my block: returns false when there was nothing to do
-template <int NB, int VARIANT>
-__device__ __forceinline__ bool sweep(volatile double *cs, const volatile uint8_t *cl, uint32_t *s_inc, uint32_t *s_out,
-                                      blk_state &st, int blk, int bx, int by, int lane, double bound,
-                                      const eval_w &wt) {
-  constexpr int S = tile_cfg<NB>::S;
-  // border changes posted by the neighbouring warps (a one-block tile has no neighbours inside the CTA)
-  if (NB > 1) {
-    uint32_t inc = ((volatile uint32_t *)s_inc)[blk * 32 + lane];
-    if (__any_sync(FULL, inc != 0)) {
-      if (inc) inc = atomicExch(&s_inc[blk * 32 + lane], 0u);
-      __threadfence_block();
-      st.need |= inc & st.freem;
-    }
-  }
-  if (!__any_sync(FULL, st.need != 0)) return false;
-  HPP_COUNT(st.c_sweeps++; { const int n_ = __reduce_add_sync(FULL, __popc(st.need)); st.c_imp += (n_ + 63) >> 6; st.c_on += n_; })
-  const int ebase = (by * HB + 1) * S + bx * HB + 2;  // shared index of cell (row 0, col 0) of my block
-  push3 ps = {0ull, 0ull, 0ull};
-  // Split the rows into "heavy" ones (evaluated one lane per column, one iteration per row) and "sparse" ones (one
-  // cell per lane and iteration, as many iterations as the fullest sparse row): pick the threshold that minimises
-  // the iteration count of this sweep.
-  const int cnt = __popc(st.need);
-  int thr = 33, best_cost = (__reduce_max_sync(FULL, cnt) + 1) >> 1;  // everything sparse: two cells per iteration
-  if (best_cost > 1) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      constexpr int cand[6] = {3, 5, 7, 9, 13, 21};
-      const int t = cand[k];
-      const int c = __popc(__ballot_sync(FULL, cnt >= t)) + (t >> 1);  // heavy rows + ceil((t-1)/2) sparse iterations
-      if ((t >> 1) < best_cost && c < best_cost) {
-        best_cost = c;
-        thr = t;
-      }
-    }
-  }
-  uint32_t heavy = thr < 33 ? __ballot_sync(FULL, cnt >= thr) : 0u;
-  while (heavy) {
-    const int r = __ffs(heavy) - 1;
-    heavy &= heavy - 1;
-    const uint32_t m = __shfl_sync(FULL, st.need, r);
-    const uint32_t nm = __shfl_sync(FULL, st.nearm, r);
-    const int e = ebase + r * S + lane;
-    const bool on = (m >> lane) & 1u;
-    HPP_COUNT(st.c_heavy++;)
-    const double c0 = cs[e];
-    uint32_t nmask;
-    const double best = eval_cell<VARIANT, S>(cs, cl, e, (nm >> lane) & 1u, wt, nmask);
-    const bool imp = on && best < c0;
-    if (imp) cs[e] = best;
-    const bool low = imp && best < bound;
-    if (!low) nmask = 0;
-    const uint32_t bimp = __ballot_sync(FULL, imp);
-    const uint32_t blow = __ballot_sync(FULL, low);
-    const unsigned long long up = (unsigned long long)__ballot_sync(FULL, nmask & 1u) |
-                                  ((unsigned long long)__ballot_sync(FULL, nmask & 2u) << 1) |
-                                  ((unsigned long long)__ballot_sync(FULL, nmask & 4u) << 2);
-    const unsigned long long own = (unsigned long long)__ballot_sync(FULL, nmask & 8u) |
-                                   ((unsigned long long)__ballot_sync(FULL, nmask & 16u) << 2);
-    const unsigned long long dn = (unsigned long long)__ballot_sync(FULL, nmask & 32u) |
-                                  ((unsigned long long)__ballot_sync(FULL, nmask & 64u) << 1) |
-                                  ((unsigned long long)__ballot_sync(FULL, nmask & 128u) << 2);
-    if (lane == r) {
-      st.need = 0;
-      ps.up |= up;
-      ps.own |= own;
-      ps.dn |= dn;
-      st.defer = (st.defer | bimp) & ~blow;
-      if (bimp) st.dirty = 1;
-    }
-    __syncwarp();
-  }
-  // sparse rows: two cells per lane and iteration (independent evaluations overlap their latencies); a thin front
-  // (at most one needed cell per row) takes the single-cell form, which is the shorter dependency chain
-  while (__any_sync(FULL, st.need != 0)) {
-    HPP_COUNT(st.c_sparse++;)
-    if (!__any_sync(FULL, (st.need & (st.need - 1)) != 0)) {
-      const bool on = st.need != 0;
-      const int x = on ? __ffs(st.need) - 1 : 0;
-      st.need = 0;
-      const int e = ebase + lane * S + x;
-      const double c0 = cs[e];
-      uint32_t nm;
-      const double b = eval_cell<VARIANT, S>(cs, cl, e, (st.nearm >> x) & 1u, wt, nm);
-      if (on && b < c0) {
-        cs[e] = b;
-        st.dirty = 1;
-        if (b < bound) {
-          add_push(ps, x, nm);
-          st.defer &= ~(1u << x);
-        } else {
-          st.defer |= 1u << x;
-        }
-      }
-      __syncwarp();
-      break;
-    }
-    const bool on0 = st.need != 0;
-    const int x0 = on0 ? __ffs(st.need) - 1 : 0;
-    st.need &= st.need - 1;
-    const bool on1 = st.need != 0;
-    const int x1 = on1 ? __ffs(st.need) - 1 : 0;
-    st.need &= st.need - 1;
-    const int e0 = ebase + lane * S + x0, e1 = ebase + lane * S + x1;
-    const double c0 = cs[e0], c1 = cs[e1];
-    uint32_t nm0, nm1;
-    const double b0 = eval_cell<VARIANT, S>(cs, cl, e0, (st.nearm >> x0) & 1u, wt, nm0);
-    const double b1 = eval_cell<VARIANT, S>(cs, cl, e1, (st.nearm >> x1) & 1u, wt, nm1);
-    const bool imp0 = on0 && b0 < c0, imp1 = on1 && b1 < c1;
-    if (imp0) {
-      cs[e0] = b0;
-      st.dirty = 1;
-      if (b0 < bound) {
-        add_push(ps, x0, nm0);
-        st.defer &= ~(1u << x0);
-      } else {
-        st.defer |= 1u << x0;
-      }
-    }
-    if (imp1) {
-      cs[e1] = b1;
-      st.dirty = 1;
-      if (b1 < bound) {
-        add_push(ps, x1, nm1);
-        st.defer &= ~(1u << x1);
-      } else {
-        st.defer |= 1u << x1;
-      }
-    }
-    __syncwarp();
-  }
-  if (__any_sync(FULL, (ps.up | ps.own | ps.dn) != 0ull)) propagate<NB>(ps, st, s_inc, s_out, bx, by, lane);
-  return true;
-}
-
-// ---------------------------------------------------------------- the persistent kernel
-template <int NB, int VARIANT>
-__global__ void __launch_bounds__(tile_cfg<NB>::THREADS, NB >= 4 ? 1 : HPP_NB2_CTAS) heur_persist_kernel(const __grid_constant__ heur_args a) {
-  using C = tile_cfg<NB>;
-  constexpr int T = C::T, S = C::S, ROWS = C::ROWS, NBLK = C::NBLK, THREADS = C::THREADS;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *cs_nv = (double *)smem_raw;                                   // ROWS * S
-  uint32_t *s_inc = (uint32_t *)(cs_nv + ROWS * S);                     // NBLK * 32
-  uint32_t *s_list = s_inc + NBLK * 32;                                 // THREADS
-  uint8_t *cl_nv = (uint8_t *)(s_list + THREADS);                       // ROWS * S (Dubins only)
-  volatile double *cs = cs_nv;
-  const volatile uint8_t *cl = cl_nv;
-  __shared__ unsigned long long s_gmin, s_minp[2];
-  __shared__ uint32_t s_count, s_mine, s_out, s_warp_cnt[32];
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int bx = wid % NB, by = wid / NB;
-  const int group = blockIdx.x / a.group_size, grank = blockIdx.x % a.group_size;
-  if (group >= a.n_groups) return;  // spare CTAs (grid not a multiple of the group size)
-  uint32_t *bar = a.bar + group * 32;
-  const int W = a.W, H = a.H, n_tiles = a.n_tiles;
-  const size_t n = (size_t)W * H;
-  __shared__ double s_db[20];
-  if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
-  __shared__ __align__(16) double2 s_rs[2];
-  if (tid < 2) s_rs[tid] = make_double2(a.wt.rs[tid][0], a.wt.rs[tid][1]);
-  eval_w wt;
-  wt.c0 = a.wt.rs[0][0];
-  wt.d0 = a.wt.rs[0][1];
-  wt.init = a.wt.init;
-  wt.rs = s_rs;
-  wt.db = s_db;
-  __syncthreads();
-
-  for (int field = group; field < a.n_fields; field += a.n_groups) {
-    double *cost = a.cost_all + (size_t)field * n;
-    uint32_t *act = a.act + (size_t)field * 3 * n_tiles;
-    unsigned long long *pmin = a.pmin + (size_t)field * 2 * n_tiles;
-    uint32_t *dmask = a.dmask + (size_t)field * n_tiles * NBLK * 32;
-    double bound = 0.0;
-    uint32_t rounds = 0, visits = 0, windows = 0, sweeps = 0;
-    unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tk = clock64();
-#define PF_MARK(i)                         \
-  if (a.prof) {                            \
-    const long long now_ = clock64();      \
-    pf[i] += (unsigned long long)(now_ - tk); \
-    tk = now_;                             \
-  }
-
-    for (uint32_t round = 0;; round++) {
-      // act buffers rotate: cur is read-only this round, next receives posts, clr is zeroed for the round after
-      uint32_t *act_cur = act + (round % 3) * n_tiles, *act_next = act + ((round + 1) % 3) * n_tiles,
-               *act_clr = act + ((round + 2) % 3) * n_tiles;
-      unsigned long long *pm_cur = pmin + (round & 1) * n_tiles, *pm_next = pmin + ((round + 1) & 1) * n_tiles;
-
-      // ---- pass 1: how many tiles are schedulable under the current bound, and the global minimum deferred cost
-      uint32_t total;
-      for (;;) {
-        if (tid == 0) {
-          s_count = 0;
-          s_gmin = INF_BITS;
-        }
-        __syncthreads();
-        uint32_t cnt = 0;
-        unsigned long long mn = INF_BITS;
-        for (int t = tid; t < n_tiles; t += THREADS) {
-          const uint32_t af = __ldcg(act_cur + t);
-          const unsigned long long pm = __ldcg(pm_cur + t);
-          if (af != 0 || __longlong_as_double((long long)pm) < bound) cnt++;
-          mn = pm < mn ? pm : mn;
-        }
-        for (int d = 16; d; d >>= 1) {
-          cnt += __shfl_down_sync(FULL, cnt, d);
-          const unsigned long long o = __shfl_down_sync(FULL, mn, d);
-          mn = o < mn ? o : mn;
-        }
-        if (lane == 0) {
-          if (cnt) atomicAdd(&s_count, cnt);
-          if (mn != INF_BITS) atomicMin(&s_gmin, mn);
-        }
-        __syncthreads();
-        total = s_count;
-        const unsigned long long g = s_gmin;
-        __syncthreads();
-        if (total != 0 || g == INF_BITS) break;
-        bound = __longlong_as_double((long long)g) + a.delta;  // open the next cost window
-        windows++;
-      }
-      if (total == 0) break;  // nothing active, nothing deferred: fixed point reached
-      rounds++;
-
-      // ---- pass 2: every CTA ranks the schedulable tiles identically; I take ranks == grank (mod group size).
-      // Housekeeping for the tiles t == grank (mod group size): carry an unscheduled tile's minimum over to the
-      // next round's table and zero the activity buffer of the round after.
-      uint32_t base_rank = 0;
-      for (int t0 = 0; t0 < n_tiles; t0 += THREADS) {
-        const int t = t0 + tid;
-        bool on = false;
-        if (t < n_tiles) {
-          const uint32_t af = __ldcg(act_cur + t);
-          const unsigned long long pm = __ldcg(pm_cur + t);
-          on = af != 0 || __longlong_as_double((long long)pm) < bound;
-          if (t % a.group_size == grank) {
-            if (!on) __stcg(pm_next + t, pm);
-            __stcg(act_clr + t, 0u);
-          }
-        }
-        const uint32_t b = __ballot_sync(FULL, on);
-        if (lane == 0) s_warp_cnt[wid] = __popc(b);
-        if (tid == 0) s_mine = 0;
-        __syncthreads();
-        uint32_t pre = base_rank, chunk = 0;
-        for (int w = 0; w < THREADS / 32; w++) {
-          const uint32_t cw = s_warp_cnt[w];
-          if (w < wid) pre += cw;
-          chunk += cw;
-        }
-        if (on) {
-          const uint32_t rank = pre + __popc(b & ((1u << lane) - 1u));
-          if ((int)((rank + round) % (uint32_t)a.group_size) == grank) s_list[atomicAdd(&s_mine, 1u)] = (uint32_t)t;
-        }
-        base_rank += chunk;
-        __syncthreads();
-        const uint32_t mine = s_mine;
-
-        // ---- process my tiles of this chunk
-        for (uint32_t k = 0; k < mine; k++) {
-          const int tile = (int)s_list[k];
-          const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-          const int x0 = tx * T, y0 = ty * T;
-          visits++;
-          PF_MARK(0);
-          // stage costs (+ halo); out-of-bounds cells hold the initial value and are never free
-          for (int i = tid; i < ROWS * (T + 2); i += THREADS) {
-            const int r = i / (T + 2), c = i - r * (T + 2);
-            const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-            double v = wt.init;
-            uint8_t k8 = CLS_BLOCKED | 9;
-            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-              v = __ldcg(cost + (size_t)gy * W + gx);
-              if (VARIANT == HPP_VARIANT_DUBINS) k8 = a.cls[(size_t)gy * W + gx];
-            }
-            cs_nv[r * S + c + 1] = v;
-            if (VARIANT == HPP_VARIANT_DUBINS) cl_nv[r * S + c + 1] = k8;
-          }
-          s_inc[tid] = 0;
-          if (tid == 0) {
-            s_out = 0;
-            s_minp[0] = INF_BITS;
-            s_minp[1] = INF_BITS;
-          }
-          // my row's masks
-          blk_state st;
-          {
-            const int gy = y0 + by * HB + lane, wx = (x0 >> 5) + bx;
-            uint32_t ob = 0xffffffffu, nb = 0;
-            if (gy < H && wx < a.pitch) {
-              ob = a.occ_bits[(size_t)gy * a.pitch + wx];
-              nb = a.near_bits[(size_t)gy * a.pitch + wx];
-              const int rem = W - (wx << 5);
-              if (rem < 32) ob |= ~((1u << rem) - 1u);
-            }
-            st.freem = ~ob;
-            st.nearm = nb;
-            st.need = 0;
-            st.dirty = 0;
-            st.posted = 0;
-            st.c_heavy = st.c_sparse = st.c_on = st.c_imp = st.c_sweeps = 0;
-            st.defer = __ldcg(dmask + ((size_t)tile * NBLK + wid) * 32 + lane);
-          }
-          const uint32_t af = __ldcg(act_cur + tile);
-          __syncthreads();
-          PF_MARK(1);
-          // ring cells facing a neighbour tile that posted a border change
-          if (af) {
-            if ((af & DIR_N) && by == 0 && lane == 0) st.need |= st.freem;
-            if ((af & DIR_S) && by == NB - 1 && lane == 31) st.need |= st.freem;
-            if ((af & DIR_W) && bx == 0) st.need |= st.freem & 1u;
-            if ((af & DIR_E) && bx == NB - 1) st.need |= st.freem & 0x80000000u;
-            if ((af & DIR_NW) && bx == 0 && by == 0 && lane == 0) st.need |= st.freem & 1u;
-            if ((af & DIR_NE) && bx == NB - 1 && by == 0 && lane == 0) st.need |= st.freem & 0x80000000u;
-            if ((af & DIR_SW) && bx == 0 && by == NB - 1 && lane == 31) st.need |= st.freem & 1u;
-            if ((af & DIR_SE) && bx == NB - 1 && by == NB - 1 && lane == 31) st.need |= st.freem & 0x80000000u;
-          }
-          // ---- relax to the tile-local fixed point under the bound, in sub-windows of delta_in: changes whose cost
-          // is >= lb wait in the deferred masks until the tile has nothing cheaper left, then lb moves to (cheapest
-          // deferred cost) + delta_in.  This is delta-stepping inside the tile: it keeps the front thin and close
-          // to cost order, so a cell is improved about once instead of twice.
-          double lb = 0.0;  // first pass: only the ring cells flagged by the neighbour tiles are evaluated
-          unsigned long long gmin_left = INF_BITS;
-          for (int it = 0;; it++) {
-            // (a warp that posted votes to continue: the receiver may already be waiting at the barrier)
-            for (;;) {
-              for (int k2 = 0; k2 < PHASE_SWEEPS; k2++) {
-                if (!sweep<NB, VARIANT>(cs, cl, s_inc, &s_out, st, wid, bx, by, lane, lb, wt)) break;
-                if (wid == 0) sweeps++;
-              }
-              const int more = __syncthreads_or((st.need != 0) || st.posted);
-              st.posted = 0;
-              pf[6]++;
-              if (!more) break;
-            }
-            // cheapest deferred cell of the tile
-            const int ebase = (by * HB + 1) * S + bx * HB + 2;
-            unsigned long long mn = INF_BITS;
-            for (uint32_t m = st.defer; m; m &= m - 1) {
-              const int x = __ffs(m) - 1;
-              const unsigned long long v = (unsigned long long)__double_as_longlong(cs[ebase + lane * S + x]);
-              mn = v < mn ? v : mn;
-            }
-            for (int d = 16; d; d >>= 1) {
-              const unsigned long long o = __shfl_xor_sync(FULL, mn, d);
-              mn = o < mn ? o : mn;
-            }
-            if (lane == 0 && mn != INF_BITS) atomicMin(&s_minp[it & 1], mn);
-            __syncthreads();
-            gmin_left = s_minp[it & 1];
-            if (tid == 0) s_minp[(it + 1) & 1] = INF_BITS;
-            const double gm = __longlong_as_double((long long)gmin_left);
-            if (gmin_left == INF_BITS || !(gm < bound)) break;
-            lb = gm + a.delta_in;
-            if (lb > bound) lb = bound;
-            // release the deferred cells that fell below lb
-            uint32_t rel = 0;
-            push3 ps = {0ull, 0ull, 0ull};
-            for (uint32_t m = st.defer; m; m &= m - 1) {
-              const int x = __ffs(m) - 1;
-              if (cs[ebase + lane * S + x] < lb) {
-                rel |= 1u << x;
-                add_push(ps, x, 0xffu);  // all eight neighbours: the exact set is not known any more
-              }
-            }
-            st.defer &= ~rel;
-            __syncwarp();
-            if (__any_sync(FULL, rel != 0)) propagate<NB>(ps, st, s_inc, &s_out, bx, by, lane);
-          }
-          if (a.prof) {
-            unsigned long long *pw = a.prof + (size_t)gridDim.x * 8;
-            if (lane == 0) {
-              atomicAdd(pw + 0, (unsigned long long)st.c_heavy);
-              atomicAdd(pw + 1, (unsigned long long)st.c_sparse);
-              atomicAdd(pw + 4, (unsigned long long)st.c_sweeps);
-            }
-            atomicAdd(pw + 2, (unsigned long long)st.c_on);
-            atomicAdd(pw + 3, (unsigned long long)st.c_imp);
-            const unsigned long long d = (unsigned long long)(clock64() - tk);
-            if (d > pf[7]) pf[7] = d;
-            pf[5]++;
-          }
-          PF_MARK(2);
-          // ---- write back: changed rows, deferred masks, cheapest deferred cost, notifications
-          {
-            const int ebase = (by * HB + 1) * S + bx * HB + 2;
-            __stcg(dmask + ((size_t)tile * NBLK + wid) * 32 + lane, st.defer);
-            uint32_t dr = __ballot_sync(FULL, st.dirty != 0);
-            const int gx = x0 + bx * HB + lane;
-            while (dr) {
-              const int r = __ffs(dr) - 1;
-              dr &= dr - 1;
-              const int gy = y0 + by * HB + r;
-              if (gx < W && gy < H) __stcg(cost + (size_t)gy * W + gx, cs[ebase + r * S + lane]);
-            }
-          }
-          __syncthreads();
-          if (tid == 0) {
-            __stcg(pm_next + tile, gmin_left);
-            const uint32_t o = s_out;
-            if (o) {
-              __threadfence();
-              // the neighbour must evaluate the ring side FACING us
-#pragma unroll
-              for (int d = 0; d < 8; d++) {
-                constexpr int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-                constexpr int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-                constexpr uint32_t facing[8] = {DIR_S, DIR_N, DIR_E, DIR_W, DIR_SE, DIR_SW, DIR_NE, DIR_NW};
-                if (o & (1u << d)) {
-                  const int nx = tx + ddx[d], ny = ty + ddy[d];
-                  if (nx >= 0 && nx < a.tiles_x && ny >= 0 && ny < a.tiles_y)
-                    atomicOr(act_next + ny * a.tiles_x + nx, facing[d]);
-                }
-              }
-            }
-          }
-          __syncthreads();
-          PF_MARK(3);
-        }
-      }
-      PF_MARK(0);
-      group_barrier(bar, a.group_size);
-      PF_MARK(4);
-    }
-#undef PF_MARK
-    if (a.prof && tid == 0)
-      for (int i = 0; i < 8; i++) a.prof[blockIdx.x * 8 + i] = pf[i];
-    if (grank == 0 && tid == 0) {
-      uint32_t *s = a.stats + field * 4;
-      s[0] = rounds;
-      s[2] = windows;
-      s[3] = sweeps;
-    }
-    if (tid == 0 && visits) atomicAdd(a.stats + field * 4 + 1, visits);
-    // the next field of this group reuses the barrier; everybody left the round loop on the same round
-  }
 }
 
 // ---------------------------------------------------------------- TMA (bulk async copy) + mbarrier helpers
@@ -1010,15 +494,10 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
       if ((af & DIR_SW) && lane == 31) st.need |= st.freem & 1u;
       if ((af & DIR_SE) && lane == 31) st.need |= st.freem & 0x80000000u;
     }
-    // relax under the bound in sub-windows (see heur_persist_kernel); everything is warp-local
+    // relax under the bound in sub-windows; everything is warp-local
     const int ebase = S + 2;
     auto run_sweeps = [&](double lb) {
-      if (a.compact) {
-        while (sweep_compact<VARIANT>(cs, cl, wc.aux, wc.s_out, st, lane, lb, wt)) {
-        }
-      } else {
-        while (sweep<1, VARIANT>(cs, cl, nullptr, wc.s_out, st, 0, 0, 0, lane, lb, wt)) {
-        }
+      while (sweep_compact<VARIANT>(cs, cl, wc.aux, wc.s_out, st, lane, lb, wt)) {
       }
     };
     // One pass over my row's deferred cells: those below lb are released (returned mask), the cheapest of the others
@@ -1111,8 +590,8 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
 }
 
 // ---------------------------------------------------------------- the warp-tile kernel (T = 32: one warp per tile)
-// Same scheduling protocol as heur_persist_kernel (cost windows, activity flags, deferred minima, one group barrier
-// per round), but a tile is a single 32x32 block solved by ONE warp with no block-level barrier at all: the 16 warps
+// Scheduling protocol: cost windows, activity flags, deferred minima, one group barrier per round; a tile is a single
+// 32x32 block solved by ONE warp with no block-level barrier at all: the 16 warps
 // of a CTA pull tiles of the round's schedule from a shared counter and never wait for each other inside a round.
 // This is the throughput configuration: with several fields in flight every warp of the GPU stays busy.
 // Warps (= tiles in flight) per CTA: 16 (123 registers) is the latency configuration; 20 (96 registers, 207 KB of
@@ -1314,7 +793,7 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
       // ---- schedule: one scan of the tile table builds my list of the round (ranks == grank mod group size,
       // rotated per round), counts the schedulable tiles and finds the global minimum of the deferred costs; when
       // nothing is schedulable the bound moves to that minimum + delta and the scan is repeated.  Housekeeping for
-      // the tiles t == grank (mod group size), as in heur_persist_kernel: carry an unscheduled tile's minimum over
+      // the tiles t == grank (mod group size): carry an unscheduled tile's minimum over
       // to the next round's table, zero the activity buffer of the round after (both idempotent under a re-scan:
       // a tile that becomes schedulable overwrites its minimum when it is processed).
       const bool solo = a.group_size == 1;
@@ -1503,232 +982,6 @@ __global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __gri
     if (lane == 0 && visits) atomicAdd(a.stats + field * 4 + 1, visits);
   }
 }
-
-// ---------------------------------------------------------------- the asynchronous kernel (one field, all SMs)
-// Latency configuration for a lone field.  Same tile visits as heur_warp_kernel, but no rounds: every warp of the GPU
-// pops tiles from one ring queue and pushes the neighbour tiles whose halo it changed, so nobody waits for the slowest
-// tile of a round.  Only the cost window still needs agreement: a counter of tiles that are queued or being visited
-// reaches zero exactly when the window is exhausted; the warp that brings it to zero scans the deferred minima, opens
-// the next window and queues the tiles that fall into it (or raises `done`).
-//   tile state word: DIR_* flags (ring sides to re-evaluate) | AQ_QUEUED | AQ_BUSY
-//     post(t, dir):  old = atomicOr(state[t], dir | QUEUED);  neither QUEUED nor BUSY before -> pending++, push(t)
-//     pop:           state[t] <- BUSY (one CAS: takes the flags, clears QUEUED)
-//     release:       old = atomicAnd(state[t], ~BUSY);  QUEUED set meanwhile -> push(t), else pending--
-// A tile is in the queue at most once, so a ring of >= n_tiles slots cannot overflow.  Launched cooperatively (all
-// warps resident: a popper may wait for the pusher of its slot).
-constexpr uint32_t AQ_QUEUED = 256u, AQ_BUSY = 512u, AQ_EMPTY = 0xffffffffu;
-enum { AQ_HEAD = 0, AQ_TAIL = 1, AQ_PENDING = 2, AQ_DONE = 3, AQ_WINDOWS = 4, AQ_VISITS = 5, AQ_BOUND = 6 /* 2 words */,
-       AQ_HDR = 32 };
-
-__device__ __forceinline__ void aq_push(uint32_t *ctl, uint32_t *ring, uint32_t mask, uint32_t tile) {
-  const uint32_t slot = atomicAdd(ctl + AQ_TAIL, 1u) & mask;
-  __stcg(ring + slot, tile);
-}
-
-template <int VARIANT, int WT_WARPS>
-__global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_async_kernel(const __grid_constant__ heur_args a) {
-  using C = tile_cfg<1>;
-  constexpr int S = C::S, ROWS = C::ROWS;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *cs_all = (double *)smem_raw;
-  uint8_t *cl_all = (uint8_t *)(cs_all + WT_WARPS * WSLOT_DOUBLES);
-  warp_aux *aux_all = (warp_aux *)(cl_all + (VARIANT == HPP_VARIANT_DUBINS ? WT_WARPS * ROWS * S : 0));
-  __shared__ uint32_t s_outw[WT_WARPS];
-  __shared__ double s_db[20];
-  __shared__ __align__(16) double2 s_rs[2];
-  __shared__ __align__(8) unsigned long long s_mbar[WT_WARPS];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int W = a.W, n_tiles = a.n_tiles;
-  if (tid < 20) s_db[tid] = a.wt.db[tid / 10][tid % 10];
-  if (tid < 2) s_rs[tid] = make_double2(a.wt.rs[tid][0], a.wt.rs[tid][1]);
-  eval_w wt;
-  wt.c0 = a.wt.rs[0][0];
-  wt.d0 = a.wt.rs[0][1];
-  wt.init = a.wt.init;
-  wt.rs = s_rs;
-  wt.db = s_db;
-  warp_ctx wc;
-  wc.cs_nv = cs_all + wid * WSLOT_DOUBLES;
-  wc.cl_nv = cl_all + wid * ROWS * S;
-  wc.aux = aux_all + wid;
-  for (int i = lane; i < (int)(sizeof(warp_aux) / 4); i += 32) ((uint32_t *)wc.aux)[i] = 0u;
-  wc.s_out = &s_outw[wid];
-  wc.mbar = smem_u32(&s_mbar[wid]);
-  wc.parity = 0;
-  if (lane == 0) mbar_init(wc.mbar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  wc.tma_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.cost_all) & 15) == 0);
-  wc.tma_2d = wc.tma_ok && a.tmap_ok && ((smem_u32(wc.cs_nv) & 127u) == 0u);
-  wc.field = 0;
-
-  uint32_t *ctl = a.aq;                     // control words
-  uint32_t *state = a.aq + AQ_HDR;          // [n_tiles]
-  uint32_t ring_size = 2;
-  while (ring_size < 2u * (uint32_t)n_tiles) ring_size <<= 1;  // twice the tiles: a slot is never reused while claimed
-  const uint32_t mask = ring_size - 1;
-  uint32_t *ring = state + n_tiles;         // [ring_size], AQ_EMPTY when free
-  unsigned long long *pmin = a.pmin;        // [n_tiles] (buffer 0 of the BSP layout)
-  double *cost = a.cost_all;
-  uint32_t *dmask = a.dmask;
-  volatile uint32_t *vctl = ctl;
-  uint32_t visits = 0;
-  unsigned idle = 0;
-
-  // CTA-local staging of popped tiles: only one warp per CTA at a time talks to the global queue (a storm of idle
-  // warps polling one cache line would slow every L2 access of the working warps); it claims up to AQ_FETCH tiles,
-  // keeps one and leaves the rest in a small shared-memory queue for the other idle warps of the CTA.
-  constexpr uint32_t AQ_FETCH = 4, LQ = 32;
-  __shared__ uint32_t s_lq[LQ];
-  __shared__ uint32_t s_lq_head, s_lq_tail, s_fetch_lock, s_done;
-  if (tid == 0) {
-    s_lq_head = 0;
-    s_lq_tail = 0;
-    s_fetch_lock = 0;
-    s_done = 0;
-  }
-  __syncthreads();
-  for (;;) {
-    // ---- pop
-    int tile = -1;
-    if (lane == 0) {
-      const uint32_t lh = *(volatile uint32_t *)&s_lq_head;
-      if (lh != *(volatile uint32_t *)&s_lq_tail) {
-        if (atomicCAS(&s_lq_head, lh, lh + 1u) == lh) tile = (int)((volatile uint32_t *)s_lq)[lh % LQ];
-      } else if (atomicCAS(&s_fetch_lock, 0u, 1u) == 0u) {
-        const uint32_t h = vctl[AQ_HEAD], t = vctl[AQ_TAIL];
-        uint32_t k = t - h;
-        if (k > AQ_FETCH) k = AQ_FETCH;
-        if (k != 0 && atomicCAS(ctl + AQ_HEAD, h, h + k) == h) {
-          for (uint32_t i = 0; i < k; i++) {
-            volatile uint32_t *slot = ring + ((h + i) & mask);
-            uint32_t v;
-            while ((v = *slot) == AQ_EMPTY) __nanosleep(20);  // the pusher took this slot and is about to write it
-            *slot = AQ_EMPTY;
-            if (i == 0) {
-              tile = (int)v;
-            } else {
-              const uint32_t lt = *(volatile uint32_t *)&s_lq_tail;
-              ((volatile uint32_t *)s_lq)[lt % LQ] = v;
-              __threadfence_block();
-              *(volatile uint32_t *)&s_lq_tail = lt + 1u;
-            }
-          }
-        } else if (k == 0 && vctl[AQ_DONE]) {
-          *(volatile uint32_t *)&s_done = 1u;
-        }
-        __threadfence_block();
-        atomicExch(&s_fetch_lock, 0u);
-      }
-    }
-    tile = __shfl_sync(FULL, tile, 0);
-    if (tile < 0) {
-      if (*(volatile uint32_t *)&s_done) break;
-      __nanosleep(idle < 8 ? 100 : 400);
-      idle++;
-      continue;
-    }
-    idle = 0;
-    // ---- take the tile: flags -> af, state <- BUSY
-    uint32_t af = 0;
-    if (lane == 0) {
-      uint32_t old = *(volatile uint32_t *)(state + tile);
-      for (;;) {
-        const uint32_t seen = atomicCAS(state + tile, old, AQ_BUSY);
-        if (seen == old) break;
-        old = seen;
-      }
-      af = old & 0xffu;
-      __threadfence();  // acquire: the poster's cost rows are visible before my staging reads
-    }
-    af = __shfl_sync(FULL, af, 0);
-    double bound;
-    {
-      const unsigned long long bb = *(volatile unsigned long long *)(ctl + AQ_BOUND);
-      bound = __longlong_as_double((long long)bb);
-    }
-    const unsigned long long left = warp_visit_tile<VARIANT>(a, cost, dmask, tile, af, bound, wt, wc, lane);
-    visits++;
-    // ---- publish: deferred minimum, neighbour posts, release
-    uint32_t ctrl = 0;
-    if (lane == 0) {
-      __stcg(pmin + tile, left);
-      const uint32_t o = ((volatile uint32_t *)s_outw)[wid];
-      __threadfence();  // release: my cost rows and pmin before the posts / the release below
-      if (o) {
-        const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-#pragma unroll
-        for (int d = 0; d < 8; d++) {
-          constexpr int ddx[8] = {0, 0, -1, 1, -1, 1, -1, 1};
-          constexpr int ddy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
-          constexpr uint32_t facing[8] = {DIR_S, DIR_N, DIR_E, DIR_W, DIR_SE, DIR_SW, DIR_NE, DIR_NW};
-          if (o & (1u << d)) {
-            const int nx = tx + ddx[d], ny = ty + ddy[d];
-            if (nx >= 0 && nx < a.tiles_x && ny >= 0 && ny < a.tiles_y) {
-              const int nb = ny * a.tiles_x + nx;
-              const uint32_t old = atomicOr(state + nb, facing[d] | AQ_QUEUED);
-              if (!(old & (AQ_QUEUED | AQ_BUSY))) {
-                atomicAdd(ctl + AQ_PENDING, 1u);
-                aq_push(ctl, ring, mask, (uint32_t)nb);
-              }
-            }
-          }
-        }
-      }
-      const uint32_t old = atomicAnd(state + tile, ~AQ_BUSY);
-      if (old & AQ_QUEUED) aq_push(ctl, ring, mask, (uint32_t)tile);  // posted to while busy: still pending
-      else if (atomicSub(ctl + AQ_PENDING, 1u) == 1u) ctrl = 1;
-    }
-    ctrl = __shfl_sync(FULL, ctrl, 0);
-    // ---- the window is exhausted and my warp is the only one doing anything: open the next window.
-    // (a guard count keeps `pending` above zero until every tile of the new window is queued)
-    while (ctrl) {
-      if (lane == 0) atomicAdd(ctl + AQ_PENDING, 1u);
-      unsigned long long g = INF_BITS;
-#pragma unroll 4
-      for (int t = lane; t < n_tiles; t += 32) {
-        const unsigned long long pm = __ldcg(pmin + t);
-        g = pm < g ? pm : g;
-      }
-      for (int d = 16; d; d >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(FULL, g, d);
-        g = o < g ? o : g;
-      }
-      if (g == INF_BITS) {
-        if (lane == 0) {
-          __threadfence();
-          vctl[AQ_DONE] = 1u;
-        }
-        break;
-      }
-      const double nbound = __longlong_as_double((long long)g) + a.delta;
-      if (lane == 0) {
-        *(volatile unsigned long long *)(ctl + AQ_BOUND) = (unsigned long long)__double_as_longlong(nbound);
-        __threadfence();
-        atomicAdd(ctl + AQ_WINDOWS, 1u);
-      }
-      __syncwarp();
-#pragma unroll 4
-      for (int t = lane; t < n_tiles; t += 32) {
-        const unsigned long long pm = __ldcg(pmin + t);
-        if (__longlong_as_double((long long)pm) < nbound) {
-          const uint32_t o2 = atomicOr(state + t, AQ_QUEUED);
-          if (!(o2 & (AQ_QUEUED | AQ_BUSY))) {
-            atomicAdd(ctl + AQ_PENDING, 1u);
-            aq_push(ctl, ring, mask, (uint32_t)t);
-          }
-        }
-      }
-      __syncwarp();
-      uint32_t again = 0;
-      if (lane == 0) again = atomicSub(ctl + AQ_PENDING, 1u) == 1u;  // everything queued was already finished
-      ctrl = __shfl_sync(FULL, again, 0);
-    }
-    __syncwarp();
-  }
-  if (lane == 0 && visits) atomicAdd(ctl + AQ_VISITS, visits);
-}
-
 // ---------------------------------------------------------------- init / seed / stats
 __global__ void __launch_bounds__(256) heur_init_kernel(double *__restrict__ cost, size_t total, double init,
                                                         unsigned long long *__restrict__ pmin, size_t n_pmin) {
@@ -1756,21 +1009,6 @@ __global__ void heur_seed_kernel(double *__restrict__ cost, size_t n, size_t n_f
 }
 
 // async kernel: control words, the goal tile queued, the first window open (state and ring are memset by the host)
-template <int NB>
-__global__ void heur_async_seed_kernel(uint32_t *__restrict__ aq, const int32_t *__restrict__ goal_xy, int tiles_x,
-                                       int n_tiles, double delta) {
-  constexpr int T = tile_cfg<NB>::T;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const int tile = (goal_xy[1] / T) * tiles_x + goal_xy[0] / T;
-  for (int i = 0; i < AQ_HDR; i++) aq[i] = 0;
-  aq[AQ_TAIL] = 1;
-  aq[AQ_PENDING] = 1;
-  aq[AQ_WINDOWS] = 1;
-  *(unsigned long long *)(aq + AQ_BOUND) = (unsigned long long)__double_as_longlong(delta);
-  aq[AQ_HDR + tile] = AQ_QUEUED;
-  aq[AQ_HDR + n_tiles] = (uint32_t)tile;  // ring[0]
-}
-
 // reachable count / max finite cost per field
 __global__ void __launch_bounds__(256) heur_stats_kernel(const double *__restrict__ cost, size_t n, double limit,
                                                          unsigned long long *__restrict__ out /* [f][2] */) {
@@ -1817,14 +1055,6 @@ void make_weights(int variant, heur_weights *w) {
   w->init = (variant == HPP_VARIANT_RS) ? INFINITY : 1000.0;
 }
 
-template <int NB>
-size_t heur_smem_bytes(int variant) {
-  using C = tile_cfg<NB>;
-  size_t b = sizeof(double) * C::ROWS * C::S + sizeof(uint32_t) * (C::NBLK * 32 + C::THREADS);
-  if (variant == HPP_VARIANT_DUBINS) b += (size_t)C::ROWS * C::S;
-  return b + 16;
-}
-
 double env_double(const char *name, double dflt) {
   const char *s = getenv(name);
   return (s && *s) ? atof(s) : dflt;
@@ -1845,20 +1075,15 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   const int threads = NB == 1 ? WT_WARPS * 32 : C::THREADS;
   size_t smem;
   const void *kern;
-  if constexpr (NB == 1) {
-    smem = (size_t)WT_WARPS * (WSLOT_DOUBLES * sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? C::ROWS * C::S : 0) + sizeof(warp_aux)) + 128;
-    kern = small ? (const void *)heur_warp_kernel<VARIANT, 4>
-                 : (many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
-                         : (const void *)heur_warp_kernel<VARIANT, 16>);
-  } else {
-    smem = heur_smem_bytes<NB>(VARIANT);
-    kern = (const void *)heur_persist_kernel<NB, VARIANT>;
-  }
+  smem = (size_t)WT_WARPS * (WSLOT_DOUBLES * sizeof(double) + (VARIANT == HPP_VARIANT_DUBINS ? C::ROWS * C::S : 0) + sizeof(warp_aux)) + 128;
+  kern = small ? (const void *)heur_warp_kernel<VARIANT, 4>
+               : (many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
+                       : (const void *)heur_warp_kernel<VARIANT, 16>);
   HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic kernel does not fit on an SM (%zu B shared)", smem);
-  const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", NB == 2 ? HPP_NB2_CTAS : (small ? 5 : 1));
+  const int per_sm_cap = (int)env_double("HPP_HEUR_CTAS_PER_SM", small ? 5 : 1);
   if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   const int G = per_sm * c->sm_count;  // co-resident CTAs
   // CTA groups: one field at a time per group, the groups never synchronise with each other.  A tile solve is a
@@ -1950,7 +1175,6 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   // window width: wide windows = fewer rounds (latency of a lone field), narrow = fewer re-evaluations (throughput)
   a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 768.0 : (n_fields < 64 ? 128.0 : 64.0)) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 32.0);
-  a.compact = (int)env_double("HPP_HEUR_COMPACT", 1);
   a.lpt = (int)env_double("HPP_HEUR_LPT", 1);
   // the fields as one (W, H, n_fields) fp64 tensor for the TMA: a tile with its halo is one 38 x 34 box.  Needs 16-byte
   // multiples for the row pitch (W even); anything else keeps the row-wise bulk copies / plain loads.
@@ -2000,51 +1224,14 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
                                                                                    a.pmin, a.dmask, tiles_x, n_tiles);
   HPP_LAUNCHED(c);
   const int hint = (int)env_double("HPP_HEUR_GROUP", 0);
-  // HPP_HEUR_ASYNC=1: a lone field through the asynchronous queue kernel (no rounds).  Off by default: it removes
-  // the wait for the slowest tile of a round, but visits tiles eagerly (1.7x the visits: a tile is re-visited after
-  // every neighbour instead of once per round) and ends up level with the round-based kernel (19.6 vs 18.3 ms at
-  // 4096^2, 3.9 vs 4.1 ms at 1024^2): both are bound by the chain of dependent sweeps.
-  bool use_async = false;
-  if constexpr (NB == 1)
-    use_async = n_fields == 1 && hint == 0 && n_tiles >= 4 * c->sm_count && env_double("HPP_HEUR_ASYNC", 0) != 0;
-  if (use_async) {
-    if constexpr (NB == 1) {
-      uint32_t ring = 2;
-      while (ring < 2u * (uint32_t)n_tiles) ring <<= 1;
-      const size_t aq_b = sizeof(uint32_t) * ((size_t)AQ_HDR + n_tiles + ring);
-      void *qp;
-      s = hpp_scratch(c, 4, aq_b, &qp);
-      if (s != HPP_OK) return s;
-      a.aq = (uint32_t *)qp;
-      HPP_CUDA(c, cudaMemsetAsync(a.aq, 0, sizeof(uint32_t) * ((size_t)AQ_HDR + n_tiles), c->stream));
-      HPP_CUDA(c, cudaMemsetAsync(a.aq + AQ_HDR + n_tiles, 0xff, sizeof(uint32_t) * ring, c->stream));
-      heur_async_seed_kernel<NB><<<1, 32, 0, c->stream>>>(a.aq, d_goals, tiles_x, n_tiles, a.delta);
-      HPP_LAUNCHED(c);
-      const size_t smem = (size_t)16 * (WSLOT_DOUBLES * sizeof(double) + (variant == HPP_VARIANT_DUBINS ? C::ROWS * C::S : 0) + sizeof(warp_aux)) + 128;
-      const void *kern = variant == HPP_VARIANT_RS ? (const void *)heur_async_kernel<HPP_VARIANT_RS, 16>
-                                                   : (const void *)heur_async_kernel<HPP_VARIANT_DUBINS, 16>;
-      HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 0;
-      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 16 * 32, smem));
-      if (per_sm < 1) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic kernel does not fit on an SM (%zu B shared)", smem);
-      int grid_a = c->sm_count;
-      if (grid_a * 16 > n_tiles) grid_a = (n_tiles + 15) / 16;
-      a.group_size = grid_a;
-      a.n_groups = 1;
-      void *params[] = {&a};
-      HPP_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(grid_a), dim3(16 * 32), params, smem, c->stream));
-      HPP_LAUNCHED(c);
-      // stats words of field 0: [0] rounds (none), [1] visits, [2] windows
-      HPP_CUDA(c, cudaMemcpyAsync(a.stats + 1, a.aq + AQ_VISITS, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-      HPP_CUDA(c, cudaMemcpyAsync(a.stats + 2, a.aq + AQ_WINDOWS, sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-    }
-  } else {
-    s = (variant == HPP_VARIANT_RS) ? launch_persist<NB, HPP_VARIANT_RS>(c, a, hint)
-                                    : launch_persist<NB, HPP_VARIANT_DUBINS>(c, a, hint);
-    if (s != HPP_OK) return s;
-  }
+  // (an asynchronous tile-queue kernel for a lone field was tried in round 1: it removes the wait for the slowest tile
+  // of a round, but visits tiles eagerly -- 1.7x the visits -- and ended up level with the round-based kernel: both are
+  // bound by the chain of dependent sweeps)
+  s = (variant == HPP_VARIANT_RS) ? launch_persist<NB, HPP_VARIANT_RS>(c, a, hint)
+                                  : launch_persist<NB, HPP_VARIANT_DUBINS>(c, a, hint);
+  if (s != HPP_OK) return s;
 
-  if (debug && !use_async) {
+  if (debug) {
     const int grid = a.group_size * a.n_groups;
     std::vector<unsigned long long> hp((size_t)grid * 8 + 8);
     HPP_CUDA(c, cudaMemcpyAsync(hp.data(), a.prof, hp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -2070,9 +1257,8 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
     HPP_CUDA(c, cudaMemcpyAsync(h_stats, a.stats, n_fields * 16, cudaMemcpyDeviceToHost, c->stream));
     HPP_CUDA(c, cudaStreamSynchronize(c->stream));
     for (size_t f = 0; f < n_fields && f < 4; f++)
-      fprintf(stderr, "[hpp heur] NB=%d%s delta=%g groups=%d x %d CTAs, field %zu: rounds=%u visits=%u windows=%u\n", NB,
-              use_async ? " async" : "", a.delta, a.n_groups, a.group_size, f, h_stats[4 * f], h_stats[4 * f + 1],
-              h_stats[4 * f + 2]);
+      fprintf(stderr, "[hpp heur] delta=%g groups=%d x %d CTAs, field %zu: rounds=%u visits=%u windows=%u\n", a.delta,
+              a.n_groups, a.group_size, f, h_stats[4 * f], h_stats[4 * f + 1], h_stats[4 * f + 2]);
   }
   if (reports) {
     uint32_t *h_stats = (uint32_t *)((uint8_t *)h_stage + goals_b);
@@ -2116,15 +1302,7 @@ extern "C" hpp_status hpp_heuristic_batch_dev(hpp_map *m, int variant, const int
                f, W, H);
   if (n_fields > 65535) HPP_FAIL(c, HPP_ERR_ARG, "at most 65535 fields per call");
   HPP_CUDA(c, cudaSetDevice(c->device));
-  // Tile side.  Default: 32, one warp per tile (heur_warp_kernel): no barrier inside a tile, TMA-staged tiles, every
-  // warp of the GPU busy when several fields are in flight, and also the lowest single-field latency measured.
-  // HPP_HEUR_NB=2|4 selects the multi-warp tile kernel (64x64 / 128x128 tiles, heur_persist_kernel) instead.
-  int nb = 1;
-  const int env_nb = (int)env_double("HPP_HEUR_NB", 0);
-  if (env_nb == 1 || env_nb == 2 || env_nb == 4) nb = env_nb;
-  if (nb == 1) return run_batch<1>(m, variant, goal_xy, n_fields, cost_dev, reports);
-  return nb == 4 ? run_batch<4>(m, variant, goal_xy, n_fields, cost_dev, reports)
-                 : run_batch<2>(m, variant, goal_xy, n_fields, cost_dev, reports);
+  return run_batch<1>(m, variant, goal_xy, n_fields, cost_dev, reports);
 }
 
 // host-buffer batch: n_fields goal cells on one map, fields returned in cost (n_fields x W*H doubles, pinned memory

@@ -210,44 +210,31 @@ def test_heuristic_batch_host_chunks(ctx, variant):
     m.close()
 
 
-def test_heuristic_all_tile_kernels_agree(ctx, monkeypatch):
-    """the three tile configurations (32: warp-tile kernel with TMA staging; 64 / 128: multi-warp tile kernel) and both
-    window settings give the same bits on even- and odd-width maps (odd widths take the non-TMA staging path)"""
+def test_heuristic_window_widths_and_staging_paths_agree(ctx, monkeypatch):
+    """narrow and unbounded cost windows give the same bits on even- and odd-width maps (odd widths take the plain-load
+    staging path, even ones the TMA tensor box copy), RS and Dubins, and on a 1024^2 cfg3-style map"""
     import hybrid_path_planning_b200 as hpp
     from oracle import pyorc as O
     for W, H in ((330, 257), (331, 120)):
         occ = block_map(W, H, 0.25, 5, seed=W)
         occ[H // 2, W // 2] = 0
         want = O.heuristic_rs(occ, (W // 2, H // 2), (0, 0), quirks=False)[0]
+        wantd = O.heuristic_dubins(occ, (W // 2, H // 2))
         m = hpp.Map(ctx, occ, 0.2)
-        for nb in ("1", "2", "4"):
-            for delta in ("24", "1000000"):
-                monkeypatch.setenv("HPP_HEUR_NB", nb)
-                monkeypatch.setenv("HPP_HEUR_DELTA", delta)
-                got, _ = m.heuristic_rs((W // 2, H // 2), (0, 0))
-                assert bits_equal(got, want), (W, H, nb, delta)
+        for delta in ("24", "1000000"):
+            monkeypatch.setenv("HPP_HEUR_DELTA", delta)
+            got, _ = m.heuristic_rs((W // 2, H // 2), (0, 0))
+            assert bits_equal(got, want), (W, H, delta)
+            gotd, _ = m.heuristic_dubins((W // 2, H // 2))
+            assert bits_equal(gotd, wantd), (W, H, delta)
         m.close()
-
-
-def test_heuristic_async_queue_kernel(ctx, monkeypatch):
-    """HPP_HEUR_ASYNC=1: the asynchronous tile-queue kernel (one field, no rounds) gives the same bits as the oracle"""
-    import hybrid_path_planning_b200 as hpp
-    from oracle import pyorc as O
+    monkeypatch.delenv("HPP_HEUR_DELTA")
     occ, goal = cfg3_map(1024, seed=3)
     want = O.heuristic_rs(occ, goal, (0, 0), quirks=False)[0]
     m = hpp.Map(ctx, occ, 0.2)
-    monkeypatch.setenv("HPP_HEUR_ASYNC", "1")
-    for delta in ("256", "48"):
-        monkeypatch.setenv("HPP_HEUR_DELTA", delta)
-        got, rep = m.heuristic_rs(goal, (0, 0))
-        assert bits_equal(got, want), delta
-        assert rep.reachable == int(np.isfinite(want).sum())
-    wantd = O.heuristic_dubins(occ[:700, :900], (450, 350))
-    m2 = hpp.Map(ctx, occ[:700, :900], 0.2)
-    gotd, _ = m2.heuristic_dubins((450, 350))
-    assert bits_equal(gotd, wantd)
+    got, rep = m.heuristic_rs(goal, (0, 0))
+    assert bits_equal(got, want) and rep.reachable == int(np.isfinite(want).sum())
     m.close()
-    m2.close()
 
 
 def test_heuristic_one_cta_per_field_list_schedule(ctx, monkeypatch):
@@ -288,10 +275,10 @@ def test_heuristic_one_cta_per_field_list_schedule(ctx, monkeypatch):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-def test_heuristic_sweep_modes_and_cta_shapes_agree(ctx, monkeypatch, variant):
-    """the warp-tile kernel's two sweep forms (HPP_HEUR_COMPACT=1: needed cells compacted over the lanes, =0: row-wise),
-    every sub-window width, and the 4-warp CTAs that big batches on small maps use (HPP_HEUR_WARPS=4) give the oracle's
-    bits -- on a map with long straight fronts (empty), thin diagonal ones (blocks) and an odd width (no TMA staging)"""
+def test_heuristic_subwindows_staging_and_cta_shapes_agree(ctx, monkeypatch, variant):
+    """every sub-window width, the row-wise bulk-copy staging and the 4-warp CTAs that big batches on small maps use
+    (HPP_HEUR_WARPS=4) give the oracle's bits -- on a map with long straight fronts (empty), thin diagonal ones (blocks)
+    and an odd width (no TMA staging)"""
     import hybrid_path_planning_b200 as hpp
     from oracle import pyorc as O
     cases = [(np.zeros((96, 130), np.int8), (5, 90)), (block_map(161, 131, 0.2, 4, seed=7), (80, 65)),
@@ -301,14 +288,11 @@ def test_heuristic_sweep_modes_and_cta_shapes_agree(ctx, monkeypatch, variant):
         occ[goal[1], goal[0]] = 0
         want = O.heuristic_rs(occ, goal, (0, 0), quirks=False)[0] if variant == 0 else O.heuristic_dubins(occ, goal)
         m = hpp.Map(ctx, occ, 0.2)
-        for compact in ("1", "0"):
-            for din in ("4", "32", "1000"):
-                monkeypatch.setenv("HPP_HEUR_COMPACT", compact)
-                monkeypatch.setenv("HPP_HEUR_DELTA_IN", din)
-                got = m.heuristic_rs(goal, (0, 0))[0] if variant == 0 else m.heuristic_dubins(goal)[0]
-                assert bits_equal(got, want), (occ.shape, compact, din)
+        for din in ("4", "32", "1000"):
+            monkeypatch.setenv("HPP_HEUR_DELTA_IN", din)
+            got = m.heuristic_rs(goal, (0, 0))[0] if variant == 0 else m.heuristic_dubins(goal)[0]
+            assert bits_equal(got, want), (occ.shape, din)
         monkeypatch.delenv("HPP_HEUR_DELTA_IN")
-        monkeypatch.setenv("HPP_HEUR_COMPACT", "1")
         monkeypatch.setenv("HPP_HEUR_TMA2D", "0")       # row-wise bulk copies instead of one tensor box copy per tile
         got = m.heuristic_rs(goal, (0, 0))[0] if variant == 0 else m.heuristic_dubins(goal)[0]
         assert bits_equal(got, want), (occ.shape, "row-wise TMA staging")
