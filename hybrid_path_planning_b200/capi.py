@@ -1,5 +1,6 @@
 """ctypes binding of include/hpp_b200.h (plumbing for tests and bench.py; not a compute path)."""
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -265,8 +266,17 @@ class Context:
         return dict(length=length.value, mode=mode.raw[:3].decode().rstrip("\0"), x=samples[:m, 0].copy(),
                     y=samples[:m, 1].copy(), yaw=samples[:m, 2].copy())
 
+    def _adopt(self, child):
+        """maps and communicators live inside the context: they are closed before it, whatever order the interpreter
+        finalises the Python objects in (a map destroyed after its context would touch freed memory)"""
+        if not hasattr(self, "_children"):
+            self._children = weakref.WeakSet()
+        self._children.add(child)
+
     def close(self):
         if getattr(self, "h", None):
+            for child in list(getattr(self, "_children", ())):
+                child.close()
             self.L.hpp_ctx_destroy(self.h)
             self.h = None
 
@@ -303,6 +313,7 @@ class Map:
         ctx.check(st)
         self.h = h
         self.n = self.W * self.H
+        ctx._adopt(self)
 
     def update(self, occ):
         occ = np.ascontiguousarray(occ, np.int8)
@@ -469,6 +480,7 @@ class Comm:
         idb = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
         ctx.check(self.L.hpp_comm_create(ctx.h, C.cast(idb, C.c_void_p), rank, world, C.byref(h)))
         self.h = h
+        ctx._adopt(self)
 
     def plan_batch_sharded(self, maps, map_of_query, variant, starts, goals, traj_cap=1 << 22):
         """all ranks pass the whole query list; returns (plan headers of ALL queries, this rank's trajectories, (lo, hi))"""

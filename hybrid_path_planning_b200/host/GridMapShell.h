@@ -19,7 +19,16 @@
 namespace hpp_host {
 
 // one hpp_ctx per (thread, GPU); device from $HPP_DEVICE (default 0).  Throws when there is no usable B200:
-// the product has no CPU path.
+// the product has no CPU path.  The context is reference counted: every map handle keeps it alive, so a Grid_map that
+// outlives the thread that created it (or is destroyed during process shutdown) never touches a freed context.  A
+// context -- and therefore a Grid_map and its copies -- must be used by one thread at a time.
+struct CtxHolder {
+  hpp_ctx *ctx = nullptr;
+  ~CtxHolder() {
+    if (ctx) hpp_ctx_destroy(ctx);
+  }
+};
+std::shared_ptr<CtxHolder> thread_ctx_ref();
 hpp_ctx *thread_ctx();
 [[noreturn]] void fail(hpp_ctx *ctx, hpp_status st, const char *what);
 inline void check(hpp_ctx *ctx, hpp_status st, const char *what) {
@@ -27,8 +36,14 @@ inline void check(hpp_ctx *ctx, hpp_status st, const char *what) {
 }
 
 struct MapHandle {
+  std::shared_ptr<CtxHolder> keep;  // released after the map is destroyed
   hpp_ctx *ctx = nullptr;
   hpp_map *map = nullptr;
+  // the vehicle / planner parameters the device map currently carries: every Grid_map copy (and every HybridAstar, which
+  // holds one) has its OWN parameters, as in the reference where the copies are independent objects; a copy pushes its
+  // parameters to the shared device map before a call whenever another copy's are installed (Grid_map::syncParams)
+  hpp_params installed{};
+  bool has_params = false;
   ~MapHandle() {
     if (map) hpp_map_destroy(map);
   }
@@ -53,9 +68,11 @@ class Grid_map {
   double getMaxOriginX() const { return Max_origin_x; }
   double getMaxOriginY() const { return Max_origin_y; }
 
-  // RS/src/Grid_map.cpp:217-220
+  // RS/src/Grid_map.cpp:217-220 (this copy only, like the reference's by-value Grid_map)
   void setcarData(const CarData &car_data);
   void setPlannerParams(const CarData &car_data, double pathLength, double step_car);
+  // installs this copy's parameters on the shared device map if another copy's are there (host-side, no device work)
+  void syncParams() const;
   // RS/src/Grid_map.cpp:239-284: true = collision or outside the map (hazard H5: the name says the opposite)
   bool isSingleStateCollisionFree(const State &current);
   // RS/src/Grid_map.cpp:286-317 (bounding-circle pre-filter; the reference's own, different, return convention)

@@ -10,21 +10,19 @@
 
 namespace hpp_host {
 
-hpp_ctx *thread_ctx() {
-  struct Holder {
-    hpp_ctx *ctx = nullptr;
-    ~Holder() {
-      if (ctx) hpp_ctx_destroy(ctx);
-    }
-  };
-  static thread_local Holder h;
-  if (!h.ctx) {
+std::shared_ptr<CtxHolder> thread_ctx_ref() {
+  static thread_local std::shared_ptr<CtxHolder> h;
+  if (!h) {
+    auto fresh = std::make_shared<CtxHolder>();
     const char *d = std::getenv("HPP_DEVICE");
-    const hpp_status st = hpp_ctx_create(d ? std::atoi(d) : 0, &h.ctx);
+    const hpp_status st = hpp_ctx_create(d ? std::atoi(d) : 0, &fresh->ctx);
     if (st != HPP_OK) throw std::runtime_error("hpp_ctx_create failed: no usable B200 (there is no CPU fallback)");
+    h = fresh;
   }
-  return h.ctx;
+  return h;
 }
+
+hpp_ctx *thread_ctx() { return thread_ctx_ref()->ctx; }
 
 void fail(hpp_ctx *ctx, hpp_status st, const char *what) {
   throw std::runtime_error(std::string(what) + ": status " + std::to_string((int)st) + ": " + hpp_last_error(ctx));
@@ -46,10 +44,14 @@ void Grid_map::init(const int8_t *occ, std::size_t n, uint32_t w, uint32_t h, fl
   Max_origin_y = originY + height * resolution;
   occ_ = std::make_shared<std::vector<int8_t>>(occ, occ + n);
   auto handle = std::make_shared<hpp_host::MapHandle>();
-  handle->ctx = hpp_host::thread_ctx();
+  handle->keep = hpp_host::thread_ctx_ref();
+  handle->ctx = handle->keep->ctx;
   // default vehicle until setcarData (the reference's Grid_map also starts with a default-constructed CarData)
-  const hpp_params p = CarData(0.6, 2.75, 1.1, 1.2, 1.9).params(path_length_, step_car_);
+  car_ = CarData(0.6, 2.75, 1.1, 1.2, 1.9);
+  const hpp_params p = car_.params(path_length_, step_car_);
   check(handle->ctx, hpp_map_create(handle->ctx, occ, w, h, res, ox, oy, &p, &handle->map), "hpp_map_create");
+  handle->installed = p;
+  handle->has_params = true;
   h_ = handle;
 }
 
@@ -59,12 +61,20 @@ void Grid_map::setPlannerParams(const CarData &car_data, double pathLength, doub
   car_ = car_data;
   path_length_ = pathLength;
   step_car_ = step_car;
+  if (h_) syncParams();  // reports unsupported parameters (e.g. pathLength > 8) here, where the reference's setter is called
+}
+
+void Grid_map::syncParams() const {
   if (!h_) return;
   const hpp_params p = car_.params(path_length_, step_car_);
+  if (h_->has_params && std::memcmp(&h_->installed, &p, sizeof p) == 0) return;
   check(h_->ctx, hpp_map_set_params(h_->map, &p), "hpp_map_set_params");
+  h_->installed = p;
+  h_->has_params = true;
 }
 
 bool Grid_map::isSingleStateCollisionFree(const State &s) {
+  syncParams();
   const double xyh[3] = {s.x, s.y, s.heading};
   uint8_t v = 1;
   check(h_->ctx, hpp_collide_circles(h_->map, xyh, 1, &v), "hpp_collide_circles");
@@ -72,6 +82,7 @@ bool Grid_map::isSingleStateCollisionFree(const State &s) {
 }
 
 bool Grid_map::isSingleStateCollisionFreeImproved(const State &s) {
+  syncParams();
   const double xyh[3] = {s.x, s.y, s.heading};
   uint8_t v = 0;
   check(h_->ctx, hpp_collide_improved(h_->map, xyh, 1, &v), "hpp_collide_improved");
@@ -79,6 +90,7 @@ bool Grid_map::isSingleStateCollisionFreeImproved(const State &s) {
 }
 
 bool Grid_map::checkCollisionSat(const State &s) {
+  syncParams();
   const double xyh[3] = {s.x, s.y, s.heading};
   uint8_t v = 1;
   check(h_->ctx, hpp_collide_sat(h_->map, xyh, 1, &v), "hpp_collide_sat");
@@ -137,6 +149,7 @@ std::vector<std::vector<State>> HybridAstarT<V>::run_batch(const std::vector<Sta
   std::vector<hpp_plan> plans(n);
   std::vector<double> traj;
   std::size_t cap = 4096 * n, used = 0;
+  grid_map_.syncParams();
   for (;;) {
     traj.resize(cap * 5);
     const hpp_status st =
@@ -172,6 +185,7 @@ std::vector<std::shared_ptr<planner::Node>> HybridAstarT<V>::GetnextNeighbours(
   const hpp_params p = car_data_.params(simulationLength, step_car);
   const int nc = hpp_num_commands(&p, V);
   std::vector<hpp_child> kids((std::size_t)nc);
+  grid_map_.syncParams();
   check(grid_map_.ctx(), hpp_expand(grid_map_.handle(), V, &in, 1, kids.data()), "hpp_expand");
   int sim = 0;
   while (sim < simulationLength && sim < HPP_MAX_SIM) sim++;
@@ -199,6 +213,7 @@ std::shared_ptr<planner::Node> HybridAstarT<V>::analyticShot(const std::shared_p
   hpp_shot shot;
   std::vector<double> samples;
   std::size_t cap = 8192, used = 0;
+  grid_map_.syncParams();
   for (;;) {
     samples.resize(cap * 5);
     const hpp_status st = (V == HPP_VARIANT_RS)
@@ -226,6 +241,7 @@ void HybridAstarT<V>::motionCommands() {
   const hpp_params p = car_data_.params(simulationLength, step_car);
   const int nc = hpp_num_commands(&p, V);
   std::vector<hpp_child> kids((std::size_t)nc);
+  grid_map_.syncParams();
   check(grid_map_.ctx(), hpp_expand(grid_map_.handle(), V, &in, 1, kids.data()), "hpp_expand");
   motionCommand.clear();
   for (const hpp_child &k : kids) motionCommand.push_back({k.steer, (double)k.direction});
@@ -245,6 +261,7 @@ double HybridAstarT<V>::PathCost(const std::shared_ptr<planner::Node> &cur, cons
   const hpp_params p = car_data_.params(simulationLength, step_car);
   const int nc = hpp_num_commands(&p, V);
   std::vector<hpp_child> kids((std::size_t)nc);
+  grid_map_.syncParams();
   check(grid_map_.ctx(), hpp_expand(grid_map_.handle(), V, &in, 1, kids.data()), "hpp_expand");
   for (const hpp_child &k : kids)  // the cost is filled for every command, colliding rollouts included
     if (k.steer == cmd[0] && (double)k.direction == cmd[1]) return k.cost;
