@@ -685,8 +685,10 @@ def extras(ctx, torch, hpp, stream, cpu_x, cfg5_dev):
         "roofline": {"bound": "hbm", "achieved": COLLIDE_BYTES_PER_POSE * npose / t / 1e9, "peak": peak,
                      "frac": COLLIDE_BYTES_PER_POSE * npose / t / 1e9 / peak, "unit": "GB/s",
                      "traffic": k4_traffic(),
-                     "note": "random 4-byte gathers cost whole DRAM sectors: the measured DRAM traffic (ncu) is 3.6x the "
-                             "algorithmic bytes and runs at 87 % of the measured HBM peak"},
+                     "note": "round 2: the taps read a compact squared-distance layer (one byte per cell, 8x4 micro-tiles): "
+                             "measured DRAM traffic (ncu) 0.60 GB = 0.67x the algorithmic bytes (round 1: 3.22 GB = 3.6x at "
+                             "87 % of the HBM peak); the kernel is now bound by its fp64 pipe (32 %) and issue slots, not by "
+                             "memory"},
         "e2e_checks_per_s": npose / t_e2e, "h2d_bytes": 24 * npose, "d2h_bytes": npose,
         "cpu": cpu4}
     m.close()
