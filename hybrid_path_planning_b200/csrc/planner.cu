@@ -672,6 +672,382 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------- pipelined RS planner
+// plan_kernel runs the phases of an iteration one after the other, and three quarters of an iteration of a long query is
+// the analytic shot (46 closed forms, ordered de-duplication, footprint checks of every candidate path).  But the shot of
+// a node is a pure function of the node's state, the goal and the map -- it does not look at the open or closed set --
+// and as long as shots FAIL the search does not look at them either.  So here the search runs ahead of its shots:
+//   warp 0 (the controller) runs HybridAstar::run's loop statement by statement -- pop, closed test, goal test,
+//       expansion, insert / replace, heap pushes -- assuming that every shot fails, and hands every popped node to the
+//       workers through a ring in shared memory;
+//   warps 1 .. (the workers) each take the next node of the ring and evaluate its whole shot alone;
+//   the controller retires the results IN POP ORDER: the first success ends the query at that node's iteration --
+//       exactly where the sequential loop would have ended, whatever the controller did beyond it (its later pops only
+//       appended nodes; the successful node's ancestors are untouched) -- and a loop that ends by the goal test, an empty
+//       open list, the iteration cap or an exhausted pool first waits for the shots of all earlier pops.
+// Results (iterations, via_shot, cost, trajectory) are those of plan_kernel; the chain of a long query shrinks from
+// pop + shot + expansion + insert + push to pop + expansion + insert + push.
+#define PIPE_RING 32
+struct pipe_job {
+  double x, y, h, cost;
+  int cur, iter;
+};
+struct pipe_res {
+  int state;  // 0 pending, 1 shot failed, 2 shot succeeded (payload below)
+  int n_samples, nseg, pad_;
+  double cost;
+  double len[5];
+  unsigned char typ[8];
+};
+struct pipe_worker {
+  rs_warp_smem S;
+  int verdict[RS_NCAND];
+  int next_path, any_free;
+};
+template <int NW>
+struct pipe_smem {
+  int query;
+  volatile int head;   // jobs published by the controller
+  int claim;           // jobs claimed by the workers
+  volatile int quit;
+  pipe_job job[PIPE_RING];
+  pipe_res res[PIPE_RING];
+  pipe_worker w[NW - 1];
+};
+
+template <int NW, int MIN_CTAS>
+__global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_consts pc, const plan_map_desc *__restrict__ descs,
+                                                            const int *__restrict__ map_of_query,
+                                                            const double *__restrict__ starts,
+                                                            const double *__restrict__ goals,
+                                                            const int *__restrict__ query_ids, int n_queries,
+                                                            const int *__restrict__ field_of_query,
+                                                            const double *__restrict__ fields,
+                                                            pnode *__restrict__ node_pool, double *__restrict__ key_pool,
+                                                            int *__restrict__ idx_pool, int *__restrict__ table_pool,
+                                                            hpp_plan *__restrict__ plans, double *__restrict__ traj,
+                                                            unsigned long long traj_cap,
+                                                            unsigned long long *__restrict__ cursor) {
+  constexpr int THREADS = NW * 32;
+  extern __shared__ __align__(16) unsigned char pipe_raw[];
+  pipe_smem<NW> &sm = *reinterpret_cast<pipe_smem<NW> *>(pipe_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned FULLM = 0xffffffffu;
+  const hpp_geom &g = pc.g;
+  const int W = g.W;
+  const long map_size = (long)W * g.H;
+  pnode *nodes = node_pool + (size_t)blockIdx.x * pc.max_nodes;
+  double *hkey = key_pool + (size_t)blockIdx.x * pc.max_nodes;
+  int *hidx = idx_pool + (size_t)blockIdx.x * pc.max_nodes;
+  int *table = table_pool + (size_t)blockIdx.x * (pc.table_mask + 1);
+  const int ncmd = pc.ec.n_cmd;
+  int *next_query = (int *)(cursor + 1);
+  for (;;) {
+    __syncthreads();  // the previous query is finished by every warp
+    if (tid == 0) {
+      sm.query = atomicAdd(next_query, 1);
+      sm.head = 0;
+      sm.claim = 0;
+      sm.quit = 0;
+    }
+    __syncthreads();
+    const int qi = sm.query;
+    if (qi >= n_queries) break;
+    const int q = query_ids[qi];
+    const double *hmap = fields + (size_t)field_of_query[qi] * map_size;
+    const plan_map_desc md = descs[map_of_query ? map_of_query[q] : 0];
+    const float *__restrict__ dist = md.dist;
+    const double gx = goals[3 * q], gy = goals[3 * q + 1], gh = goals[3 * q + 2];
+    for (int i = tid; i <= pc.table_mask; i += THREADS) table[i] = -1;
+    __syncthreads();
+
+    if (wid != 0) {
+      // ================================================================ worker: one whole shot per job
+      pipe_worker &me = sm.w[wid - 1];
+      for (;;) {
+        int c = 0;
+        if (lane == 0) {
+          c = atomicAdd(&sm.claim, 1);
+          while (c >= sm.head && !sm.quit) __nanosleep(100);
+          if (sm.quit) c = -1;  // the query is over (every shot that mattered has been retired)
+        }
+        c = __shfl_sync(FULLM, c, 0);
+        if (c < 0) break;
+        __threadfence_block();
+        const pipe_job jb = sm.job[c % PIPE_RING];
+        rs_generate(me.S, jb.x, jb.y, jb.h, gx, gy, gh, pc.maxc);
+        const int n_acc = me.S.n_acc;
+        rs_shot_result SR;
+        SR.found = 0; SR.chosen = -1; SR.n_samples = 0; SR.cand = -1; SR.cost = 0.0; SR.n_paths = n_acc;
+        if (n_acc > 0) {
+          int hit0 = 0;
+          // sample 0 of every candidate path is the start pose itself (x, y unchanged, pi_2_pi(yaw)): looked at once
+          if (lane == 0) {
+            hit0 = circles_collide_ilp(g, pc.cc, dist, jb.x, jb.y, pi_2_pi(0.0 + jb.h));
+            me.next_path = 0;
+            me.any_free = 0;
+          }
+          hit0 = __shfl_sync(FULLM, hit0, 0);
+          __syncwarp();
+          rs_check_paths_grouped<PLAN_PATH_GROUP>(me.S, n_acc, &me.next_path, me.verdict, &me.any_free, g, pc.cc, dist,
+                                                  jb.x, jb.y, jb.h, pc.maxc, hit0);
+          __syncwarp();
+          if (me.any_free) {
+            rs_order_paths(me.S, jb.cost, pc.maxc, pc.max_steer);
+            double best = INFINITY;
+            for (int o = 0; o < n_acc; o++)
+              if (rs_fold_path(me.S, o, me.verdict[me.S.order[o]], SR, best)) break;
+          }
+        }
+        if (lane == 0) {
+          pipe_res &r = sm.res[c % PIPE_RING];
+          if (SR.found) {
+            const int k = SR.cand;
+            r.n_samples = SR.n_samples;
+            r.nseg = me.S.nseg[k];
+            r.cost = SR.cost;
+            for (int i = 0; i < 5; i++) {
+              r.len[i] = me.S.len[k][i];
+              r.typ[i] = me.S.typ[k][i];
+            }
+          }
+          __threadfence_block();
+          *(volatile int *)&r.state = SR.found ? 2 : 1;
+        }
+        __syncwarp();
+      }
+      continue;  // next query (the controller does the back-track)
+    }
+
+    // ================================================================== controller (warp 0)
+    const double sx = starts[3 * q], sy = starts[3 * q + 1], sh = starts[3 * q + 2];
+    const int s_cx = (int)(hpp_div_res(g, sx - g.ox)), s_cy = (int)(hpp_div_res(g, sy - g.oy));
+    const int g_cx = (int)(hpp_div_res(g, gx - g.ox)), g_cy = (int)(hpp_div_res(g, gy - g.oy));
+    int n_nodes = 0, hn = 0, iterations = 0, status = 0;
+    int goal_node = -1, via_shot = 0, shot_samples = 0;
+    double shot_cost = 0.0;
+    int head = 0, retired = 0, win = -1;  // win: ring index of the first successful shot
+    const long start_index = (long)s_cy * W + s_cx;
+    if (start_index < 0 || start_index >= map_size) {
+      status = 2;  // the reference indexes goal_map_ out of range here (undefined behaviour)
+    } else {
+      if (lane == 0) {
+        pnode nd;
+        nd.x = sx; nd.y = sy; nd.h = sh; nd.cost = 0.0; nd.steer = 0.0; nd.parent = -1; nd.dir = 1; nd.cmd = -1; nd.pad = 0;
+        nodes[0] = nd;
+        int slot;
+        table_find(table, nodes, pc.table_mask, sx, sy, sh, slot);
+        table[slot] = 0;
+        gheap_push(hkey, hidx, hn, 0.0 + 30.0 * hmap[start_index], 0);
+      }
+      n_nodes = 1;
+      hn = 1;
+      __syncwarp();
+    }
+    // retires finished shots in pop order; returns true when one of them succeeded (win = its job index)
+    auto retire = [&]() {
+      for (;;) {
+        int st = 0;
+        if (lane == 0 && retired < head) st = *(volatile int *)&sm.res[retired % PIPE_RING].state;
+        st = __shfl_sync(FULLM, st, 0);
+        if (st == 0) return false;
+        if (st == 2) {
+          win = retired;
+          return true;
+        }
+        retired++;
+      }
+    };
+    int end_node = -1;  // node at which the loop itself ended by the goal test
+    while (status == 0 && hn > 0) {
+      if (retire()) break;
+      iterations++;
+      if (iterations > PLAN_ITER_CAP) break;
+      // ---- pop
+      const int top = gheap_pop_warp(hkey, hidx, hn);
+      int tv = 0;
+      if (lane == 0) {
+        int slot = 0;
+        const pnode &tn = nodes[top];
+        tv = table_find(table, nodes, pc.table_mask, tn.x, tn.y, tn.h, slot);
+        if (tv >= 0 && !(tv & 1)) table[slot] = tv | 1;  // openSet.erase + closedSet[currentState] = currentNode
+      }
+      tv = __shfl_sync(FULLM, tv, 0);
+      if (tv < 0 || (tv & 1)) continue;  // already in the closed set
+      const int cur = tv >> 1;
+      const pnode cn = nodes[cur];
+      // ---- the analytic shot of this node goes to the workers
+      while (head - retired >= PIPE_RING) {
+        if (retire()) break;
+        __nanosleep(100);
+      }
+      if (win >= 0) break;
+      if (lane == 0) {
+        pipe_job &jb = sm.job[head % PIPE_RING];
+        jb.x = cn.x; jb.y = cn.y; jb.h = cn.h; jb.cost = cn.cost; jb.cur = cur; jb.iter = iterations;
+        *(volatile int *)&sm.res[head % PIPE_RING].state = 0;
+        __threadfence_block();
+        sm.head = head + 1;
+      }
+      head++;
+      __syncwarp();
+      // ---- goal test (RS/src/HybridAstar.cpp:641-655)
+      {
+        double hd = fabs(cn.h - gh);
+        if (hd > PI_ASTAR) hd = fabs(hd - 2 * PI_ASTAR);
+        const int c_cx = (int)(hpp_div_res(g, cn.x - g.ox)), c_cy = (int)(hpp_div_res(g, cn.y - g.oy));
+        if (c_cx == g_cx && c_cy == g_cy && hd <= 0.05) {
+          end_node = cur;
+          break;
+        }
+      }
+      // ---- expansion (GetnextNeighbours, RS/src/HybridAstar.cpp:25-79): lane = motion command
+      double cxs = cn.x, cys = cn.y, chs = cn.h, ccost = 0, fkey = 0.0;
+      int valid = 0, ins_slot = -1, replace = 0;
+      if (lane < ncmd) {
+        int hit = 0;
+        for (int i = 0; i < pc.ec.sim; i++) {
+          vehicle_step(cxs, cys, chs, pc.ec.dir[lane], pc.ec.step, pc.ec.dtheta[lane]);
+          if (!hit) hit = circles_collide_ilp(g, pc.cc, dist, cxs, cys, chs);
+        }
+        valid = !hit;
+      }
+      // ---- insert / replace in command order
+      if (valid) {
+        ccost = path_cost(pc.ec, lane, cn.cost, cn.steer, cn.dir);
+        int sl;
+        const int v = table_find(table, nodes, pc.table_mask, cxs, cys, chs, sl);
+        if (v >= 0 && (v & 1)) valid = 0;  // in the closed set
+        else {
+          const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
+          const long nidx = (long)ccy * W + ccx;
+          if (nidx < 0 || nidx >= map_size) valid = 0;  // :674-677
+          else {
+            fkey = ccost + 30.0 * hmap[nidx];
+            if (v >= 0) {
+              if (ccost < nodes[v >> 1].cost) replace = 1;  // strictly cheaper than the open node
+              else valid = 0;
+            }
+            ins_slot = sl;
+          }
+        }
+      }
+      const unsigned vm = __ballot_sync(FULLM, valid);
+      const int n_new = __popc(vm);
+      if (n_nodes + n_new > pc.max_nodes) {
+        status = 1;
+        break;
+      }
+      if (valid) {
+        const int my = n_nodes + __popc(vm & ((1u << lane) - 1u));
+        pnode nd;
+        nd.x = cxs; nd.y = cys; nd.h = chs; nd.cost = ccost; nd.steer = pc.ec.steer[lane]; nd.parent = cur;
+        nd.dir = (signed char)(int)pc.ec.dir[lane]; nd.cmd = (signed char)lane; nd.pad = 0;
+        nodes[my] = nd;
+        __threadfence_block();
+        if (replace) table[ins_slot] = my << 1;
+        else {
+          int sl = ins_slot;
+          while (atomicCAS(&table[sl], -1, my << 1) != -1) sl = (sl + 1) & pc.table_mask;
+        }
+      }
+      __syncwarp();
+      for (unsigned mset = vm; mset;) {  // heap pushes in command order
+        const int b = __ffs(mset) - 1;
+        mset &= mset - 1;
+        const double k = __shfl_sync(FULLM, fkey, b);
+        const int my = n_nodes + __popc(vm & ((1u << b) - 1u));
+        gheap_push_warp(hkey, hidx, hn, k, my);
+      }
+      n_nodes += n_new;
+    }
+    // ---- the loop is over: shots of earlier pops come first
+    while (win < 0 && retired < head) {
+      if (retire()) break;
+      __nanosleep(100);
+    }
+    if (lane == 0) sm.quit = 1;
+    pipe_res wr;
+    wr.n_samples = 0; wr.nseg = 0; wr.cost = 0.0;
+    if (win >= 0) {
+      __threadfence_block();
+      const pipe_job jb = sm.job[win % PIPE_RING];
+      wr = sm.res[win % PIPE_RING];
+      goal_node = jb.cur;
+      iterations = jb.iter;
+      via_shot = 1;
+      status = 0;
+      shot_samples = wr.n_samples;
+      shot_cost = wr.cost;
+    } else if (end_node >= 0) {
+      goal_node = end_node;
+    }
+
+    // ---- back-track (RS/src/HybridAstar.cpp:690-710)
+    int total = 1;  // failure: the goal state alone (hazard H10)
+    if (goal_node >= 0) {
+      total = via_shot ? shot_samples : 0;
+      for (int b = goal_node; b >= 0; b = nodes[b].parent) total += (nodes[b].cmd == -1) ? 1 : pc.ec.sim;
+    }
+    unsigned long long off = 0;
+    if (lane == 0) off = atomicAdd(cursor, (unsigned long long)total);
+    off = __shfl_sync(FULLM, off, 0);
+    if (off + (unsigned long long)total <= traj_cap) {
+      double *out = traj + off * 5;
+      if (goal_node < 0) {
+        if (lane == 0) {
+          out[0] = gx; out[1] = gy; out[2] = gh; out[3] = (double)g_cx; out[4] = (double)g_cy;
+        }
+      } else {
+        int pos = total;
+        if (via_shot) {
+          pos -= shot_samples;
+          store_visitor sv;
+          sv.out = out + (size_t)pos * 5;
+          sv.g = &g;
+          sv.cap = shot_samples;
+          const pnode cn = nodes[goal_node];
+          warp_sample_path<false>(wr.len, wr.typ, wr.nseg, pc.maxc, pc.maxc, cn.x, cn.y, cn.h, sv);
+        }
+        if (lane == 0) {
+          for (int b = goal_node; b >= 0; b = nodes[b].parent) {
+            const pnode nd = nodes[b];
+            if (nd.cmd == -1) {
+              pos -= 1;
+              double *r = out + (size_t)pos * 5;
+              r[0] = nd.x; r[1] = nd.y; r[2] = nd.h;
+              r[3] = (double)(int)(hpp_div_res(g, nd.x - g.ox));
+              r[4] = (double)(int)(hpp_div_res(g, nd.y - g.oy));
+            } else {
+              pos -= pc.ec.sim;
+              const pnode pr = nodes[nd.parent];
+              double x = pr.x, y = pr.y, h = pr.h;
+              for (int i = 0; i < pc.ec.sim; i++) {
+                vehicle_step(x, y, h, pc.ec.dir[nd.cmd], pc.ec.step, pc.ec.dtheta[nd.cmd]);
+                double *r = out + (size_t)(pos + i) * 5;
+                r[0] = x; r[1] = y; r[2] = h;
+                r[3] = (double)(int)(hpp_div_res(g, x - g.ox));
+                r[4] = (double)(int)(hpp_div_res(g, y - g.oy));
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      hpp_plan P;
+      P.n_states = total;
+      P.iterations = iterations;
+      P.via_shot = via_shot;
+      P.status = status;
+      P.cost = (goal_node < 0) ? 0.0 : (via_shot ? shot_cost : nodes[goal_node].cost);
+      P.traj_offset = off;
+      plans[q] = P;
+    }
+    __syncwarp();
+  }
+}
+
 // ---- unit hook: the warp-collective heap against the one-thread replay on the same operations (one warp)
 __global__ void heap_ops_kernel(const double *__restrict__ keys, const int *__restrict__ ops, int n_ops,
                                 double *ka, int *ia, double *kb, int *ib, int *pops, long long *first_mismatch) {
@@ -867,10 +1243,29 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
                                                             : (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_BATCH>)
                            : (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_LONE>
                                                             : (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_BATCH>);
-    const int occ_slot = variant * 2 + (plan_warps == PLAN_WARPS_LONE ? 1 : 0);
+    // Reeds-Shepp: the pipelined kernel (search on warp 0, one whole shot per worker warp).  HPP_PLAN_PIPE=0 selects the
+    // phase-by-phase kernel, =2 forces two CTAs per SM, =3 one
+    size_t plan_smem_bytes = 0;
+    static const int pipe_env = getenv("HPP_PLAN_PIPE") ? atoi(getenv("HPP_PLAN_PIPE")) : 1;
+    const bool pipe = variant == HPP_VARIANT_RS && pipe_env != 0;
+    if (pipe) {
+      // One 8-warp CTA per SM (no spills): a pipelined query keeps an SM's instruction fetch busy on its own -- its
+      // eight warps are at eight different places of the shot code -- and two of them on one SM run at half speed each.
+      // Only batches large enough to hold more long queries than there are SMs (cfg5: 2.2 % of 8 192 = 184 queries at
+      // the iteration cap on 148 SMs) take the two-per-SM build (128 registers), which avoids a second wave of them.
+      plan_warps = 8;
+      const bool two = pipe_env == 2 || (pipe_env == 1 && ng > (size_t)32 * c->sm_count);
+      kern = two ? (const void *)plan_pipe_kernel<8, 2> : (const void *)plan_pipe_kernel<8, 1>;
+      plan_smem_bytes = sizeof(pipe_smem<8>);
+      if (plan_smem_bytes > 48 * 1024)
+        HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem_bytes));
+    }
+    // cached per kernel shape (the RS slots hold the pipelined kernel's two builds; HPP_PLAN_PIPE is read once)
+    const int occ_slot = pipe ? (kern == (const void *)plan_pipe_kernel<8, 2> ? 0 : 1)
+                              : variant * 2 + (plan_warps == PLAN_WARPS_LONE ? 1 : 0);
     int occ_blocks = c->plan_occ_blocks[occ_slot];
     if (occ_blocks == 0) {
-      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, kern, plan_warps * 32, 0));
+      HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, kern, plan_warps * 32, plan_smem_bytes));
       c->plan_occ_blocks[occ_slot] = occ_blocks;
     }
     if (occ_blocks < 1) occ_blocks = 1;
@@ -951,8 +1346,8 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
         unsigned long long a_cap = traj_cap;
         void *params[] = {&pc,       &a_descs, &a_mq,   &a_starts, &a_goals, &a_qids,  &a_nq,   &a_fq,
                           &a_fields, &d_nodes, &d_keys, &d_idx,    &d_table, &d_plans, &d_traj, &a_cap,
-                          &d_cursor, &d_prof};
-        cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, 0, c->stream);
+                          &d_cursor, &d_prof};  // (the pipelined kernel takes all but the last)
+        cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, plan_smem_bytes, c->stream);
       }
       c->launches++;
       e = cudaGetLastError();
