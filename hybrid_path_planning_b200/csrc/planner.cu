@@ -1,23 +1,24 @@
 // planner.cu -- whole Hybrid A* queries on the device: HybridAstar::run (RS/src/HybridAstar.cpp:553-729,
 // DB/src/HybridAstar.cpp:315-496) for a batch of independent start/goal pairs on one map.
 //
-// One CTA of four (batches) or eight (small batches) warps owns one query from start to finish (and then takes the next one from a counter): no
-// host round trip per A* iteration.  The iterations of a query are a sequential chain, so the CTA's job is to make
-// one iteration short: the 46 Reeds-Shepp closed forms are spread over the warps family by family, the candidate
-// paths are sampled and footprint-checked one per warp, and the expansion's rollouts run one thread per
-// (command, state); pop, de-duplication and the heap pushes stay on one warp / one thread.
+// Two kernels, one CTA per query (which then takes the next query from a counter): no host round trip per A* iteration.
+//   plan_pipe_kernel  Reeds-Shepp planner.  Warp 0 runs the reference's loop statement by statement -- pop, openSet
+//                     lookup, closed test, goal test, expansion (lane = motion command), insert / replace in command
+//                     order, heap pushes -- ASSUMING that analytic shots fail, and hands every popped node to the worker
+//                     warps; each worker evaluates one node's whole shot (46 closed forms, ordered de-duplication,
+//                     footprint checks of every candidate path, cost order when one is free); results are retired in
+//                     pop order, so the first success ends the query exactly where the sequential loop would have.
+//   plan_kernel       Dubins planner, phase by phase: the shot is a single path (warp 0) and the expansion's SAT checks
+//                     (one warp per state) run beside it.
 // Per query the CTA keeps, in its own slice of global memory,
 //   * a node pool (state, Cost_path, steering angle, direction, parent, command index),
 //   * the open list as a binary heap of (f, node) that replays libstdc++'s std::push_heap / std::pop_heap for
 //     the reference's cost-only comparator, so equal-f nodes pop in the reference's order,
 //   * one open-addressing hash table keyed by the State doubles that plays both openSet and closedSet
 //     (value = node index, low bit = "closed").
-// Each iteration follows the reference statement by statement: pop -> openSet lookup -> closed test -> analytic
-// shot (K7/K8 device code) -> goal test (same cell and |dheading| <= 0.05 with PI = 3.14159) -> expansion
-// (K6 device code: lanes = motion commands for RS, warp-wide SAT per state for Dubins) -> insert/replace in
-// command order.  The 3500-iteration cap, the 1-state failure trajectory and the back-track order are kept.
-// Child trajectories are not stored: they are re-rolled from (parent state, command) at back-track time.
-// The heuristic field of every distinct goal cell comes from K3 (hpp_heuristic_batch_dev) beforehand.
+// The 3500-iteration cap, the 1-state failure trajectory and the back-track order are kept.  Child trajectories are not
+// stored: they are re-rolled from (parent state, command) at back-track time.  The heuristic field of every distinct
+// (map, goal cell) comes from K3 (hpp_heuristic_batch_dev) beforehand.
 #include <algorithm>
 #include <chrono>
 #include <vector>
@@ -256,44 +257,11 @@ struct plan_mail {
 };
 
 struct plan_smem {
-  rs_warp_smem S;
   plan_mail mail[2];
   int query;
-  int verdict[RS_NCAND];                // kept sample count (or -1) of every accepted path
-  int next_path, any_free;              // RS shot: path hand-out counter, "some path is collision-free"
   unsigned hit;                         // expansion: commands with a colliding state
-  int hit0;                             // RS shot: footprint verdict of the start pose (sample 0 of every path)
   double child[HPP_MAX_COMMANDS][3];    // expansion: last state of every command's rollout
 };
-
-// formula evaluated by (warp, lane): the closed forms of one family share their code path, so each warp gets at most
-// three families (RS/src/reeds_shepp_path.cpp:795-817 issue order: SLS 0-1, LSL 2-5, LSR 6-9, LRL 10-17, LRLRn 18-21,
-// LRLRp 22-25, LRSL 26-29 and 34-37, LRSR 30-33 and 38-41, LRSLR 42-45)
-template <int NW>
-__device__ __forceinline__ int plan_formula_of(int wid, int lane) {
-  if (NW == 4) {
-    switch (wid) {
-      case 0: return lane < 10 ? lane : -1;
-      case 1: return lane < 12 ? 10 + lane : -1;
-      case 2: return lane < 8 ? 22 + lane : (lane < 12 ? 26 + lane : -1);
-      default: return lane < 4 ? 30 + lane : (lane < 12 ? 34 + lane : -1);
-    }
-  } else if (NW == 8) {
-    switch (wid) {
-      case 0: return lane < 6 ? lane : -1;
-      case 1: return lane < 4 ? 6 + lane : -1;
-      case 2: return lane < 8 ? 10 + lane : -1;
-      case 3: return lane < 4 ? 18 + lane : -1;
-      case 4: return lane < 4 ? 22 + lane : -1;
-      case 5: return lane < 4 ? 26 + lane : (lane < 8 ? 30 + lane : -1);
-      case 6: return lane < 4 ? 30 + lane : (lane < 8 ? 34 + lane : -1);
-      default: return lane < 4 ? 42 + lane : -1;
-    }
-  } else {
-    const int t = wid * 32 + lane;
-    return t < RS_NCAND ? t : -1;
-  }
-}
 
 template <int VARIANT, int PLAN_WARPS>
 __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, const plan_map_desc *__restrict__ descs,
@@ -310,10 +278,10 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
                                                             unsigned long long *__restrict__ cursor,
                                                             unsigned long long *__restrict__ prof) {
   static_assert(PLAN_WARPS >= 2, "warp 0 and at least one helper warp");
+  static_assert(VARIANT == HPP_VARIANT_DUBINS, "the Reeds-Shepp planner is plan_pipe_kernel");
   constexpr int PLAN_THREADS = PLAN_WARPS * 32;
   __shared__ plan_smem sm;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  rs_warp_smem &S = sm.S;
   const hpp_geom &g = pc.g;
   const int W = g.W, H = g.H;
   const long map_size = (long)W * H;
@@ -343,7 +311,6 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
     const double *hmap = fields + (size_t)field_of_query[qi] * map_size;
     // the query's map (maps of one launch share their geometry and vehicle, hpp_plan_batch_multi)
     const plan_map_desc md = descs[map_of_query ? map_of_query[q] : 0];
-    const float *__restrict__ dist = md.dist;
     const uint32_t *__restrict__ bits = md.bits;
     const int pitch = md.pitch;
     const double sx = starts[3 * q], sy = starts[3 * q + 1], sh = starts[3 * q + 2];
@@ -396,8 +363,6 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
           mail.hn = hn;
           mail.tv = tv;
           sm.hit = 0u;
-          sm.next_path = 0;
-          sm.any_free = 0;
         }
       }
       __syncthreads();
@@ -408,58 +373,8 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
       const pnode cn = nodes[cur];
       PLAN_MARK(0)
 
-      // ---- analytic shot (+ for Dubins, the expansion's footprint checks on the other warps meanwhile)
-      if (VARIANT == HPP_VARIANT_RS) {
-        const rs_frame f = rs_make_frame(cn.x, cn.y, cn.h, gx, gy, gh, pc.maxc);
-        const int idx = plan_formula_of<PLAN_WARPS>(wid, lane);
-        if (idx >= 0) rs_eval_formula(idx, f.x, f.y, f.dth, f.xb, f.yb, S);
-        __syncthreads();
-        PLAN_MARK(6)
-        if (wid == 0) rs_dedup(S);
-        if (wid != 0 || PLAN_WARPS == 1) {
-          // meanwhile the other warps roll out the expansion (GetnextNeighbours, RS/src/HybridAstar.cpp:25-79): one
-          // thread per (command, state of its rollout); the result is dropped if the shot succeeds
-          const int t0 = PLAN_WARPS == 1 ? tid : tid - 32, ts = PLAN_WARPS == 1 ? 32 : PLAN_THREADS - 32;
-          for (int p = t0; p <= n_poses; p += ts) {
-            if (p == n_poses) {
-              // sample 0 of every candidate path is the start pose itself: looked at once per shot
-              // (world transform of (0,0,0), RS/src/reeds_shepp_path.cpp:76-81: x, y unchanged, pi_2_pi(yaw))
-              sm.hit0 = circles_collide_ilp(g, pc.cc, dist, cn.x, cn.y, pi_2_pi(0.0 + cn.h));
-              break;
-            }
-            const int c = p / pc.ec.sim, i = p % pc.ec.sim;
-            double x = cn.x, y = cn.y, h = cn.h;
-            for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
-            if (circles_collide_ilp(g, pc.cc, dist, x, y, h)) atomicOr(&sm.hit, 1u << c);
-            if (i == pc.ec.sim - 1) {
-              sm.child[c][0] = x; sm.child[c][1] = y; sm.child[c][2] = h;
-            }
-          }
-        }
-        __syncthreads();
-        PLAN_MARK(1)
-        const int n_acc = S.n_acc;
-        SR.found = 0; SR.chosen = -1; SR.n_samples = 0; SR.cand = -1; SR.cost = 0.0; SR.n_paths = n_acc;
-        // every accepted path is sampled and footprint-checked, the warps taking them one at a time from a counter.
-        // The reference tries them in cost order and stops at the first free one (> 5 paths) or keeps the cheapest
-        // free one; which path that is does not depend on how many were looked at, so the order -- a sequential
-        // heap replay -- is only worked out when some path is free (once per successful query).
-        // (grouped: a warp walks 32 / PLAN_PATH_GROUP paths at once, one per lane group, see rs_check_paths_grouped)
-        rs_check_paths_grouped<PLAN_PATH_GROUP>(S, n_acc, &sm.next_path, sm.verdict, &sm.any_free, g, pc.cc, dist, cn.x,
-                                                cn.y, cn.h, pc.maxc, sm.hit0);
-        __syncthreads();
-        if (sm.any_free) {
-          if (wid == 0) rs_order_paths(S, cn.cost, pc.maxc, pc.max_steer);
-          __syncthreads();
-          double best = INFINITY;
-          for (int o = 0; o < n_acc; o++)
-            if (rs_fold_path(S, o, sm.verdict[S.order[o]], SR, best)) break;
-        }
-        if (SR.found) {
-          shot_samples = SR.n_samples;
-          shot_cost = SR.cost;
-        }
-      } else {
+      // ---- analytic shot on warp 0, the expansion's footprint checks on the other warps meanwhile
+      {
         if (wid == 0) {
           DB = db_plan(cn.x, cn.y, cn.h, gx, gy, gh, pc.maxc);
           sat_visitor vis;
@@ -539,8 +454,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
           else {
             const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
             const long nidx = (long)ccy * W + ccx;
-            if (VARIANT == HPP_VARIANT_RS && (nidx < 0 || nidx >= map_size)) valid = 0;  // :674-677
-            else {
+            {  // (the Dubins planner does not range-check the cell index, DB/src/HybridAstar.cpp:442-444)
               fkey = ccost + 30.0 * hmap[nidx];
               if (v >= 0) {
                 if (ccost < nodes[v >> 1].cost) replace = 1;  // strictly cheaper than the open node
@@ -626,12 +540,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
           sv.g = &g;
           sv.cap = shot_samples;
           const pnode cn = nodes[goal_node];
-          if (VARIANT == HPP_VARIANT_RS) {
-            const int k = SR.cand;
-            warp_sample_path<false>(S.len[k], S.typ[k], S.nseg[k], pc.maxc, pc.maxc, cn.x, cn.y, cn.h, sv);
-          } else {
-            warp_sample_path<true>(DB.len, DB.typ, DB.nmode, pc.maxc, 0.1, cn.x, cn.y, cn.h, sv);
-          }
+          warp_sample_path<true>(DB.len, DB.typ, DB.nmode, pc.maxc, 0.1, cn.x, cn.y, cn.h, sv);
         }
         if (lane == 0) {
           for (int b = goal_node; b >= 0; b = nodes[b].parent) {
@@ -680,7 +589,9 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
 //   warp 0 (the controller) runs HybridAstar::run's loop statement by statement -- pop, closed test, goal test,
 //       expansion, insert / replace, heap pushes -- assuming that every shot fails, and hands every popped node to the
 //       workers through a ring in shared memory;
-//   warps 1 .. (the workers) each take the next node of the ring and evaluate its whole shot alone;
+//   warps 1 .. 3 roll out the expansion's 26 x 4 poses together with the controller (one thread per pose, a named
+//       barrier before and after), because the expansion is on the controller's chain;
+//   warps 4 .. (the workers) each take the next node of the ring and evaluate its whole shot alone;
 //   the controller retires the results IN POP ORDER: the first success ends the query at that node's iteration --
 //       exactly where the sequential loop would have ended, whatever the controller did beyond it (its later pops only
 //       appended nodes; the successful node's ancestors are untouched) -- and a loop that ends by the goal test, an empty
@@ -704,16 +615,25 @@ struct pipe_worker {
   int verdict[RS_NCAND];
   int next_path, any_free;
 };
+#define PIPE_EXP_WARPS 3  // warps 1..3 roll out the expansion with the controller (4 x 32 threads >= 26 commands x 4 states)
 template <int NW>
 struct pipe_smem {
   int query;
   volatile int head;   // jobs published by the controller
   int claim;           // jobs claimed by the workers
   volatile int quit;
+  volatile int exp_quit;               // expansion helpers: the query is over
+  unsigned exp_hit;                    // expansion: commands with a colliding state
+  double exp_from[3];                  // expansion: the node being expanded
+  double exp_child[HPP_MAX_COMMANDS][3];  // expansion: last state of every command's rollout
   pipe_job job[PIPE_RING];
   pipe_res res[PIPE_RING];
-  pipe_worker w[NW - 1];
+  pipe_worker w[NW - 1 - PIPE_EXP_WARPS];
 };
+// named barrier of the controller and its expansion helpers (barrier 0 is __syncthreads)
+__device__ __forceinline__ void pipe_exp_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"((1 + PIPE_EXP_WARPS) * 32) : "memory");
+}
 
 template <int NW, int MIN_CTAS>
 __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_consts pc, const plan_map_desc *__restrict__ descs,
@@ -727,8 +647,17 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
                                                             int *__restrict__ idx_pool, int *__restrict__ table_pool,
                                                             hpp_plan *__restrict__ plans, double *__restrict__ traj,
                                                             unsigned long long traj_cap,
-                                                            unsigned long long *__restrict__ cursor) {
+                                                            unsigned long long *__restrict__ cursor,
+                                                            unsigned long long *__restrict__ prof) {
   constexpr int THREADS = NW * 32;
+#ifdef HPP_PLAN_PROF
+  unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PIPE_T0 const long long t0_ = clock64();
+#define PIPE_ADD(i) pf[i] += (unsigned long long)(clock64() - t0_);
+#else
+#define PIPE_T0
+#define PIPE_ADD(i)
+#endif
   extern __shared__ __align__(16) unsigned char pipe_raw[];
   pipe_smem<NW> &sm = *reinterpret_cast<pipe_smem<NW> *>(pipe_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -749,6 +678,7 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       sm.head = 0;
       sm.claim = 0;
       sm.quit = 0;
+      sm.exp_quit = 0;
     }
     __syncthreads();
     const int qi = sm.query;
@@ -761,9 +691,33 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
     for (int i = tid; i <= pc.table_mask; i += THREADS) table[i] = -1;
     __syncthreads();
 
+    // one thread per (command, state of its rollout) of the node in sm.exp_from (GetnextNeighbours,
+    // RS/src/HybridAstar.cpp:25-79); run by the controller and its helpers between two named barriers
+    auto rollouts = [&]() {
+      const int p = tid;  // tid < 128 here
+      if (p < ncmd * pc.ec.sim) {
+        const int c = p / pc.ec.sim, i = p % pc.ec.sim;
+        double x = sm.exp_from[0], y = sm.exp_from[1], h = sm.exp_from[2];
+        for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
+        if (circles_collide_ilp(g, pc.cc, dist, x, y, h)) atomicOr(&sm.exp_hit, 1u << c);
+        if (i == pc.ec.sim - 1) {
+          sm.exp_child[c][0] = x; sm.exp_child[c][1] = y; sm.exp_child[c][2] = h;
+        }
+      }
+    };
+    if (wid >= 1 && wid <= PIPE_EXP_WARPS) {
+      // ================================================================ expansion helper
+      for (;;) {
+        pipe_exp_barrier();  // the controller has published a node (or the end of the query)
+        if (sm.exp_quit) break;
+        rollouts();
+        pipe_exp_barrier();  // hit bits and child states are complete
+      }
+      continue;
+    }
     if (wid != 0) {
       // ================================================================ worker: one whole shot per job
-      pipe_worker &me = sm.w[wid - 1];
+      pipe_worker &me = sm.w[wid - 1 - PIPE_EXP_WARPS];
       for (;;) {
         int c = 0;
         if (lane == 0) {
@@ -775,7 +729,11 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         if (c < 0) break;
         __threadfence_block();
         const pipe_job jb = sm.job[c % PIPE_RING];
-        rs_generate(me.S, jb.x, jb.y, jb.h, gx, gy, gh, pc.maxc);
+        {
+          PIPE_T0
+          rs_generate(me.S, jb.x, jb.y, jb.h, gx, gy, gh, pc.maxc);
+          PIPE_ADD(0)
+        }
         const int n_acc = me.S.n_acc;
         rs_shot_result SR;
         SR.found = 0; SR.chosen = -1; SR.n_samples = 0; SR.cand = -1; SR.cost = 0.0; SR.n_paths = n_acc;
@@ -789,9 +747,17 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
           }
           hit0 = __shfl_sync(FULLM, hit0, 0);
           __syncwarp();
-          rs_check_paths_grouped<PLAN_PATH_GROUP>(me.S, n_acc, &me.next_path, me.verdict, &me.any_free, g, pc.cc, dist,
-                                                  jb.x, jb.y, jb.h, pc.maxc, hit0);
+          {
+            PIPE_T0
+            rs_check_paths_grouped<PLAN_PATH_GROUP>(me.S, n_acc, &me.next_path, me.verdict, &me.any_free, g, pc.cc, dist,
+                                                    jb.x, jb.y, jb.h, pc.maxc, hit0);
+            PIPE_ADD(1)
+          }
           __syncwarp();
+#ifdef HPP_PLAN_PROF
+          pf[2] += 1;
+          pf[3] += (unsigned long long)n_acc;
+#endif
           if (me.any_free) {
             rs_order_paths(me.S, jb.cost, pc.maxc, pc.max_steer);
             double best = INFINITY;
@@ -816,6 +782,12 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         }
         __syncwarp();
       }
+#ifdef HPP_PLAN_PROF
+      if (prof && lane == 0 && wid == 1 + PIPE_EXP_WARPS) {
+        for (int i = 0; i < 4; i++) atomicAdd(prof + i, pf[i]);
+      }
+      for (int i = 0; i < 8; i++) pf[i] = 0;
+#endif
       continue;  // next query (the controller does the back-track)
     }
 
@@ -859,6 +831,9 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       }
     };
     int end_node = -1;  // node at which the loop itself ended by the goal test
+#ifdef HPP_PLAN_PROF
+    const long long tloop_ = clock64();
+#endif
     while (status == 0 && hn > 0) {
       if (retire()) break;
       iterations++;
@@ -877,9 +852,13 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       const int cur = tv >> 1;
       const pnode cn = nodes[cur];
       // ---- the analytic shot of this node goes to the workers
-      while (head - retired >= PIPE_RING) {
-        if (retire()) break;
-        __nanosleep(100);
+      {
+        PIPE_T0
+        while (head - retired >= PIPE_RING) {
+          if (retire()) break;
+          __nanosleep(100);
+        }
+        PIPE_ADD(5)
       }
       if (win >= 0) break;
       if (lane == 0) {
@@ -901,16 +880,19 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
           break;
         }
       }
-      // ---- expansion (GetnextNeighbours, RS/src/HybridAstar.cpp:25-79): lane = motion command
-      double cxs = cn.x, cys = cn.y, chs = cn.h, ccost = 0, fkey = 0.0;
+      // ---- expansion: the controller and its helpers, one thread per (command, state)
+      if (lane == 0) {
+        sm.exp_from[0] = cn.x; sm.exp_from[1] = cn.y; sm.exp_from[2] = cn.h;
+        sm.exp_hit = 0u;
+      }
+      pipe_exp_barrier();
+      rollouts();
+      pipe_exp_barrier();
+      double cxs = 0, cys = 0, chs = 0, ccost = 0, fkey = 0.0;
       int valid = 0, ins_slot = -1, replace = 0;
       if (lane < ncmd) {
-        int hit = 0;
-        for (int i = 0; i < pc.ec.sim; i++) {
-          vehicle_step(cxs, cys, chs, pc.ec.dir[lane], pc.ec.step, pc.ec.dtheta[lane]);
-          if (!hit) hit = circles_collide_ilp(g, pc.cc, dist, cxs, cys, chs);
-        }
-        valid = !hit;
+        valid = !((sm.exp_hit >> lane) & 1u);
+        cxs = sm.exp_child[lane][0]; cys = sm.exp_child[lane][1]; chs = sm.exp_child[lane][2];
       }
       // ---- insert / replace in command order
       if (valid) {
@@ -961,11 +943,29 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       }
       n_nodes += n_new;
     }
+#ifdef HPP_PLAN_PROF
+    pf[4] += (unsigned long long)(clock64() - tloop_);
+#endif
+    if (lane == 0) sm.exp_quit = 1;
+    pipe_exp_barrier();  // releases the expansion helpers
     // ---- the loop is over: shots of earlier pops come first
-    while (win < 0 && retired < head) {
-      if (retire()) break;
-      __nanosleep(100);
+    {
+      PIPE_T0
+      while (win < 0 && retired < head) {
+        if (retire()) break;
+        __nanosleep(100);
+      }
+      PIPE_ADD(6)
     }
+#ifdef HPP_PLAN_PROF
+    if (prof && lane == 0 && iterations > 3000) {
+      atomicAdd(prof + 4, pf[4]);
+      atomicAdd(prof + 5, pf[5]);
+      atomicAdd(prof + 6, pf[6]);
+      atomicAdd(prof + 7, (unsigned long long)iterations);
+    }
+    for (int i = 0; i < 8; i++) pf[i] = 0;
+#endif
     if (lane == 0) sm.quit = 1;
     pipe_res wr;
     wr.n_samples = 0; wr.nseg = 0; wr.cost = 0.0;
@@ -1238,16 +1238,13 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
       const int v = atoi(ev);
       if (v == PLAN_WARPS_LONE || v == PLAN_WARPS_BATCH) plan_warps = v;
     }
-    const void *kern = variant == HPP_VARIANT_RS
-                           ? (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_LONE>
-                                                            : (const void *)plan_kernel<HPP_VARIANT_RS, PLAN_WARPS_BATCH>)
-                           : (plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_LONE>
-                                                            : (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_BATCH>);
-    // Reeds-Shepp: the pipelined kernel (search on warp 0, one whole shot per worker warp).  HPP_PLAN_PIPE=0 selects the
-    // phase-by-phase kernel, =2 forces two CTAs per SM, =3 one
+    const void *kern = plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_LONE>
+                                                     : (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_BATCH>;
+    // Reeds-Shepp: the pipelined kernel (search on warp 0, one whole shot per worker warp).  HPP_PLAN_PIPE=2 forces two
+    // CTAs per SM, =3 one
     size_t plan_smem_bytes = 0;
     static const int pipe_env = getenv("HPP_PLAN_PIPE") ? atoi(getenv("HPP_PLAN_PIPE")) : 1;
-    const bool pipe = variant == HPP_VARIANT_RS && pipe_env != 0;
+    const bool pipe = variant == HPP_VARIANT_RS;
     if (pipe) {
       // One 8-warp CTA per SM (no spills): a pipelined query keeps an SM's instruction fetch busy on its own -- its
       // eight warps are at eight different places of the shot code -- and two of them on one SM run at half speed each.
@@ -1366,6 +1363,12 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
     unsigned long long hp[8];
     void *dp = nullptr;
     if (hpp_scratch(c, 5, 64, &dp) == HPP_OK && cudaMemcpy(hp, dp, 64, cudaMemcpyDeviceToHost) == cudaSuccess && hp[7])
+      if (variant == HPP_VARIANT_RS)
+        fprintf(stderr, "[pipe prof] worker 1 of every CTA: %llu shots, %.1f paths/shot, generate %.0f + path checks %.0f cycles per "
+                "shot; controllers of long queries: %llu iterations, loop %.0f cycles/iteration of which ring-full waits %.0f, "
+                "drain %.0f cycles/query-iteration\n", hp[2], hp[2] ? (double)hp[3] / hp[2] : 0.0, hp[2] ? (double)hp[0] / hp[2] : 0.0,
+                hp[2] ? (double)hp[1] / hp[2] : 0.0, hp[7], (double)hp[4] / hp[7], (double)hp[5] / hp[7], (double)hp[6] / hp[7]);
+      else
       fprintf(stderr, "[plan prof] %llu iterations of long queries; cycles/iteration: pop %.0f formulas %.0f dedup+order %.0f "
               "path checks %.0f expand %.0f insert %.0f push %.0f\n", hp[7], (double)hp[0] / hp[7], (double)hp[6] / hp[7],
               (double)hp[1] / hp[7], (double)hp[2] / hp[7], (double)hp[3] / hp[7], (double)hp[4] / hp[7],
