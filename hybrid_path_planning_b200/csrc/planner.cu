@@ -1254,6 +1254,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
       const bool two = pipe_env == 2 || (pipe_env == 1 && ng > (size_t)32 * c->sm_count);
       kern = two ? (const void *)plan_pipe_kernel<8, 2> : (const void *)plan_pipe_kernel<8, 1>;
       plan_smem_bytes = sizeof(pipe_smem<8>);
+
       if (plan_smem_bytes > 48 * 1024)
         HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem_bytes));
     }
