@@ -694,8 +694,8 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
     // one thread per (command, state of its rollout) of the node in sm.exp_from (GetnextNeighbours,
     // RS/src/HybridAstar.cpp:25-79); run by the controller and its helpers between two named barriers
     auto rollouts = [&]() {
-      const int p = tid;  // tid < 128 here
-      if (p < ncmd * pc.ec.sim) {
+      // tid < 128 here; pathLength 4 (the default) gives 104 poses, pathLength 8 gives 208: a second round
+      for (int p = tid; p < ncmd * pc.ec.sim; p += (1 + PIPE_EXP_WARPS) * 32) {
         const int c = p / pc.ec.sim, i = p % pc.ec.sim;
         double x = sm.exp_from[0], y = sm.exp_from[1], h = sm.exp_from[2];
         for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);

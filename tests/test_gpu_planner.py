@@ -126,3 +126,31 @@ def test_open_list_warp_heap_matches_libstdcxx_replay(ctx):
         # keys come out in non-decreasing order between pushes of smaller keys: check the drain at the end
         drain = keys[np.array(ops)[popped[-size:]]] if size else np.array([])
         assert np.all(np.diff(drain[np.isfinite(drain)]) >= 0)
+
+
+@pytest.mark.parametrize("variant,path_length,step", [(0, 6.0, 1.0), (0, 8.0, 0.5), (1, 6.0, 1.0), (0, 2.0, 1.0)])
+def test_plan_batch_other_planner_parameters(ctx, variant, path_length, step):
+    """pathLength / step_car other than the launch file's 4 / 1: rollouts of 2, 6 and 8 states per command (8 x 26 = 208 poses
+    are more than the 128 threads that roll out the Reeds-Shepp expansion: a second round), compared with the oracle's run
+    with the same simulation length and step"""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    occ = parking_map(256, seed=3)
+    params = (0.6, 2.75, 1.1, 1.2, 1.9, path_length, step)
+    m = hpp.Map(ctx, occ, 0.2, params=params)
+    om = O.Map(occ, 0.2)
+    starts, goals = _free_pairs(om, 20, 11, variant)
+    plans, traj = m.plan_batch(variant, starts, goals)
+    same = solved = 0
+    for i in range(20):
+        w = O.run(om, variant, tuple(starts[i]), tuple(goals[i]), sim_len=path_length, step=step, quirks=True)
+        g = plans[i]
+        assert (g["n_states"] > 1) == (len(w["traj"]) > 1), i
+        assert abs(g["cost"] - w["cost"]) <= 1e-4 * max(1.0, abs(w["cost"])), i
+        solved += int(g["n_states"] > 1)
+        if g["iterations"] == w["iterations"] and g["n_states"] == len(w["traj"]):
+            same += 1
+            tr = traj[int(g["traj_offset"]):int(g["traj_offset"]) + int(g["n_states"])]
+            np.testing.assert_allclose(tr[:, :3], w["traj"][:, :3], rtol=0, atol=1e-9)
+    assert same >= 16 and solved >= 5
+    m.close()
