@@ -142,6 +142,71 @@ __device__ __forceinline__ int circle_hits_u8(const hpp_geom &g, const uint8_t *
   return circle_finish(t, f0, f1, f2, f3, r);
 }
 
+// ---------------------------------------------------------------------------------------- float32 filter
+// Most poses are nowhere near the verdict boundary: their clearance differs from the circle radius by centimetres,
+// while the reference's fp64 arithmetic is needed only to place the last 1e-15.  circles_filter_u8 evaluates the same
+// bilinear clearance in float32 (a fifth of the instructions) and returns a verdict only when it is CERTAIN to be
+// the reference's; everything else (2 = undecided) goes through the exact path above.  Why the answer is certain:
+//  * Away from the map border (index 2 .. W-4, checked here) the reference's value is F(p) + e_ref, F = the bilinear
+//    interpolation of the layer between cell centres, a CONTINUOUS function of the position p (the same on both sides
+//    of a cell boundary, so it does not matter which taps either side picks), and e_ref is its fp64 rounding plus the
+//    final cast to float: <= 2^-24 * V, V = the largest tap.
+//  * The layer is an exact Euclidean distance transform times the resolution, so neighbouring taps differ by at most
+//    res (1 + 2^-19) -- clamped at 255 or not -- and |F(p') - F(p)| <= res (1 + 2^-19) (|du| + |dv|) for a position
+//    error (du, dv) in cells.
+//  * The float32 position is off by at most E = 2^-23 D + C (e_sc + 2^-21) cells per axis: D = max(W, H) + 4 bounds the
+//    index coordinate (its cast and the final subtraction round by half an ulp each), C = max_k (|cx_k| + |cy_k|) / res
+//    is the circle offset in cells, e_sc = 4e-6 bounds sine and cosine: heading cast (|h| <= 16: 9.6e-7), two-constant
+//    range reduction (2.4e-7), clamp to the documented __sinf/__cosf range (5e-7), and their error there (2^-21.41).
+//  * The float32 interpolation itself: 10 operations on values <= V, <= 16 * 2^-24 * V.
+// So |value32 - value_ref| <= M = 2 res (1 + 2^-19) E + 20 * 2^-24 V + 2^-23 r, and the host passes r_lo = (r - 1.5 M)
+// rounded down and r_hi = (r + 1.5 M) rounded up: value32 < r_lo means the reference saw value < r, value32 > r_hi
+// means it did not.  A collision on ANY circle is the reference's verdict, so one certain hit decides the pose; a
+// free verdict needs all four circles certainly free.  On the cfg4 map 0.4 % of the poses come back undecided.
+struct filt_consts {
+  double x0, y0;      // centre of cell (0,0): pos + (0.5 len - 0.5 res)
+  double rcp_res;
+  float cu[4], cv[4]; // circle offsets in cells
+  float r_lo, r_hi;
+  int W, H, on;       // on = 0: map too small for the border rule, everything is undecided
+};
+
+__device__ __forceinline__ uint32_t d2_col(int i) { return ((uint32_t)(i >> 3) << 5) + (uint32_t)(i & 7); }
+
+template <int FIRST, int LAST>
+__device__ __forceinline__ int circles_filter_u8(const filt_consts &fc, const uint8_t *__restrict__ d2, int tiles_x,
+                                                 const float *lut, double x, double y, double h) {
+  const float hf = (float)h;
+  if (!(fabsf(hf) <= 16.f)) return 2;
+  const float kf = rintf(hf * 0.15915494f);
+  float hr = fmaf(-kf, 6.2831855f, hf);       // 2 pi = 6.2831855f - 1.7484555e-7
+  hr = fmaf(kf, 1.7484555e-7f, hr);
+  hr = fminf(fmaxf(hr, -3.1415925f), 3.1415925f);
+  float s, c;
+  __sincosf(hr, &s, &c);
+  const float ax = (float)((fc.x0 - x) * fc.rcp_res), ay = (float)((fc.y0 - y) * fc.rcp_res);
+  int undecided = 0;
+#pragma unroll
+  for (int k = FIRST; k < LAST; k++) {
+    const float u = ax - (fc.cu[k] * c - fc.cv[k] * s);
+    const float v = ay - (fc.cu[k] * s + fc.cv[k] * c);
+    const float ful = floorf(u), fvl = floorf(v);
+    const int il = (int)ful, jl = (int)fvl;
+    if (!((unsigned)(il - 2) <= (unsigned)(fc.W - 6) && (unsigned)(jl - 2) <= (unsigned)(fc.H - 6))) return 2;
+    const float fu = u - ful, fv = v - fvl;
+    const uint32_t c0 = d2_col(il), c1 = d2_col(il + 1);
+    const uint32_t r0 = (uint32_t)(jl >> 2) * ((uint32_t)tiles_x << 5) + ((uint32_t)(jl & 3) << 3);
+    const uint32_t r1 = (uint32_t)((jl + 1) >> 2) * ((uint32_t)tiles_x << 5) + ((uint32_t)((jl + 1) & 3) << 3);
+    const float f00 = lut[__ldg(d2 + (r0 + c0))], f10 = lut[__ldg(d2 + (r0 + c1))];
+    const float f01 = lut[__ldg(d2 + (r1 + c0))], f11 = lut[__ldg(d2 + (r1 + c1))];
+    const float lo = f00 + fu * (f10 - f00), hi = f01 + fu * (f11 - f01);
+    const float val = lo + fv * (hi - lo);
+    if (val < fc.r_lo) return 1;
+    undecided |= !(val > fc.r_hi);
+  }
+  return undecided ? 2 : 0;
+}
+
 // throughput form: the four circles in the reference's order, later circles are skipped after a hit
 __device__ __forceinline__ int circles_collide(const hpp_geom &g, const circ_consts &cc,
                                                const float *__restrict__ dist, double x, double y, double h) {

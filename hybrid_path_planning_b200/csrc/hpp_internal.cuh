@@ -21,8 +21,8 @@ struct hpp_ctx {
   uint32_t *h_flags;   // pinned host, 64 words
   uint32_t *d_flags;   // device, 64 words
   // grow-only scratch (device) + pinned host staging for the host-pointer entry points
-  void *d_scratch[6];
-  size_t d_scratch_bytes[6];
+  void *d_scratch[8];
+  size_t d_scratch_bytes[8];
   void *h_pinned[2];
   size_t h_pinned_bytes[2];
   // hpp_plan_batch: values that cost a driver round trip each (tens of microseconds of a 0.3 ms single-query call)

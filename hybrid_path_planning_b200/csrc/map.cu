@@ -33,7 +33,7 @@ extern "C" hpp_status hpp_ctx_destroy(hpp_ctx *c) {
   if (!c) return HPP_ERR_ARG;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < 6; i++)
+  for (int i = 0; i < 8; i++)
     if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
   for (int i = 0; i < 2; i++)
     if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);

@@ -23,4 +23,6 @@ for k in range(reps + 2):
         a.record(stream); m.collide_circles_dev(poses, npose, verd); b.record(stream)
     ctx.sync(); ts.append(a.elapsed_time(b))
 t = min(ts[2:])
+import hashlib
+print("verdict sha1", hashlib.sha1(verd.cpu().numpy().tobytes()).hexdigest()[:16])
 print(f"K4 p={p_occ}: {t:.3f} ms  {npose / t / 1e6:.2f} Gchecks/s  {89 * npose / t / 1e6:.0f} GB/s algorithmic  colliding={verd.float().mean().item():.3f}")
