@@ -52,13 +52,10 @@ __global__ void __launch_bounds__(256) collide_circles_u8_kernel(hpp_geom g, cir
 // (DRAM traffic is 0.67x the algorithmic bytes).  Pass 1 decides ~99.6 % of the poses in ~1/5 of the instructions and
 // appends the rest to a list (one atomicAdd per warp); pass 2 is the exact kernel over that list.
 __global__ void __launch_bounds__(256) collide_filter_kernel(filt_consts fc, const uint8_t *__restrict__ d2, int tiles_x,
-                                                             float res_f, const double *__restrict__ xyh, size_t n,
+                                                             const double *__restrict__ xyh, size_t n,
                                                              uint8_t *__restrict__ verdict,
                                                              uint32_t *__restrict__ undecided,
                                                              unsigned long long *__restrict__ n_undecided) {
-  __shared__ float lut[256];
-  lut[threadIdx.x] = __fmul_rn(__fsqrt_rn((float)threadIdx.x), res_f);
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t n_up = (n + 31) & ~(size_t)31;  // whole warps run the loop (the ballot below)
@@ -67,7 +64,7 @@ __global__ void __launch_bounds__(256) collide_filter_kernel(filt_consts fc, con
     int r = 0;
     if (in) {
       const double x = xyh[3 * i], y = xyh[3 * i + 1], h = xyh[3 * i + 2];
-      r = fc.on ? circles_filter_u8<0, 4>(fc, d2, tiles_x, lut, x, y, h) : 2;
+      r = fc.on ? circles_filter_u8<0, 4>(fc, d2, tiles_x, x, y, h) : 2;
       if (r != 2) verdict[i] = (uint8_t)r;
     }
     const unsigned m = __ballot_sync(0xffffffffu, r == 2);
@@ -178,9 +175,9 @@ static filt_consts make_fc(const hpp_map *m) {
   const double E = ldexp(D, -23) + C * (4e-6 + ldexp(1.0, -21));
   const double V = sqrt(255.0) * g.res * (1.0 + 1e-6);
   const double r = m->car.cr;
-  const double M = 2.0 * g.res * (1.0 + ldexp(1.0, -19)) * E + 20.0 * ldexp(V, -24) + ldexp(fabs(r), -23);
-  fc.r_lo = nextafterf((float)(r - 1.5 * M), -INFINITY);
-  fc.r_hi = nextafterf((float)(r + 1.5 * M), INFINITY);
+  const double M = 2.0 * g.res * (1.0 + ldexp(1.0, -19)) * E + 48.0 * ldexp(V, -24) + ldexp(fabs(r), -23);
+  fc.r_lo = nextafterf((float)((r - 1.5 * M) / g.res), -INFINITY);
+  fc.r_hi = nextafterf((float)((r + 1.5 * M) / g.res), INFINITY);
   fc.W = g.W;
   fc.H = g.H;
   fc.on = g.W >= 8 && g.H >= 8 && C < 1e5 && r > 0.0 && r - 1.5 * M > 0.0;
@@ -215,7 +212,7 @@ extern "C" hpp_status hpp_collide_circles_dev(hpp_map *m, const double *xyh_dev,
     uint32_t *d_list = (uint32_t *)((uint8_t *)scr + 256);
     HPP_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), c->stream));
     const filt_consts fc = make_fc(m);
-    collide_filter_kernel<<<grid, 256, 0, c->stream>>>(fc, m->d_d2u8, m->d2_tiles_x, m->g.res_f, xyh_dev, n, verdict_dev,
+    collide_filter_kernel<<<grid, 256, 0, c->stream>>>(fc, m->d_d2u8, m->d2_tiles_x, xyh_dev, n, verdict_dev,
                                                        d_list, d_count);
     HPP_LAUNCHED(c);
     collide_u8_list_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(m->g, make_cc(m), m->d_d2u8, m->d2_tiles_x, xyh_dev,

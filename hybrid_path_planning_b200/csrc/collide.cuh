@@ -158,24 +158,30 @@ __device__ __forceinline__ int circle_hits_u8(const hpp_geom &g, const uint8_t *
 //    index coordinate (its cast and the final subtraction round by half an ulp each), C = max_k (|cx_k| + |cy_k|) / res
 //    is the circle offset in cells, e_sc = 4e-6 bounds sine and cosine: heading cast (|h| <= 16: 9.6e-7), two-constant
 //    range reduction (2.4e-7), clamp to the documented __sinf/__cosf range (5e-7), and their error there (2^-21.41).
-//  * The float32 interpolation itself: 10 operations on values <= V, <= 16 * 2^-24 * V.
-// So |value32 - value_ref| <= M = 2 res (1 + 2^-19) E + 20 * 2^-24 V + 2^-23 r, and the host passes r_lo = (r - 1.5 M)
-// rounded down and r_hi = (r + 1.5 M) rounded up: value32 < r_lo means the reference saw value < r, value32 > r_hi
-// means it did not.  A collision on ANY circle is the reference's verdict, so one certain hit decides the pose; a
+//  * The float32 interpolation itself works in cells on sqrt.approx(d2) (relative error 2^-23; the layer holds
+//    RN(RN(sqrt d2) * res_f), another 2^-23) and takes 10 operations on values <= V: <= 48 * 2^-24 * V in all.
+// So |res * value32 - value_ref| <= M = 2 res (1 + 2^-19) E + 48 * 2^-24 V + 2^-23 r, and the host passes
+// r_lo = (r - 1.5 M) / res rounded down and r_hi = (r + 1.5 M) / res rounded up: value32 < r_lo means the reference saw
+// value < r, value32 > r_hi means it did not.  A collision on ANY circle is the reference's verdict, so one certain hit decides the pose; a
 // free verdict needs all four circles certainly free.  On the cfg4 map 0.4 % of the poses come back undecided.
 struct filt_consts {
   double x0, y0;      // centre of cell (0,0): pos + (0.5 len - 0.5 res)
   double rcp_res;
   float cu[4], cv[4]; // circle offsets in cells
-  float r_lo, r_hi;
+  float r_lo, r_hi;   // in cells
   int W, H, on;       // on = 0: map too small for the border rule, everything is undecided
 };
 
-__device__ __forceinline__ uint32_t d2_col(int i) { return ((uint32_t)(i >> 3) << 5) + (uint32_t)(i & 7); }
+// sqrt.approx.f32: one MUFU, maximum relative error 2^-23 (PTX ISA); the margin below carries it
+__device__ __forceinline__ float filt_sqrt(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
 
 template <int FIRST, int LAST>
 __device__ __forceinline__ int circles_filter_u8(const filt_consts &fc, const uint8_t *__restrict__ d2, int tiles_x,
-                                                 const float *lut, double x, double y, double h) {
+                                                 double x, double y, double h) {
   const float hf = (float)h;
   if (!(fabsf(hf) <= 16.f)) return 2;
   const float kf = rintf(hf * 0.15915494f);
@@ -188,19 +194,31 @@ __device__ __forceinline__ int circles_filter_u8(const filt_consts &fc, const ui
   int undecided = 0;
 #pragma unroll
   for (int k = FIRST; k < LAST; k++) {
-    const float u = ax - (fc.cu[k] * c - fc.cv[k] * s);
-    const float v = ay - (fc.cu[k] * s + fc.cv[k] * c);
-    const float ful = floorf(u), fvl = floorf(v);
-    const int il = (int)ful, jl = (int)fvl;
+    const float u = fmaf(fc.cv[k], s, fmaf(-fc.cu[k], c, ax));
+    const float v = fmaf(-fc.cv[k], c, fmaf(-fc.cu[k], s, ay));
+    // floor without the conversion pipe: u + 1.5 * 2^23 rounded DOWN is floor(u) + 1.5 * 2^23 exactly (ulp 1 there), its
+    // low bits are the integer.  NaN, infinite and huge u give an index far outside the map: undecided.
+    const float tu = __fadd_rd(u, 12582912.f), tv = __fadd_rd(v, 12582912.f);
+    const int il = __float_as_int(tu) - 0x4B400000, jl = __float_as_int(tv) - 0x4B400000;
     if (!((unsigned)(il - 2) <= (unsigned)(fc.W - 6) && (unsigned)(jl - 2) <= (unsigned)(fc.H - 6))) return 2;
-    const float fu = u - ful, fv = v - fvl;
-    const uint32_t c0 = d2_col(il), c1 = d2_col(il + 1);
-    const uint32_t r0 = (uint32_t)(jl >> 2) * ((uint32_t)tiles_x << 5) + ((uint32_t)(jl & 3) << 3);
-    const uint32_t r1 = (uint32_t)((jl + 1) >> 2) * ((uint32_t)tiles_x << 5) + ((uint32_t)((jl + 1) & 3) << 3);
-    const float f00 = lut[__ldg(d2 + (r0 + c0))], f10 = lut[__ldg(d2 + (r0 + c1))];
-    const float f01 = lut[__ldg(d2 + (r1 + c0))], f11 = lut[__ldg(d2 + (r1 + c1))];
-    const float lo = f00 + fu * (f10 - f00), hi = f01 + fu * (f11 - f01);
-    const float val = lo + fv * (hi - lo);
+    const float fu = u - (tu - 12582912.f), fv = v - (tv - 12582912.f);
+    // the taps: one 8-byte load per tile row brings (il, jl) and (il + 1, jl) together (the kernel is bound by L1 tag
+    // lookups, one per lane and load); only il % 8 == 7 needs the neighbouring tile
+    const uint32_t rs = (uint32_t)tiles_x << 5, tc = (uint32_t)(il >> 3) << 5;
+    const uint32_t r0 = (uint32_t)(jl >> 2) * rs + ((uint32_t)(jl & 3) << 3) + tc, r1 = r0 + ((jl & 3) == 3 ? rs - 24u : 8u);
+    const unsigned sh = (unsigned)(il & 7) << 3;
+    const unsigned long long q0 = __ldg((const unsigned long long *)(d2 + r0)) >> sh;
+    const unsigned long long q1 = __ldg((const unsigned long long *)(d2 + r1)) >> sh;
+    unsigned a00 = (unsigned)q0 & 0xffu, a10 = ((unsigned)q0 >> 8) & 0xffu;
+    unsigned a01 = (unsigned)q1 & 0xffu, a11 = ((unsigned)q1 >> 8) & 0xffu;
+    if (sh == 56u) {
+      a10 = __ldg(d2 + (r0 + 32u));
+      a11 = __ldg(d2 + (r1 + 32u));
+    }
+    const float f00 = filt_sqrt((float)a00), f10 = filt_sqrt((float)a10);
+    const float f01 = filt_sqrt((float)a01), f11 = filt_sqrt((float)a11);
+    const float lo = fmaf(fu, f10 - f00, f00), hi = fmaf(fu, f11 - f01, f01);
+    const float val = fmaf(fv, hi - lo, lo);  // in cells
     if (val < fc.r_lo) return 1;
     undecided |= !(val > fc.r_hi);
   }
