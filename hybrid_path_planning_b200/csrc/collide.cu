@@ -148,15 +148,7 @@ __global__ void __launch_bounds__(256) collide_sat_kernel(hpp_geom g, rect_const
   }
 }
 
-static circ_consts make_cc(const hpp_map *m) {
-  circ_consts cc;
-  for (int k = 0; k < 4; k++) {
-    cc.cx[k] = m->car.cx[k];
-    cc.cy[k] = m->car.cy[k];
-  }
-  cc.cr = m->car.cr;
-  return cc;
-}
+static circ_consts make_cc(const hpp_map *m) { return hpp_make_circ_consts(m); }
 // the float32 filter's constants and its certainty margin M (derivation: collide.cuh, circles_filter_u8)
 static filt_consts make_fc(const hpp_map *m) {
   filt_consts fc;
@@ -164,23 +156,19 @@ static filt_consts make_fc(const hpp_map *m) {
   fc.x0 = g.posx + (0.5 * g.lenx - 0.5 * g.res);
   fc.y0 = g.posy + (0.5 * g.leny - 0.5 * g.res);
   fc.rcp_res = g.rcp_res;
-  double C = 0.0;
   for (int k = 0; k < 4; k++) {
     fc.cu[k] = (float)(m->car.cx[k] / g.res);
     fc.cv[k] = (float)(m->car.cy[k] / g.res);
-    const double ck = (fabs(m->car.cx[k]) + fabs(m->car.cy[k])) / g.res;
-    if (ck > C) C = ck;
   }
-  const double D = (double)(g.W > g.H ? g.W : g.H) + 4.0;
-  const double E = ldexp(D, -23) + C * (4e-6 + ldexp(1.0, -21));
+  const filt_margin fm = hpp_filt_margin(m);
   const double V = sqrt(255.0) * g.res * (1.0 + 1e-6);
   const double r = m->car.cr;
-  const double M = 2.0 * g.res * (1.0 + ldexp(1.0, -19)) * E + 48.0 * ldexp(V, -24) + ldexp(fabs(r), -23);
+  const double M = fm.A + 48.0 * ldexp(V, -24);
   fc.r_lo = nextafterf((float)((r - 1.5 * M) / g.res), -INFINITY);
   fc.r_hi = nextafterf((float)((r + 1.5 * M) / g.res), INFINITY);
   fc.W = g.W;
   fc.H = g.H;
-  fc.on = g.W >= 8 && g.H >= 8 && C < 1e5 && r > 0.0 && r - 1.5 * M > 0.0;
+  fc.on = g.W >= 8 && g.H >= 8 && fm.C < 1e5 && r > 0.0 && r - 1.5 * M > 0.0;
   return fc;
 }
 static rect_consts make_rc(const hpp_map *m) {

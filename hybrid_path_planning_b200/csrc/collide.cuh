@@ -10,10 +10,18 @@
 // All arithmetic is fp64 in the reference's operation order; the library is compiled with -fmad=false so
 // nothing is contracted into FMAs (the reference build targets baseline x86-64: no FMA).
 #pragma once
+#include <math.h>
+#include <stdlib.h>
+
 #include "hpp_internal.cuh"
 
 struct circ_consts {
   double cx[4], cy[4], cr;
+  // the float32 filter over the float distance layer (circles_filter_f32 below; hpp_make_circ_consts fills them)
+  double fx0, fy0;      // centre of cell (0,0): pos + (0.5 len - 0.5 res)
+  float fcu[4], fcv[4]; // circle offsets in cells
+  float f_lo, f_hi;     // certain collision below f_lo, certainly clear above f_hi (metres)
+  int f_on;
 };
 // CarData::setCircles' bounding circle (RS/src/CarData.cpp:78-81), for isSingleStateCollisionFreeImproved
 struct bound_consts {
@@ -225,6 +233,57 @@ __device__ __forceinline__ int circles_filter_u8(const filt_consts &fc, const ui
   return undecided ? 2 : 0;
 }
 
+// The same filter over the FLOAT distance layer (the planner's per-query chains: maps of a few hundred cells that live
+// in L1/L2, where the fp64 position arithmetic -- not the taps -- is the dependent chain).  All four circles at once,
+// sixteen taps in flight.  The layer is not clamped here, so the interpolation error is relative to the taps at hand
+// (all within 1.5 res of the value): with A = 2 res (1 + 2^-19) E + 2^-23 r and B = 48 * 2^-24 the verdict is certain
+// when value32 (1 + B) < r - A - 1.5 res B (collision) or value32 (1 - B) > r + A + 1.5 res B (clear); the host folds
+// that, with the same 1.5 x slack as above, into f_lo and f_hi.
+__device__ __forceinline__ int circles_filter_f32(const hpp_geom &g, const circ_consts &cc, const float *__restrict__ dist,
+                                                  double x, double y, double h) {
+  const float hf = (float)h;
+  if (!(fabsf(hf) <= 16.f)) return 2;
+  const float kf = rintf(hf * 0.15915494f);
+  float hr = fmaf(-kf, 6.2831855f, hf);
+  hr = fmaf(kf, 1.7484555e-7f, hr);
+  hr = fminf(fmaxf(hr, -3.1415925f), 3.1415925f);
+  float s, c;
+  __sincosf(hr, &s, &c);
+  const float ax = (float)((cc.fx0 - x) * g.rcp_res), ay = (float)((cc.fy0 - y) * g.rcp_res);
+  float fu[4], fv[4];
+  int base[4];
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float u = fmaf(cc.fcv[k], s, fmaf(-cc.fcu[k], c, ax));
+    const float v = fmaf(-cc.fcv[k], c, fmaf(-cc.fcu[k], s, ay));
+    const float tu = __fadd_rd(u, 12582912.f), tv = __fadd_rd(v, 12582912.f);
+    const int il = __float_as_int(tu) - 0x4B400000, jl = __float_as_int(tv) - 0x4B400000;
+    inside = inside && (unsigned)(il - 2) <= (unsigned)(g.W - 6) && (unsigned)(jl - 2) <= (unsigned)(g.H - 6);
+    fu[k] = u - (tu - 12582912.f);
+    fv[k] = v - (tv - 12582912.f);
+    base[k] = jl * g.W + il;
+  }
+  if (!inside) return 2;
+  float f[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    f[k][0] = __ldg(dist + base[k]);
+    f[k][1] = __ldg(dist + base[k] + 1);
+    f[k][2] = __ldg(dist + base[k] + g.W);
+    f[k][3] = __ldg(dist + base[k] + g.W + 1);
+  }
+  int hit = 0, undecided = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float lo = fmaf(fu[k], f[k][1] - f[k][0], f[k][0]), hi = fmaf(fu[k], f[k][3] - f[k][2], f[k][2]);
+    const float val = fmaf(fv[k], hi - lo, lo);
+    hit |= val < cc.f_lo;
+    undecided |= !(val > cc.f_hi);
+  }
+  return hit ? 1 : (undecided ? 2 : 0);
+}
+
 // throughput form: the four circles in the reference's order, later circles are skipped after a hit
 __device__ __forceinline__ int circles_collide(const hpp_geom &g, const circ_consts &cc,
                                                const float *__restrict__ dist, double x, double y, double h) {
@@ -243,6 +302,10 @@ __device__ __forceinline__ int circles_collide(const hpp_geom &g, const circ_con
 // Not inlined: the planner kernels are instruction-fetch bound, one shared copy keeps their code small.
 static __device__ __noinline__ int circles_collide_ilp(const hpp_geom &g, const circ_consts &cc,
                                                    const float *__restrict__ dist, double x, double y, double h) {
+  if (cc.f_on) {
+    const int r = circles_filter_f32(g, cc, dist, x, y, h);
+    if (r != 2) return r;
+  }
   double s, c;
   sincos(h, &s, &c);
   circle_taps t[4];
@@ -261,6 +324,46 @@ static __device__ __noinline__ int circles_collide_ilp(const hpp_geom &g, const 
 #pragma unroll
   for (int k = 0; k < 4; k++) hit |= circle_finish(t[k], f[k][0], f[k][1], f[k][2], f[k][3], cc.cr);
   return hit;
+}
+
+// host: the circle constants of a map, exact part and filter part (margins derived at circles_filter_u8 / _f32)
+struct filt_margin {
+  double E, A, C;  // position error in cells, its share of the margin in metres, circle offset in cells
+};
+static inline filt_margin hpp_filt_margin(const hpp_map *m) {
+  const hpp_geom &g = m->g;
+  filt_margin fm;
+  fm.C = 0.0;
+  for (int k = 0; k < 4; k++) {
+    const double ck = (fabs(m->car.cx[k]) + fabs(m->car.cy[k])) / g.res;
+    if (ck > fm.C) fm.C = ck;
+  }
+  const double D = (double)(g.W > g.H ? g.W : g.H) + 4.0;
+  fm.E = ldexp(D, -23) + fm.C * (4e-6 + ldexp(1.0, -21));
+  fm.A = 2.0 * g.res * (1.0 + ldexp(1.0, -19)) * fm.E + ldexp(fabs(m->car.cr), -23);
+  return fm;
+}
+static inline circ_consts hpp_make_circ_consts(const hpp_map *m) {
+  circ_consts cc;
+  const hpp_geom &g = m->g;
+  for (int k = 0; k < 4; k++) {
+    cc.cx[k] = m->car.cx[k];
+    cc.cy[k] = m->car.cy[k];
+    cc.fcu[k] = (float)(m->car.cx[k] / g.res);
+    cc.fcv[k] = (float)(m->car.cy[k] / g.res);
+  }
+  cc.cr = m->car.cr;
+  cc.fx0 = g.posx + (0.5 * g.lenx - 0.5 * g.res);
+  cc.fy0 = g.posy + (0.5 * g.leny - 0.5 * g.res);
+  const filt_margin fm = hpp_filt_margin(m);
+  const double B = 48.0 * ldexp(1.0, -24), r = m->car.cr;
+  const double lo = (r - 1.5 * (fm.A + 1.5 * g.res * B)) / (1.0 + 1.5 * B);
+  const double hi = (r + 1.5 * (fm.A + 1.5 * g.res * B)) / (1.0 - 1.5 * B);
+  cc.f_lo = nextafterf((float)lo, -INFINITY);
+  cc.f_hi = nextafterf((float)hi, INFINITY);
+  static const bool off = getenv("HPP_NO_FILTER") != nullptr;  // exact arithmetic everywhere (same results, for comparison)
+  cc.f_on = !off && g.W >= 8 && g.H >= 8 && fm.C < 1e5 && r > 0.0 && lo > 0.0;
+  return cc;
 }
 
 // ---------------------------------------------------------------------------------------- SAT

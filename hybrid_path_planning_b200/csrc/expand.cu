@@ -102,12 +102,7 @@ extern "C" hpp_status hpp_expand_dev(hpp_map *m, int variant, const hpp_node *pa
   expand_consts ec;
   hpp_make_expand_consts(m, variant, &ec);
   if (variant == HPP_VARIANT_RS) {
-    circ_consts cc;
-    for (int k = 0; k < 4; k++) {
-      cc.cx[k] = m->car.cx[k];
-      cc.cy[k] = m->car.cy[k];
-    }
-    cc.cr = m->car.cr;
+    const circ_consts cc = hpp_make_circ_consts(m);
     long long want = hpp_div_up((long long)n, 8);
     int grid = (int)(want < (long long)c->sm_count * 8 ? want : (long long)c->sm_count * 8);
     expand_rs_kernel<<<grid, 256, 0, c->stream>>>(m->g, ec, cc, m->d_distance, parents_dev, n, children_dev);

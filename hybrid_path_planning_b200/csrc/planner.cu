@@ -1216,11 +1216,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
     memset(&pc, 0, sizeof pc);
     pc.g = m0->g;
     hpp_make_expand_consts(m0, variant, &pc.ec);
-    for (int k = 0; k < 4; k++) {
-      pc.cc.cx[k] = m0->car.cx[k];
-      pc.cc.cy[k] = m0->car.cy[k];
-    }
-    pc.cc.cr = m0->car.cr;
+    pc.cc = hpp_make_circ_consts(m0);
     for (int k = 0; k < 5; k++) {
       pc.rx[k] = m0->car.rx[k];
       pc.ry[k] = m0->car.ry[k];

@@ -7,15 +7,7 @@ struct rect_consts {
   float rx[5], ry[5];
 };
 
-static circ_consts make_cc(const hpp_map *m) {
-  circ_consts cc;
-  for (int k = 0; k < 4; k++) {
-    cc.cx[k] = m->car.cx[k];
-    cc.cy[k] = m->car.cy[k];
-  }
-  cc.cr = m->car.cr;
-  return cc;
-}
+static circ_consts make_cc(const hpp_map *m) { return hpp_make_circ_consts(m); }
 static rect_consts make_rc(const hpp_map *m) {
   rect_consts rc;
   for (int k = 0; k < 5; k++) {
