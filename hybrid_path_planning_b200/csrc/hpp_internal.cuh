@@ -21,6 +21,7 @@ struct hpp_ctx {
   uint32_t *h_flags;   // pinned host, 64 words
   uint32_t *d_flags;   // device, 64 words
   // grow-only scratch (device) + pinned host staging for the host-pointer entry points
+  int refs;              // the creator's reference + one per live map / communicator (hpp_ctx_retain / _release)
   void *d_scratch[8];
   size_t d_scratch_bytes[8];
   void *h_pinned[2];
@@ -35,6 +36,11 @@ struct hpp_ctx {
 #define CLS_NEAR4 0x40    // some in-bounds 4-neighbour is blocked (RS/src/HybridAstar.cpp:507-519)
 #define CLS_CNT_MASK 0x0F // number of isInCollision cells in the 3x3 block, out of bounds included
                           // (DB/src/HybridAstar.cpp:204-218)
+
+// Maps and communicators keep their context alive: hpp_ctx_destroy drops the creator's reference and the resources
+// go with the last one, whatever order a garbage-collected host language finalises the handles in.
+void hpp_ctx_retain(hpp_ctx *c);
+void hpp_ctx_release(hpp_ctx *c);
 
 struct hpp_geom {
   int W, H;

@@ -25,12 +25,15 @@ extern "C" hpp_status hpp_ctx_create(int device, hpp_ctx **out) {
     free(c);
     return HPP_ERR_CUDA;
   }
+  c->refs = 1;
   *out = c;
   return HPP_OK;
 }
 
-extern "C" hpp_status hpp_ctx_destroy(hpp_ctx *c) {
-  if (!c) return HPP_ERR_ARG;
+void hpp_ctx_retain(hpp_ctx *c) { __atomic_add_fetch(&c->refs, 1, __ATOMIC_RELAXED); }
+
+void hpp_ctx_release(hpp_ctx *c) {
+  if (__atomic_sub_fetch(&c->refs, 1, __ATOMIC_ACQ_REL) > 0) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 8; i++)
@@ -46,6 +49,13 @@ extern "C" hpp_status hpp_ctx_destroy(hpp_ctx *c) {
   }
   cudaStreamDestroy(c->stream);
   free(c);
+}
+
+extern "C" hpp_status hpp_ctx_destroy(hpp_ctx *c) {
+  if (!c) return HPP_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  hpp_ctx_release(c);  // the resources go now, or with the last map / communicator still alive
   return HPP_OK;
 }
 
@@ -264,6 +274,7 @@ static hpp_status map_alloc(hpp_ctx *c, uint32_t W, uint32_t H, float resolution
   hpp_map *m = (hpp_map *)calloc(1, sizeof(hpp_map));
   if (!m) return HPP_ERR_NOMEM;
   m->ctx = c;
+  hpp_ctx_retain(c);  // released by hpp_map_destroy
   m->n = (size_t)W * H;
   m->g.W = (int)W;
   m->g.H = (int)H;
@@ -370,7 +381,9 @@ extern "C" hpp_status hpp_map_destroy(hpp_map *m) {
   cudaFree(m->d_obstacle);
   cudaFree(m->d_distance);
   cudaFree(m->d_d2u8);
+  hpp_ctx *c = m->ctx;
   free(m);
+  hpp_ctx_release(c);
   return HPP_OK;
 }
 

@@ -126,6 +126,7 @@ extern "C" hpp_status hpp_comm_create(hpp_ctx *c, const uint8_t id[HPP_COMM_ID_B
   HPP_NCCL(c, a->CommInitRank(&comm, world, u, rank));
   hpp_comm *k = new hpp_comm;
   k->ctx = c;
+  hpp_ctx_retain(c);  // released by hpp_comm_destroy
   k->comm = comm;
   k->rank = rank;
   k->world = world;
@@ -138,7 +139,9 @@ extern "C" void hpp_comm_destroy(hpp_comm *k) {
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   nccl()->CommDestroy(k->comm);
+  hpp_ctx *c = k->ctx;
   delete k;
+  hpp_ctx_release(c);
 }
 
 extern "C" int hpp_comm_rank(const hpp_comm *k) { return k ? k->rank : -1; }

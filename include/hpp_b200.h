@@ -59,6 +59,9 @@ typedef struct {
 
 /* ---------------------------------------------------------------- context */
 hpp_status hpp_ctx_create(int device, hpp_ctx **out);
+/* Maps and communicators keep their context alive: hpp_ctx_destroy gives up the caller's reference, and the stream and
+ * scratch memory are released with the last map / communicator of the context (so a garbage-collected binding may
+ * finalise its handles in any order).  The ctx pointer itself must not be passed to any call after hpp_ctx_destroy. */
 hpp_status hpp_ctx_destroy(hpp_ctx *ctx);
 hpp_status hpp_ctx_sync(hpp_ctx *ctx);
 void *hpp_ctx_stream(hpp_ctx *ctx); /* cudaStream_t the ctx enqueues on */
