@@ -64,7 +64,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(HERE, "libhpp_b200.so")
+    """HPP_B200_LIB: another build of the same library (A/B measurements of two builds inside one GPU session)"""
+    return os.environ.get("HPP_B200_LIB") or os.path.join(HERE, "libhpp_b200.so")
 
 
 def lib():

@@ -307,7 +307,7 @@ static __device__ __noinline__ int circles_collide_ilp(const hpp_geom &g, const 
     if (r != 2) return r;
   }
   double s, c;
-  sincos(h, &s, &c);
+  hpp_sincos(h, &s, &c);
   circle_taps t[4];
   float f[4][4];
 #pragma unroll

@@ -18,7 +18,7 @@ struct expand_consts {
 // one Euler step of the bicycle model (RS/src/CarData.cpp:63-74): heading is NOT normalised
 __device__ __forceinline__ void vehicle_step(double &x, double &y, double &h, double m, double dt, double dtheta) {
   double s, c;
-  sincos(h, &s, &c);
+  hpp_sincos(h, &s, &c);
   x = x + (m * dt * c);
   y = y + (m * dt * s);
   h = h + (m * dt * dtheta);

@@ -139,6 +139,39 @@ static inline int hpp_div_up(long long a, long long b) { return (int)((a + b - 1
 // double (24 significant bits), so it always holds here; checked against a/d on 3.2e9 random operands over 22 resolutions
 // and exponents +-930.  Zeros, subnormal-range and huge operands take the plain division.
 #ifdef __CUDACC__
+// libm by CALL, for the planner and shot code.  An inlined fp64 sincos is ~950 SASS instructions (argument reduction with its
+// Payne-Hanek slow path, two polynomials), tan / atan2 / acos are of the same order, and the Reeds-Shepp formulas, the path
+// samplers and the footprint check hold some sixty call sites: inlined, plan_pipe_kernel was 185 KB of code, more than the
+// SM's instruction cache, and ncu showed `no_instruction` as its first stall reason (12.6 cycles per issued instruction
+// with two CTAs per SM).  One copy per translation unit, same code as the inlined form, so the same bits.
+#ifdef HPP_LIBM_INLINE  // (A/B builds: -DHPP_LIBM_INLINE gives the inlined form back)
+#define HPP_LIBM_CALL __forceinline__
+#else
+#define HPP_LIBM_CALL __noinline__
+#endif
+struct hpp_sc {
+  double s, c;
+};
+[[maybe_unused]] static __device__ HPP_LIBM_CALL hpp_sc hpp_sincos_call(double a) {
+  hpp_sc r;
+  sincos(a, &r.s, &r.c);
+  return r;
+}
+__device__ __forceinline__ void hpp_sincos(double a, double *s, double *c) {
+  const hpp_sc r = hpp_sincos_call(a);
+  *s = r.s;
+  *c = r.c;
+}
+[[maybe_unused]] static __device__ HPP_LIBM_CALL double hpp_sin(double a) { return sin(a); }
+[[maybe_unused]] static __device__ HPP_LIBM_CALL double hpp_cos(double a) { return cos(a); }
+[[maybe_unused]] static __device__ HPP_LIBM_CALL double hpp_tan(double a) { return tan(a); }
+[[maybe_unused]] static __device__ HPP_LIBM_CALL double hpp_atan2(double y, double x) { return atan2(y, x); }
+[[maybe_unused]] static __device__ HPP_LIBM_CALL double hpp_acos(double a) { return acos(a); }
+[[maybe_unused]] static __device__ HPP_LIBM_CALL double hpp_asin(double a) { return asin(a); }
+[[maybe_unused]] static __device__ HPP_LIBM_CALL double hpp_fmod(double a, double b) { return fmod(a, b); }
+#endif
+
+#ifdef __CUDACC__
 static __device__ __noinline__ double hpp_div_slow(double a, double d) { return a / d; }  // cold: one copy per kernel
 __device__ __forceinline__ double hpp_div_res(const hpp_geom &g, double a) {
   const double m = fabs(a);
