@@ -510,8 +510,9 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
     if (prof && tid == 0 && iterations > 3000) {
       for (int i = 0; i < 7; i++) atomicAdd(prof + i, pf[i]);
       atomicAdd(prof + 7, (unsigned long long)iterations);
+      for (int i = 8; i < 12; i++) atomicAdd(prof + i, pf[i]);
     }
-    for (int i = 0; i < 8; i++) pf[i] = 0;
+    for (int i = 0; i < 12; i++) pf[i] = 0;
 #endif
     if (wid != 0) continue;  // the back-track is warp 0's
 
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
                                                             unsigned long long *__restrict__ prof) {
   constexpr int THREADS = NW * 32;
 #ifdef HPP_PLAN_PROF
-  unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long pf[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PIPE_T0 const long long t0_ = clock64();
 #define PIPE_ADD(i) pf[i] += (unsigned long long)(clock64() - t0_);
 #else
@@ -839,6 +840,9 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       iterations++;
       if (iterations > PLAN_ITER_CAP) break;
       // ---- pop
+#ifdef HPP_PLAN_PROF
+      const long long tp_ = clock64();
+#endif
       const int top = gheap_pop_warp(hkey, hidx, hn);
       int tv = 0;
       if (lane == 0) {
@@ -848,6 +852,9 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         if (tv >= 0 && !(tv & 1)) table[slot] = tv | 1;  // openSet.erase + closedSet[currentState] = currentNode
       }
       tv = __shfl_sync(FULLM, tv, 0);
+#ifdef HPP_PLAN_PROF
+      pf[8] += (unsigned long long)(clock64() - tp_);
+#endif
       if (tv < 0 || (tv & 1)) continue;  // already in the closed set
       const int cur = tv >> 1;
       const pnode cn = nodes[cur];
@@ -885,9 +892,16 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         sm.exp_from[0] = cn.x; sm.exp_from[1] = cn.y; sm.exp_from[2] = cn.h;
         sm.exp_hit = 0u;
       }
+#ifdef HPP_PLAN_PROF
+      const long long te_ = clock64();
+#endif
       pipe_exp_barrier();
       rollouts();
       pipe_exp_barrier();
+#ifdef HPP_PLAN_PROF
+      const long long ti_ = clock64();
+      pf[9] += (unsigned long long)(ti_ - te_);
+#endif
       double cxs = 0, cys = 0, chs = 0, ccost = 0, fkey = 0.0;
       int valid = 0, ins_slot = -1, replace = 0;
       if (lane < ncmd) {
@@ -934,6 +948,10 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         }
       }
       __syncwarp();
+#ifdef HPP_PLAN_PROF
+      const long long tq_ = clock64();
+      pf[10] += (unsigned long long)(tq_ - ti_);
+#endif
       for (unsigned mset = vm; mset;) {  // heap pushes in command order
         const int b = __ffs(mset) - 1;
         mset &= mset - 1;
@@ -942,6 +960,9 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         gheap_push_warp(hkey, hidx, hn, k, my);
       }
       n_nodes += n_new;
+#ifdef HPP_PLAN_PROF
+      pf[11] += (unsigned long long)(clock64() - tq_);
+#endif
     }
 #ifdef HPP_PLAN_PROF
     pf[4] += (unsigned long long)(clock64() - tloop_);
@@ -1197,7 +1218,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   cudaMemsetAsync(d_cursor, 0, 16, c->stream);
   unsigned long long *d_prof = nullptr;
 #ifdef HPP_PLAN_PROF
-  if (hpp_scratch(c, 5, 64, (void **)&d_prof) == HPP_OK) cudaMemsetAsync(d_prof, 0, 64, c->stream);
+  if (hpp_scratch(c, 5, 128, (void **)&d_prof) == HPP_OK) cudaMemsetAsync(d_prof, 0, 128, c->stream);
 #endif
   std::vector<int> fq(n);
   std::vector<int32_t> chunk_goals;
@@ -1357,14 +1378,15 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   }
 #ifdef HPP_PLAN_PROF
   if (st == HPP_OK) {
-    unsigned long long hp[8];
+    unsigned long long hp[16];
     void *dp = nullptr;
-    if (hpp_scratch(c, 5, 64, &dp) == HPP_OK && cudaMemcpy(hp, dp, 64, cudaMemcpyDeviceToHost) == cudaSuccess && hp[7])
+    if (hpp_scratch(c, 5, 128, &dp) == HPP_OK && cudaMemcpy(hp, dp, 128, cudaMemcpyDeviceToHost) == cudaSuccess && hp[7])
       if (variant == HPP_VARIANT_RS)
         fprintf(stderr, "[pipe prof] worker 1 of every CTA: %llu shots, %.1f paths/shot, generate %.0f + path checks %.0f cycles per "
                 "shot; controllers of long queries: %llu iterations, loop %.0f cycles/iteration of which ring-full waits %.0f, "
-                "drain %.0f cycles/query-iteration\n", hp[2], hp[2] ? (double)hp[3] / hp[2] : 0.0, hp[2] ? (double)hp[0] / hp[2] : 0.0,
-                hp[2] ? (double)hp[1] / hp[2] : 0.0, hp[7], (double)hp[4] / hp[7], (double)hp[5] / hp[7], (double)hp[6] / hp[7]);
+                "drain %.0f cycles/query-iteration; pop %.0f expansion %.0f insert %.0f pushes %.0f\n", hp[2], hp[2] ? (double)hp[3] / hp[2] : 0.0, hp[2] ? (double)hp[0] / hp[2] : 0.0,
+                hp[2] ? (double)hp[1] / hp[2] : 0.0, hp[7], (double)hp[4] / hp[7], (double)hp[5] / hp[7], (double)hp[6] / hp[7],
+                (double)hp[8] / hp[7], (double)hp[9] / hp[7], (double)hp[10] / hp[7], (double)hp[11] / hp[7]);
       else
       fprintf(stderr, "[plan prof] %llu iterations of long queries; cycles/iteration: pop %.0f formulas %.0f dedup+order %.0f "
               "path checks %.0f expand %.0f insert %.0f push %.0f\n", hp[7], (double)hp[0] / hp[7], (double)hp[6] / hp[7],
