@@ -247,6 +247,115 @@ __device__ __forceinline__ void gheap_push_warp(double *key, int *idx, int &n, d
   __syncwarp();
 }
 
+// The pushes of one expansion (up to 26, no pop in between) as ONE memory round trip.  gheap_push_warp costs a round
+// trip per push (its ancestors are loaded after the previous push has stored), and an expansion's pushes were 5.6 k of
+// the 19 k cycles of an iteration on the parking maps.  The ancestors of the new slots n+1 .. n+m overlap almost
+// entirely: level L (L-th ancestors) holds the consecutive slots (n+1)>>L .. (n+m)>>L, at most m / 2^L + 2 of them, ~60
+// entries in all.  They are loaded into shared memory together, the m sift-ups run there one after the other with the
+// same ballot as gheap_push_warp (so the result is the sequential one, std::push_heap after std::push_heap), and
+// everything is stored back together.  A batch that crosses a power of two (the new slots are on two depths, so one
+// slot would sit on two levels of the cache), a heap below 64 entries or a single push take gheap_push_warp.
+#define HEAP_CACHE_LEVELS 19
+#define HEAP_CACHE_WIDTH 28
+struct heap_cache {
+  double key[HEAP_CACHE_LEVELS][HEAP_CACHE_WIDTH];
+  int idx[HEAP_CACHE_LEVELS][HEAP_CACHE_WIDTH];
+};
+// fkey: the key of the lane's entry (lanes of vm, pushed in lane order); payloads first_id, first_id + 1, ...
+__device__ __forceinline__ void gheap_push_batch(double *key, int *idx, int &n, heap_cache &hc, double fkey, unsigned vm,
+                                                 int first_id) {
+  const unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int m = __popc(vm);
+  const int s1 = n + 1, s2 = n + m;  // 1-based slots of the new entries: the parent of slot s is s >> 1
+  const int D = 31 - __clz(s1);      // depth of the new slots = number of ancestor levels
+  if (m < 2 || s1 < 64 || 31 - __clz(s2) != D || D >= HEAP_CACHE_LEVELS || m > HEAP_CACHE_WIDTH - 2) {
+    int j = 0;
+    for (unsigned mset = vm; mset; j++) {
+      const int b = __ffs(mset) - 1;
+      mset &= mset - 1;
+      gheap_push_warp(key, idx, n, __shfl_sync(FULLM, fkey, b), first_id + j);
+    }
+    return;
+  }
+  // every lane takes at most one entry of levels 1..4 (at most 14 + 8 + 5 + 3 slots) and one of levels 5..D (at most two
+  // slots each): all loads are issued before the first is used, one round trip
+  int La = 0, da = 0, Lb = 5 + (lane >> 1), db = lane & 1;
+  {
+    int rest = lane;
+    for (int L = 1; L <= 4 && La == 0; L++) {
+      const int cnt = (s2 >> L) - (s1 >> L) + 1;
+      if (rest < cnt) {
+        La = L;
+        da = rest;
+      }
+      rest -= cnt;
+    }
+  }
+  const bool va = La != 0, vb = Lb <= D && db < (s2 >> Lb) - (s1 >> Lb) + 1;
+  const int na_ = va ? (s1 >> La) + da - 1 : 0, nb_ = vb ? (s1 >> Lb) + db - 1 : 0;  // 0-based heap positions
+  double ka_ = 0.0, kb_ = 0.0;
+  int ia_ = 0, ib_ = 0;
+  if (va) {
+    ka_ = key[na_];
+    ia_ = idx[na_];
+  }
+  if (vb) {
+    kb_ = key[nb_];
+    ib_ = idx[nb_];
+  }
+  if (va) {
+    hc.key[La][da] = ka_;
+    hc.idx[La][da] = ia_;
+  }
+  if (vb) {
+    hc.key[Lb][db] = kb_;
+    hc.idx[Lb][db] = ib_;
+  }
+  __syncwarp();
+  const bool lvl = lane <= D;  // lane t works on level t (0 = the new slot itself)
+  int j = 0;
+  for (unsigned mset = vm; mset; j++) {
+    const int b = __ffs(mset) - 1;
+    mset &= mset - 1;
+    const double k = __shfl_sync(FULLM, fkey, b);
+    const int s = s1 + j;
+    const int pos = lvl ? (s >> lane) - (s1 >> lane) : 0;
+    double a = 0.0;
+    int ai = 0;
+    if (lane >= 1 && lvl) {
+      a = hc.key[lane][pos];
+      ai = hc.idx[lane][pos];
+    }
+    const unsigned gt = __ballot_sync(FULLM, lane >= 1 && lvl && a > k);
+    const int moves = __ffs(~(gt >> 1)) - 1;  // leading run of ancestors that move down
+    const double a_up = __shfl_down_sync(FULLM, a, 1);
+    const int ai_up = __shfl_down_sync(FULLM, ai, 1);
+    if (lane < moves) {
+      hc.key[lane][pos] = a_up;
+      hc.idx[lane][pos] = ai_up;
+    } else if (lane == moves) {
+      hc.key[lane][pos] = k;
+      hc.idx[lane][pos] = first_id + j;
+    }
+    __syncwarp();
+  }
+  if (va) {
+    key[na_] = hc.key[La][da];
+    idx[na_] = hc.idx[La][da];
+  }
+  if (vb) {
+    key[nb_] = hc.key[Lb][db];
+    idx[nb_] = hc.idx[Lb][db];
+  }
+  if (lane < m) {  // the new slots themselves
+    key[n + lane] = hc.key[0][lane];
+    idx[n + lane] = hc.idx[0][lane];
+  }
+  n += m;
+  __syncwarp();
+}
+
 // what the threads of a query's CTA tell each other (two copies, alternating per iteration, so that one barrier per
 // hand-over is enough)
 struct plan_mail {
@@ -510,9 +619,8 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) plan_kernel(plan_consts pc, c
     if (prof && tid == 0 && iterations > 3000) {
       for (int i = 0; i < 7; i++) atomicAdd(prof + i, pf[i]);
       atomicAdd(prof + 7, (unsigned long long)iterations);
-      for (int i = 8; i < 12; i++) atomicAdd(prof + i, pf[i]);
     }
-    for (int i = 0; i < 12; i++) pf[i] = 0;
+    for (int i = 0; i < 8; i++) pf[i] = 0;
 #endif
     if (wid != 0) continue;  // the back-track is warp 0's
 
@@ -627,9 +735,11 @@ struct pipe_smem {
   unsigned exp_hit;                    // expansion: commands with a colliding state
   double exp_from[3];                  // expansion: the node being expanded
   double exp_child[HPP_MAX_COMMANDS][3];  // expansion: last state of every command's rollout
+  double exp_sc[HPP_MAX_COMMANDS][HPP_MAX_SIM][2];  // expansion: (m dt cos h_i, m dt sin h_i) of every command's step i
   pipe_job job[PIPE_RING];
   pipe_res res[PIPE_RING];
   pipe_worker w[NW - 1 - PIPE_EXP_WARPS];
+  heap_cache hcache;                   // controller: the ancestors of an expansion's pushes (gheap_push_batch)
 };
 // named barrier of the controller and its expansion helpers (barrier 0 is __syncthreads)
 __device__ __forceinline__ void pipe_exp_barrier() {
@@ -648,7 +758,9 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
                                                             int *__restrict__ idx_pool, int *__restrict__ table_pool,
                                                             hpp_plan *__restrict__ plans, double *__restrict__ traj,
                                                             unsigned long long traj_cap,
-                                                            unsigned long long *__restrict__ cursor,
+                                                            unsigned long long *__restrict__ cursor, int iter_budget,
+                                                            const int *__restrict__ qi_list, const int *__restrict__ n_list,
+                                                            int *__restrict__ deferred, int *__restrict__ n_deferred,
                                                             unsigned long long *__restrict__ prof) {
   constexpr int THREADS = NW * 32;
 #ifdef HPP_PLAN_PROF
@@ -682,8 +794,9 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       sm.exp_quit = 0;
     }
     __syncthreads();
-    const int qi = sm.query;
-    if (qi >= n_queries) break;
+    // second pass of a two-pass batch: the queries the first pass set aside (qi_list, *n_list of them)
+    if (sm.query >= (n_list ? *n_list : n_queries)) break;
+    const int qi = qi_list ? qi_list[sm.query] : sm.query;
     const int q = query_ids[qi];
     const double *hmap = fields + (size_t)field_of_query[qi] * map_size;
     const plan_map_desc md = descs[map_of_query ? map_of_query[q] : 0];
@@ -695,11 +808,31 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
     // one thread per (command, state of its rollout) of the node in sm.exp_from (GetnextNeighbours,
     // RS/src/HybridAstar.cpp:25-79); run by the controller and its helpers between two named barriers
     auto rollouts = [&]() {
-      // tid < 128 here; pathLength 4 (the default) gives 104 poses, pathLength 8 gives 208: a second round
-      for (int p = tid; p < ncmd * pc.ec.sim; p += (1 + PIPE_EXP_WARPS) * 32) {
+      // tid < 128 here; pathLength 4 (the default) gives 104 poses, pathLength 8 gives 208: a second round.
+      // CarData's Euler step (vehicle_step) is x += m dt cos h, y += m dt sin h, h += m dt dtheta: the headings of a
+      // command's steps do not depend on the positions, so thread (c, i) takes the sine and cosine of step i alone
+      // (one libm call instead of i + 1 in a row) and the positions are the same sums, in the same order, afterwards.
+      const int np = ncmd * pc.ec.sim;
+      for (int p = tid; p < np; p += (1 + PIPE_EXP_WARPS) * 32) {
         const int c = p / pc.ec.sim, i = p % pc.ec.sim;
+        const double m = pc.ec.dir[c], dt = pc.ec.step;
+        double h = sm.exp_from[2];
+        for (int k = 0; k < i; k++) h = h + (m * dt * pc.ec.dtheta[c]);
+        double sn, cs;
+        hpp_sincos(h, &sn, &cs);
+        sm.exp_sc[c][i][0] = m * dt * cs;
+        sm.exp_sc[c][i][1] = m * dt * sn;
+      }
+      pipe_exp_barrier();
+      for (int p = tid; p < np; p += (1 + PIPE_EXP_WARPS) * 32) {
+        const int c = p / pc.ec.sim, i = p % pc.ec.sim;
+        const double m = pc.ec.dir[c], dt = pc.ec.step;
         double x = sm.exp_from[0], y = sm.exp_from[1], h = sm.exp_from[2];
-        for (int k = 0; k <= i; k++) vehicle_step(x, y, h, pc.ec.dir[c], pc.ec.step, pc.ec.dtheta[c]);
+        for (int k = 0; k <= i; k++) {
+          x = x + sm.exp_sc[c][k][0];
+          y = y + sm.exp_sc[c][k][1];
+          h = h + (m * dt * pc.ec.dtheta[c]);
+        }
         if (circles_collide_ilp(g, pc.cc, dist, x, y, h)) atomicOr(&sm.exp_hit, 1u << c);
         if (i == pc.ec.sim - 1) {
           sm.exp_child[c][0] = x; sm.exp_child[c][1] = y; sm.exp_child[c][2] = h;
@@ -832,6 +965,7 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       }
     };
     int end_node = -1;  // node at which the loop itself ended by the goal test
+    bool set_aside = false;
 #ifdef HPP_PLAN_PROF
     const long long tloop_ = clock64();
 #endif
@@ -839,6 +973,10 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       if (retire()) break;
       iterations++;
       if (iterations > PLAN_ITER_CAP) break;
+      if (iterations > iter_budget) {  // a long query: set aside for the second pass (unless an earlier shot succeeds)
+        set_aside = true;
+        break;
+      }
       // ---- pop
 #ifdef HPP_PLAN_PROF
       const long long tp_ = clock64();
@@ -911,15 +1049,18 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       // ---- insert / replace in command order
       if (valid) {
         ccost = path_cost(pc.ec, lane, cn.cost, cn.steer, cn.dir);
+        // (the heuristic of the child's cell is fetched before the table is searched: one round trip less on the chain)
+        const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
+        const long nidx = (long)ccy * W + ccx;
+        const bool in_map = !(nidx < 0 || nidx >= map_size);
+        const double hval = in_map ? hmap[nidx] : 0.0;
         int sl;
         const int v = table_find(table, nodes, pc.table_mask, cxs, cys, chs, sl);
         if (v >= 0 && (v & 1)) valid = 0;  // in the closed set
         else {
-          const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
-          const long nidx = (long)ccy * W + ccx;
-          if (nidx < 0 || nidx >= map_size) valid = 0;  // :674-677
+          if (!in_map) valid = 0;  // :674-677
           else {
-            fkey = ccost + 30.0 * hmap[nidx];
+            fkey = ccost + 30.0 * hval;
             if (v >= 0) {
               if (ccost < nodes[v >> 1].cost) replace = 1;  // strictly cheaper than the open node
               else valid = 0;
@@ -952,13 +1093,7 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       const long long tq_ = clock64();
       pf[10] += (unsigned long long)(tq_ - ti_);
 #endif
-      for (unsigned mset = vm; mset;) {  // heap pushes in command order
-        const int b = __ffs(mset) - 1;
-        mset &= mset - 1;
-        const double k = __shfl_sync(FULLM, fkey, b);
-        const int my = n_nodes + __popc(vm & ((1u << b) - 1u));
-        gheap_push_warp(hkey, hidx, hn, k, my);
-      }
+      gheap_push_batch(hkey, hidx, hn, sm.hcache, fkey, vm, n_nodes);  // heap pushes in command order
       n_nodes += n_new;
 #ifdef HPP_PLAN_PROF
       pf[11] += (unsigned long long)(clock64() - tq_);
@@ -984,10 +1119,15 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       atomicAdd(prof + 5, pf[5]);
       atomicAdd(prof + 6, pf[6]);
       atomicAdd(prof + 7, (unsigned long long)iterations);
+      for (int i = 8; i < 12; i++) atomicAdd(prof + i, pf[i]);
     }
-    for (int i = 0; i < 8; i++) pf[i] = 0;
+    for (int i = 0; i < 12; i++) pf[i] = 0;
 #endif
     if (lane == 0) sm.quit = 1;
+    if (set_aside && win < 0) {  // nothing is written for this query now: the second pass runs it from its start
+      if (lane == 0) deferred[atomicAdd(n_deferred, 1)] = qi;
+      continue;
+    }
     pipe_res wr;
     wr.n_samples = 0; wr.nseg = 0; wr.cost = 0.0;
     if (win >= 0) {
@@ -1073,16 +1213,29 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
 __global__ void heap_ops_kernel(const double *__restrict__ keys, const int *__restrict__ ops, int n_ops,
                                 double *ka, int *ia, double *kb, int *ib, int *pops, long long *first_mismatch) {
   const int lane = threadIdx.x & 31;
+  __shared__ heap_cache hc;
   int na = 0, nb = 0;
   long long bad = -1;
   for (int i = 0; i < n_ops; i++) {
     const int op = ops[i];
     int pa = -1, pb = -1;
     if (op >= 0) {
-      if (lane == 0) gheap_push(ka, ia, na, keys[op], i);
+      // a run of pushes (up to 26, an expansion's worth): one by one on heap A, as one gheap_push_batch on heap B
+      int run = 1;
+      while (run < 26 && i + run < n_ops && ops[i + run] >= 0) run++;
+      if (lane == 0)
+        for (int r = 0; r < run; r++) gheap_push(ka, ia, na, keys[ops[i + r]], i + r);
       na = __shfl_sync(0xffffffffu, na, 0);
       __syncwarp();
-      gheap_push_warp(kb, ib, nb, keys[op], i);
+      if (run == 1) {
+        gheap_push_warp(kb, ib, nb, keys[op], i);
+      } else {
+        const double fk = lane < run ? keys[ops[i + lane]] : 0.0;
+        gheap_push_batch(kb, ib, nb, hc, fk, run == 32 ? 0xffffffffu : ((1u << run) - 1u), i);
+      }
+      if (pops && lane == 0)
+        for (int r = 0; r < run; r++) pops[i + r] = -1;
+      i += run - 1;
     } else if (na > 0) {
       if (lane == 0) pa = gheap_pop(ka, ia, na);
       na = __shfl_sync(0xffffffffu, na, 0);
@@ -1191,7 +1344,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   }
   const auto t1 = t_now();
   char *d_io = nullptr;
-  const size_t io_bytes = n * 48 + n * 12 + n * sizeof(hpp_plan) + n_maps * sizeof(plan_map_desc) + traj_cap * 40 + 64;
+  const size_t io_bytes = n * 48 + n * 16 + n * sizeof(hpp_plan) + n_maps * sizeof(plan_map_desc) + traj_cap * 40 + 96;
   hpp_status st = hpp_scratch(c, 0, io_bytes, (void **)&d_io);
   if (st != HPP_OK) {
     c->plan_free_bytes = 0;  // the cached figure was stale: ask again next time
@@ -1202,7 +1355,8 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   hpp_plan *d_plans = (hpp_plan *)(d_mq + n + (n & 1));
   unsigned long long *d_cursor = (unsigned long long *)(d_plans + n);
   plan_map_desc *d_descs = (plan_map_desc *)(d_cursor + 2);
-  double *d_traj = (double *)(d_descs + n_maps);
+  int *d_defer = (int *)(d_descs + n_maps), *d_ndefer = d_defer + n;  // queries set aside for the second pass
+  double *d_traj = (double *)(d_ndefer + 2 + (n & 1));
   std::vector<plan_map_desc> descs(n_maps);
   for (size_t k = 0; k < n_maps; k++) {
     descs[k].dist = maps[k]->d_distance;
@@ -1260,6 +1414,14 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
     // Reeds-Shepp: the pipelined kernel (search on warp 0, one whole shot per worker warp).  HPP_PLAN_PIPE=2 forces two
     // CTAs per SM, =3 one
     size_t plan_smem_bytes = 0;
+    // Two passes for big Reeds-Shepp batches (HPP_PLAN_BUDGET iterations in the first, default 64; 0 = one pass): 95 % of
+    // the cfg5 queries end within 56 iterations and 2 % run into the 3 500-iteration cap, which makes the batch time the
+    // time of the SM that drew the most cap hitters from the queue.  The first pass (two CTAs per SM) sets a query aside
+    // when it passes the budget; the second pass runs exactly those, from their start, one per SM -- every long query
+    // starts at once on an SM of its own instead of behind whatever its CTA drew before.  Same results: a query's
+    // outcome does not depend on what ran beside it.
+    static const int pass_budget = getenv("HPP_PLAN_BUDGET") ? atoi(getenv("HPP_PLAN_BUDGET")) : 64;
+    bool two_pass = false;
     static const int pipe_env = getenv("HPP_PLAN_PIPE") ? atoi(getenv("HPP_PLAN_PIPE")) : 1;
     const bool pipe = variant == HPP_VARIANT_RS;
     if (pipe) {
@@ -1271,6 +1433,10 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
       const bool two = pipe_env == 2 || (pipe_env == 1 && ng > (size_t)32 * c->sm_count);
       kern = two ? (const void *)plan_pipe_kernel<8, 2> : (const void *)plan_pipe_kernel<8, 1>;
       plan_smem_bytes = sizeof(pipe_smem<8>);
+      two_pass = two && pass_budget > 0;
+      if (two_pass && plan_smem_bytes > 48 * 1024)
+        HPP_CUDA(c, cudaFuncSetAttribute((const void *)plan_pipe_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)plan_smem_bytes));
 
       if (plan_smem_bytes > 48 * 1024)
         HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem_bytes));
@@ -1359,10 +1525,30 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
         const int *a_qids = d_qids + q0, *a_fq = d_fq + q0;
         int a_nq = (int)(q1 - q0);
         unsigned long long a_cap = traj_cap;
-        void *params[] = {&pc,       &a_descs, &a_mq,   &a_starts, &a_goals, &a_qids,  &a_nq,   &a_fq,
-                          &a_fields, &d_nodes, &d_keys, &d_idx,    &d_table, &d_plans, &d_traj, &a_cap,
-                          &d_cursor, &d_prof};  // (the pipelined kernel takes all but the last)
-        cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, plan_smem_bytes, c->stream);
+        if (!pipe) {
+          void *params[] = {&pc,       &a_descs, &a_mq,   &a_starts, &a_goals, &a_qids,  &a_nq,   &a_fq,
+                            &a_fields, &d_nodes, &d_keys, &d_idx,    &d_table, &d_plans, &d_traj, &a_cap,
+                            &d_cursor, &d_prof};
+          cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, plan_smem_bytes, c->stream);
+        } else {
+          int a_budget = two_pass ? pass_budget : PLAN_ITER_CAP + 1;
+          const int *a_list = nullptr, *a_nlist = nullptr;
+          if (two_pass) cudaMemsetAsync(d_ndefer, 0, 4, c->stream);
+          void *params[] = {&pc,       &a_descs, &a_mq,   &a_starts, &a_goals, &a_qids,  &a_nq,     &a_fq,    &a_fields,
+                            &d_nodes,  &d_keys,  &d_idx,  &d_table,  &d_plans, &d_traj,  &a_cap,    &d_cursor, &a_budget,
+                            &a_list,   &a_nlist, &d_defer, &d_ndefer, &d_prof};
+          cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, plan_smem_bytes, c->stream);
+          if (two_pass) {  // the queries set aside, one CTA per SM (the count stays on the device)
+            c->launches++;
+            cudaMemsetAsync(d_cursor + 1, 0, 8, c->stream);
+            a_budget = PLAN_ITER_CAP + 1;
+            a_list = d_defer;
+            a_nlist = d_ndefer;
+            const int grid2 = grid < c->sm_count ? grid : c->sm_count;
+            cudaLaunchKernel((const void *)plan_pipe_kernel<8, 1>, dim3(grid2), dim3(plan_warps * 32), params,
+                             plan_smem_bytes, c->stream);
+          }
+        }
       }
       c->launches++;
       e = cudaGetLastError();

@@ -101,7 +101,8 @@ def test_plan_batch_shared_goal_and_failure_convention(ctx):
 
 def test_open_list_warp_heap_matches_libstdcxx_replay(ctx):
     """the planner's warp-collective pop_heap / push_heap (four levels per memory round trip, whole ancestor chain at
-    once) leave exactly the arrays of the one-thread libstdc++ replay after every operation -- on A*-like traffic
+    once) and its batched push (a burst of pushes through a shared-memory copy of their ancestors: gheap_push_batch,
+    taken by the hook for every run of two or more pushes) leave exactly the arrays of the one-thread libstdc++ replay after every operation -- on A*-like traffic
     (bursts of pushes with many equal keys, then a pop), on heaps that cross level boundaries, and on drains to empty --
     and the popped payloads follow the comparator's order with ties resolved identically"""
     rng = np.random.default_rng(5)
