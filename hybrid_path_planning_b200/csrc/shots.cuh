@@ -316,8 +316,24 @@ __device__ __forceinline__ void rs_generate(rs_warp_smem &S, double sx, double s
                                             double gyaw, double maxc) {
   const int lane = threadIdx.x & 31;
   const rs_frame f = rs_make_frame(sx, sy, syaw, gx, gy, gyaw, maxc);
-  rs_eval_formula(lane, f.x, f.y, f.dth, f.xb, f.yb, S);
-  if (lane + 32 < RS_NCAND) rs_eval_formula(lane + 32, f.x, f.y, f.dth, f.xb, f.yb, S);
+  // Lanes of different families run one after the other (different code), so every family is kept inside ONE of the two
+  // rounds: LSL, LSR, LRL (8), LRSL (8), LRSR (8) = 32 formulas in the first, SLS, LRLRN, LRLRP, LRSLR = 14 in the second --
+  // nine family passes instead of the twelve of "lane = formula index".  Results are filed under the formula index, so
+  // the de-duplication sees them in the reference's order whatever lane worked them out.
+  {
+    int idx;  // first round: formulas 2..17 (LSL, LSR, LRL fwd + back), 26..29 / 34..37 (LRSL), 30..33 / 38..41 (LRSR)
+    if (lane < 16) idx = 2 + lane;
+    else if (lane < 20) idx = 26 + (lane - 16);
+    else if (lane < 24) idx = 34 + (lane - 20);
+    else if (lane < 28) idx = 30 + (lane - 24);
+    else idx = 38 + (lane - 28);
+    rs_eval_formula(idx, f.x, f.y, f.dth, f.xb, f.yb, S);
+    int idx2 = -1;  // second round: 0..1 (SLS), 18..25 (LRLRN, LRLRP), 42..45 (LRSLR)
+    if (lane < 2) idx2 = lane;
+    else if (lane < 10) idx2 = 18 + (lane - 2);
+    else if (lane < 14) idx2 = 42 + (lane - 10);
+    if (idx2 >= 0) rs_eval_formula(idx2, f.x, f.y, f.dth, f.xb, f.yb, S);
+  }
   __syncwarp();
   rs_dedup(S);
 }
