@@ -738,12 +738,30 @@ struct pipe_smem {
   double exp_sc[HPP_MAX_COMMANDS][HPP_MAX_SIM][2];  // expansion: (m dt cos h_i, m dt sin h_i) of every command's step i
   pipe_job job[PIPE_RING];
   pipe_res res[PIPE_RING];
-  pipe_worker w[NW - 1 - PIPE_EXP_WARPS];
-  heap_cache hcache;                   // controller: the ancestors of an expansion's pushes (gheap_push_batch)
+  pipe_worker w[NW - 2 - PIPE_EXP_WARPS];
+  heap_cache hcache;                   // heap warp: the ancestors of an expansion's pushes (gheap_push_batch)
+  // controller -> heap warp: command c (parity c & 1) = "push these keys, then pop"; heap warp -> controller: the root
+  // the pop left behind
+  int hm_m[2], hm_first[2];
+  double hm_keys[2][HPP_MAX_COMMANDS];
+  double hm_root_key;
+  int hm_root_idx;                     // -1: the heap is empty
+  volatile int hm_quit;
 };
 // named barrier of the controller and its expansion helpers (barrier 0 is __syncthreads)
 __device__ __forceinline__ void pipe_exp_barrier() {
   asm volatile("bar.sync 1, %0;" ::"n"((1 + PIPE_EXP_WARPS) * 32) : "memory");
+}
+// producer / consumer barriers of the controller and the heap warp (64 threads): 2 = "a command is posted" (the
+// controller arrives, the heap warp waits), 3 = "its root is posted" (the heap warp arrives, the controller waits)
+__device__ __forceinline__ void pipe_heap_post(int id) {
+  __threadfence_block();
+  if (id == 2) asm volatile("bar.arrive 2, 64;" ::: "memory");
+  else asm volatile("bar.arrive 3, 64;" ::: "memory");
+}
+__device__ __forceinline__ void pipe_heap_wait(int id) {
+  if (id == 2) asm volatile("bar.sync 2, 64;" ::: "memory");
+  else asm volatile("bar.sync 3, 64;" ::: "memory");
 }
 
 template <int NW, int MIN_CTAS>
@@ -792,6 +810,7 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       sm.claim = 0;
       sm.quit = 0;
       sm.exp_quit = 0;
+      sm.hm_quit = 0;
     }
     __syncthreads();
     // second pass of a two-pass batch: the queries the first pass set aside (qi_list, *n_list of them)
@@ -846,6 +865,31 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         if (sm.exp_quit) break;
         rollouts();
         pipe_exp_barrier();  // hit bits and child states are complete
+      }
+      continue;
+    }
+    if (wid == NW - 1) {
+      // ================================================================ heap warp: the open list's priority queue
+      // std::priority_queue's arrays are touched by this warp alone once the search runs.  A command is the pushes of
+      // the previous expansion (in command order) followed by the pop of the node the controller is already working
+      // on; the answer is the root that pop leaves behind, which is all the controller needs to know its next node
+      // (see the controller's loop).  The sift-down and the sift-ups overlap the controller's expansion and insertion.
+      int n = 1;  // the start node, pushed by the controller before its first command
+      for (int seq = 0;; seq++) {
+        pipe_heap_wait(2);
+        if (sm.hm_quit) break;
+        const int par = seq & 1;
+        const int m = sm.hm_m[par];
+        if (m > 0) {
+          const double fk = lane < m ? sm.hm_keys[par][lane] : 0.0;
+          gheap_push_batch(hkey, hidx, n, sm.hcache, fk, m >= 32 ? 0xffffffffu : ((1u << m) - 1u), sm.hm_first[par]);
+        }
+        gheap_pop_warp(hkey, hidx, n);
+        if (lane == 0) {
+          sm.hm_root_idx = n > 0 ? hidx[0] : -1;
+          sm.hm_root_key = n > 0 ? hkey[0] : 0.0;
+        }
+        pipe_heap_post(3);
       }
       continue;
     }
@@ -969,7 +1013,15 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
 #ifdef HPP_PLAN_PROF
     const long long tloop_ = clock64();
 #endif
-    while (status == 0 && hn > 0) {
+    // The open list lives with the heap warp; the controller keeps what it needs to go on without waiting for it:
+    // `count` entries, and the payload of the top.  After "push k_1 .. k_m, pop" the next top follows from the root R the
+    // pop left behind and the keys of THIS expansion's pushes alone: std::push_heap moves a new key up past every
+    // ancestor that is strictly greater, and every ancestor is >= the root, so a key below the root's becomes the root
+    // and any other key leaves it alone -- the top after the pushes is R, unless some key is strictly smaller, then the
+    // first of the smallest keys (an equal later one does not displace it).  The heap warp replays the pushes and the
+    // pop in the reference's order meanwhile, so the arrays -- and every tie among equal keys -- are std::priority_queue's.
+    int count = hn, top_idx = 0, pend_m = 0, pend_first = 0, par = 0;
+    while (status == 0 && count > 0) {
       if (retire()) break;
       iterations++;
       if (iterations > PLAN_ITER_CAP) break;
@@ -977,11 +1029,19 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
         set_aside = true;
         break;
       }
-      // ---- pop
+      // ---- pop: the heap warp gets the previous expansion's pushes and this pop; the node is known already
 #ifdef HPP_PLAN_PROF
       const long long tp_ = clock64();
 #endif
-      const int top = gheap_pop_warp(hkey, hidx, hn);
+      if (lane == 0) {
+        sm.hm_m[par] = pend_m;
+        sm.hm_first[par] = pend_first;
+      }
+      pipe_heap_post(2);
+      par ^= 1;
+      pend_m = 0;
+      count--;
+      const int top = top_idx;
       int tv = 0;
       if (lane == 0) {
         int slot = 0;
@@ -993,117 +1053,155 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
 #ifdef HPP_PLAN_PROF
       pf[8] += (unsigned long long)(clock64() - tp_);
 #endif
-      if (tv < 0 || (tv & 1)) continue;  // already in the closed set
-      const int cur = tv >> 1;
-      const pnode cn = nodes[cur];
-      // ---- the analytic shot of this node goes to the workers
-      {
-        PIPE_T0
-        while (head - retired >= PIPE_RING) {
-          if (retire()) break;
-          __nanosleep(100);
+      bool leave = false;
+      unsigned vm = 0u;
+      double fkey = 0.0;
+      int n_new = 0;
+      do {
+        if (tv < 0 || (tv & 1)) break;  // already in the closed set
+        const int cur = tv >> 1;
+        const pnode cn = nodes[cur];
+        // ---- the analytic shot of this node goes to the workers
+        {
+          PIPE_T0
+          while (head - retired >= PIPE_RING) {
+            if (retire()) break;
+            __nanosleep(100);
+          }
+          PIPE_ADD(5)
         }
-        PIPE_ADD(5)
-      }
-      if (win >= 0) break;
-      if (lane == 0) {
-        pipe_job &jb = sm.job[head % PIPE_RING];
-        jb.x = cn.x; jb.y = cn.y; jb.h = cn.h; jb.cost = cn.cost; jb.cur = cur; jb.iter = iterations;
-        *(volatile int *)&sm.res[head % PIPE_RING].state = 0;
-        __threadfence_block();
-        sm.head = head + 1;
-      }
-      head++;
-      __syncwarp();
-      // ---- goal test (RS/src/HybridAstar.cpp:641-655)
-      {
-        double hd = fabs(cn.h - gh);
-        if (hd > PI_ASTAR) hd = fabs(hd - 2 * PI_ASTAR);
-        const int c_cx = (int)(hpp_div_res(g, cn.x - g.ox)), c_cy = (int)(hpp_div_res(g, cn.y - g.oy));
-        if (c_cx == g_cx && c_cy == g_cy && hd <= 0.05) {
-          end_node = cur;
+        if (win >= 0) {
+          leave = true;
           break;
         }
-      }
-      // ---- expansion: the controller and its helpers, one thread per (command, state)
-      if (lane == 0) {
-        sm.exp_from[0] = cn.x; sm.exp_from[1] = cn.y; sm.exp_from[2] = cn.h;
-        sm.exp_hit = 0u;
-      }
-#ifdef HPP_PLAN_PROF
-      const long long te_ = clock64();
-#endif
-      pipe_exp_barrier();
-      rollouts();
-      pipe_exp_barrier();
-#ifdef HPP_PLAN_PROF
-      const long long ti_ = clock64();
-      pf[9] += (unsigned long long)(ti_ - te_);
-#endif
-      double cxs = 0, cys = 0, chs = 0, ccost = 0, fkey = 0.0;
-      int valid = 0, ins_slot = -1, replace = 0;
-      if (lane < ncmd) {
-        valid = !((sm.exp_hit >> lane) & 1u);
-        cxs = sm.exp_child[lane][0]; cys = sm.exp_child[lane][1]; chs = sm.exp_child[lane][2];
-      }
-      // ---- insert / replace in command order
-      if (valid) {
-        ccost = path_cost(pc.ec, lane, cn.cost, cn.steer, cn.dir);
-        // (the heuristic of the child's cell is fetched before the table is searched: one round trip less on the chain)
-        const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
-        const long nidx = (long)ccy * W + ccx;
-        const bool in_map = !(nidx < 0 || nidx >= map_size);
-        const double hval = in_map ? hmap[nidx] : 0.0;
-        int sl;
-        const int v = table_find(table, nodes, pc.table_mask, cxs, cys, chs, sl);
-        if (v >= 0 && (v & 1)) valid = 0;  // in the closed set
-        else {
-          if (!in_map) valid = 0;  // :674-677
-          else {
-            fkey = ccost + 30.0 * hval;
-            if (v >= 0) {
-              if (ccost < nodes[v >> 1].cost) replace = 1;  // strictly cheaper than the open node
-              else valid = 0;
-            }
-            ins_slot = sl;
+        if (lane == 0) {
+          pipe_job &jb = sm.job[head % PIPE_RING];
+          jb.x = cn.x; jb.y = cn.y; jb.h = cn.h; jb.cost = cn.cost; jb.cur = cur; jb.iter = iterations;
+          *(volatile int *)&sm.res[head % PIPE_RING].state = 0;
+          __threadfence_block();
+          sm.head = head + 1;
+        }
+        head++;
+        __syncwarp();
+        // ---- goal test (RS/src/HybridAstar.cpp:641-655)
+        {
+          double hd = fabs(cn.h - gh);
+          if (hd > PI_ASTAR) hd = fabs(hd - 2 * PI_ASTAR);
+          const int c_cx = (int)(hpp_div_res(g, cn.x - g.ox)), c_cy = (int)(hpp_div_res(g, cn.y - g.oy));
+          if (c_cx == g_cx && c_cy == g_cy && hd <= 0.05) {
+            end_node = cur;
+            leave = true;
+            break;
           }
         }
-      }
-      const unsigned vm = __ballot_sync(FULLM, valid);
-      const int n_new = __popc(vm);
-      if (n_nodes + n_new > pc.max_nodes) {
-        status = 1;
-        break;
-      }
-      if (valid) {
-        const int my = n_nodes + __popc(vm & ((1u << lane) - 1u));
-        pnode nd;
-        nd.x = cxs; nd.y = cys; nd.h = chs; nd.cost = ccost; nd.steer = pc.ec.steer[lane]; nd.parent = cur;
-        nd.dir = (signed char)(int)pc.ec.dir[lane]; nd.cmd = (signed char)lane; nd.pad = 0;
-        nodes[my] = nd;
-        __threadfence_block();
-        if (replace) table[ins_slot] = my << 1;
-        else {
-          int sl = ins_slot;
-          while (atomicCAS(&table[sl], -1, my << 1) != -1) sl = (sl + 1) & pc.table_mask;
+        // ---- expansion: the controller and its helpers, one thread per (command, state)
+        if (lane == 0) {
+          sm.exp_from[0] = cn.x; sm.exp_from[1] = cn.y; sm.exp_from[2] = cn.h;
+          sm.exp_hit = 0u;
         }
-      }
-      __syncwarp();
+#ifdef HPP_PLAN_PROF
+        const long long te_ = clock64();
+#endif
+        pipe_exp_barrier();
+        rollouts();
+        pipe_exp_barrier();
+#ifdef HPP_PLAN_PROF
+        const long long ti_ = clock64();
+        pf[9] += (unsigned long long)(ti_ - te_);
+#endif
+        double cxs = 0, cys = 0, chs = 0, ccost = 0;
+        int valid = 0, ins_slot = -1, replace = 0;
+        if (lane < ncmd) {
+          valid = !((sm.exp_hit >> lane) & 1u);
+          cxs = sm.exp_child[lane][0]; cys = sm.exp_child[lane][1]; chs = sm.exp_child[lane][2];
+        }
+        // ---- insert / replace in command order
+        if (valid) {
+          ccost = path_cost(pc.ec, lane, cn.cost, cn.steer, cn.dir);
+          // (the heuristic of the child's cell is fetched before the table is searched: one round trip less on the chain)
+          const int ccx = (int)(hpp_div_res(g, cxs - g.ox)), ccy = (int)(hpp_div_res(g, cys - g.oy));
+          const long nidx = (long)ccy * W + ccx;
+          const bool in_map = !(nidx < 0 || nidx >= map_size);
+          const double hval = in_map ? hmap[nidx] : 0.0;
+          int sl;
+          const int v = table_find(table, nodes, pc.table_mask, cxs, cys, chs, sl);
+          if (v >= 0 && (v & 1)) valid = 0;  // in the closed set
+          else {
+            if (!in_map) valid = 0;  // :674-677
+            else {
+              fkey = ccost + 30.0 * hval;
+              if (v >= 0) {
+                if (ccost < nodes[v >> 1].cost) replace = 1;  // strictly cheaper than the open node
+                else valid = 0;
+              }
+              ins_slot = sl;
+            }
+          }
+        }
+        vm = __ballot_sync(FULLM, valid);
+        n_new = __popc(vm);
+        if (n_nodes + n_new > pc.max_nodes) {
+          status = 1;
+          vm = 0u;
+          n_new = 0;
+          leave = true;
+          break;
+        }
+        if (valid) {
+          const int rank = __popc(vm & ((1u << lane) - 1u));
+          const int my = n_nodes + rank;
+          pnode nd;
+          nd.x = cxs; nd.y = cys; nd.h = chs; nd.cost = ccost; nd.steer = pc.ec.steer[lane]; nd.parent = cur;
+          nd.dir = (signed char)(int)pc.ec.dir[lane]; nd.cmd = (signed char)lane; nd.pad = 0;
+          nodes[my] = nd;
+          sm.hm_keys[par][rank] = fkey;  // the pushes of the next command, in command order
+          __threadfence_block();
+          if (replace) table[ins_slot] = my << 1;
+          else {
+            int sl = ins_slot;
+            while (atomicCAS(&table[sl], -1, my << 1) != -1) sl = (sl + 1) & pc.table_mask;
+          }
+        }
+        __syncwarp();
+#ifdef HPP_PLAN_PROF
+        pf[10] += (unsigned long long)(clock64() - ti_);
+#endif
+      } while (false);
+      // ---- the root this pop left behind, and with it the next top
 #ifdef HPP_PLAN_PROF
       const long long tq_ = clock64();
-      pf[10] += (unsigned long long)(tq_ - ti_);
 #endif
-      gheap_push_batch(hkey, hidx, hn, sm.hcache, fkey, vm, n_nodes);  // heap pushes in command order
-      n_nodes += n_new;
+      pipe_heap_wait(3);
 #ifdef HPP_PLAN_PROF
       pf[11] += (unsigned long long)(clock64() - tq_);
 #endif
+      if (leave) break;
+      const int r_idx = sm.hm_root_idx;
+      const double r_key = sm.hm_root_key;
+      top_idx = r_idx;
+      if (n_new > 0) {
+        double kmin = (vm >> lane) & 1u ? fkey : INFINITY;
+        for (int o = 16; o > 0; o >>= 1) kmin = fmin(kmin, __shfl_xor_sync(FULLM, kmin, o));
+        if (r_idx < 0 || kmin < r_key) {
+          const unsigned eq = __ballot_sync(FULLM, ((vm >> lane) & 1u) && fkey == kmin);
+          const int b = __ffs(eq) - 1;
+          top_idx = n_nodes + __popc(vm & ((1u << b) - 1u));
+        }
+      }
+      pend_m = n_new;
+      pend_first = n_nodes;
+      n_nodes += n_new;
+      count += n_new;
     }
 #ifdef HPP_PLAN_PROF
     pf[4] += (unsigned long long)(clock64() - tloop_);
 #endif
-    if (lane == 0) sm.exp_quit = 1;
+    if (lane == 0) {
+      sm.exp_quit = 1;
+      sm.hm_quit = 1;
+    }
     pipe_exp_barrier();  // releases the expansion helpers
+    pipe_heap_post(2);   // and the heap warp
     // ---- the loop is over: shots of earlier pops come first
     {
       PIPE_T0
@@ -1411,38 +1509,38 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
     }
     const void *kern = plan_warps == PLAN_WARPS_LONE ? (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_LONE>
                                                      : (const void *)plan_kernel<HPP_VARIANT_DUBINS, PLAN_WARPS_BATCH>;
-    // Reeds-Shepp: the pipelined kernel (search on warp 0, one whole shot per worker warp).  HPP_PLAN_PIPE=2 forces two
-    // CTAs per SM, =3 one
+    // Reeds-Shepp: the pipelined kernel (search on warp 0, the open list on the last warp, one whole shot per worker warp)
     size_t plan_smem_bytes = 0;
     // Two passes for big Reeds-Shepp batches (HPP_PLAN_BUDGET iterations in the first, default 64; 0 = one pass): 95 % of
     // the cfg5 queries end within 56 iterations and 2 % run into the 3 500-iteration cap, which makes the batch time the
-    // time of the SM that drew the most cap hitters from the queue.  The first pass (two CTAs per SM) sets a query aside
-    // when it passes the budget; the second pass runs exactly those, from their start, one per SM -- every long query
-    // starts at once on an SM of its own instead of behind whatever its CTA drew before.  Same results: a query's
+    // time of the SM that drew the most cap hitters from the queue.  The first pass sets a query aside when it passes the
+    // budget; the second pass runs exactly those, from their start -- every long query starts at once on an SM of its
+    // own instead of behind whatever its CTA drew before.  Same results: a query's
     // outcome does not depend on what ran beside it.
     static const int pass_budget = getenv("HPP_PLAN_BUDGET") ? atoi(getenv("HPP_PLAN_BUDGET")) : 64;
     bool two_pass = false;
-    static const int pipe_env = getenv("HPP_PLAN_PIPE") ? atoi(getenv("HPP_PLAN_PIPE")) : 1;
     const bool pipe = variant == HPP_VARIANT_RS;
     if (pipe) {
-      // One 8-warp CTA per SM (no spills): a pipelined query keeps an SM's instruction fetch busy on its own -- its
-      // eight warps are at eight different places of the shot code -- and two of them on one SM run at half speed each.
-      // Only batches large enough to hold more long queries than there are SMs (cfg5: 2.2 % of 8 192 = 184 queries at
-      // the iteration cap on 148 SMs) take the two-per-SM build (128 registers), which avoids a second wave of them.
-      plan_warps = 8;
-      const bool two = pipe_env == 2 || (pipe_env == 1 && ng > (size_t)32 * c->sm_count);
-      kern = two ? (const void *)plan_pipe_kernel<8, 2> : (const void *)plan_pipe_kernel<8, 1>;
-      plan_smem_bytes = sizeof(pipe_smem<8>);
-      two_pass = two && pass_budget > 0;
-      if (two_pass && plan_smem_bytes > 48 * 1024)
-        HPP_CUDA(c, cudaFuncSetAttribute((const void *)plan_pipe_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)plan_smem_bytes));
-
+      // One CTA per SM: controller, three expansion helpers, the shot workers, the heap warp.  A pipelined query keeps
+      // an SM's instruction fetch busy on its own -- its warps are at different places of 140 KB of code -- and two of
+      // them on one SM ran at half speed each, so there is no two-per-SM build any more.  Ten warps (five workers): a
+      // shot costs a worker ~47 k cycles and the search now asks for one every ~10 k (HPP_PLAN_PIPE_NW=9: four workers).
+      static const int nw_env = getenv("HPP_PLAN_PIPE_NW") ? atoi(getenv("HPP_PLAN_PIPE_NW")) : 10;
+      if (nw_env == 9) {
+        plan_warps = 9;
+        kern = (const void *)plan_pipe_kernel<9, 1>;
+        plan_smem_bytes = sizeof(pipe_smem<9>);
+      } else {
+        plan_warps = 10;
+        kern = (const void *)plan_pipe_kernel<10, 1>;
+        plan_smem_bytes = sizeof(pipe_smem<10>);
+      }
+      two_pass = ng > (size_t)32 * c->sm_count && pass_budget > 0;
       if (plan_smem_bytes > 48 * 1024)
         HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem_bytes));
     }
     // cached per kernel shape (the RS slots hold the pipelined kernel's two builds; HPP_PLAN_PIPE is read once)
-    const int occ_slot = pipe ? (kern == (const void *)plan_pipe_kernel<8, 2> ? 0 : 1)
+    const int occ_slot = pipe ? (plan_warps == 9 ? 0 : 1)
                               : variant * 2 + (plan_warps == PLAN_WARPS_LONE ? 1 : 0);
     int occ_blocks = c->plan_occ_blocks[occ_slot];
     if (occ_blocks == 0) {
@@ -1545,8 +1643,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
             a_list = d_defer;
             a_nlist = d_ndefer;
             const int grid2 = grid < c->sm_count ? grid : c->sm_count;
-            cudaLaunchKernel((const void *)plan_pipe_kernel<8, 1>, dim3(grid2), dim3(plan_warps * 32), params,
-                             plan_smem_bytes, c->stream);
+            cudaLaunchKernel(kern, dim3(grid2), dim3(plan_warps * 32), params, plan_smem_bytes, c->stream);
           }
         }
       }

@@ -56,7 +56,9 @@ __device__ __forceinline__ double pi_2_pi(double theta) {  // :821-834 (and DB/s
 
 enum { F_SLS, F_LSL, F_LSR, F_LRL, F_LRLRN, F_LRLRP, F_LRSL, F_LRSR, F_LRSLR };
 
-static __device__ __noinline__ bool rs_family(int fam, double x, double y, double phi, double &t, double &u, double &v) {
+// sp, cp: sin(phi), cos(phi), taken once per lane by the caller (every family but SLS starts from them)
+static __device__ __noinline__ bool rs_family(int fam, double x, double y, double phi, double sp, double cp, double &t,
+                                              double &u, double &v) {
   switch (fam) {
     case F_SLS: {  // :217-239
       phi = rs_M(phi);
@@ -77,7 +79,7 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
     }
     case F_LSL: {  // :143-157
       double uu, tt;
-      rs_R(x - hpp_sin(phi), y - 1.0 + hpp_cos(phi), uu, tt);
+      rs_R(x - sp, y - 1.0 + cp, uu, tt);
       if (tt >= 0.0) {
         double vv = rs_M(phi - tt);
         if (vv >= 0.0) {
@@ -89,7 +91,7 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
     }
     case F_LSR: {  // :159-179
       double u1, t1;
-      rs_R(x + hpp_sin(phi), y - 1.0 - hpp_cos(phi), u1, t1);
+      rs_R(x + sp, y - 1.0 - cp, u1, t1);
       u1 = u1 * u1;
       if (u1 >= 4.0) {
         double uu = sqrt(u1 - 4.0);
@@ -105,7 +107,7 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
     }
     case F_LRL: {  // :181-199
       double u1, t1;
-      rs_R(x - hpp_sin(phi), y - 1.0 + hpp_cos(phi), u1, t1);
+      rs_R(x - sp, y - 1.0 + cp, u1, t1);
       if (u1 <= 4.0) {
         double uu = -2.0 * hpp_asin(0.25 * u1);
         double tt = rs_M(t1 + 0.5 * uu + RS_PI);
@@ -119,8 +121,8 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
     }
     case F_LRLRN:
     case F_LRLRP: {  // :374-417 with calc_tauOmega :359-372
-      double xi = x + hpp_sin(phi);
-      double eta = y - 1.0 - hpp_cos(phi);
+      double xi = x + sp;
+      double eta = y - 1.0 - cp;
       double uu, vq;
       if (fam == F_LRLRN) {
         double rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
@@ -135,10 +137,14 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
         vq = uu;
       }
       double delta = rs_M(uu - vq);
-      double A = hpp_sin(uu) - hpp_sin(delta);
-      double B = hpp_cos(uu) - hpp_cos(delta) - 1.0;
+      double su, cu, sd, cd;  // each angle's sine and cosine once (the reference calls sin / cos term by term)
+      hpp_sincos(uu, &su, &cu);
+      hpp_sincos(delta, &sd, &cd);
+      const double cvq = (fam == F_LRLRN) ? hpp_cos(vq) : cu;  // LRLRP: vq is uu itself
+      double A = su - sd;
+      double B = cu - cd - 1.0;
       double t1 = hpp_atan2(eta * A - xi * B, xi * A + eta * B);
-      double t2 = 2.0 * (hpp_cos(delta) - hpp_cos(vq) - hpp_cos(uu)) + 3.0;
+      double t2 = 2.0 * (cd - cvq - cu) + 3.0;
       double tau = t2 < 0 ? rs_M(t1 + RS_PI) : rs_M(t1);
       double omega = rs_M(tau - uu + vq - phi);
       bool ok = (fam == F_LRLRN) ? (tau >= 0.0 && omega <= 0.0) : (tau >= 0.0 && omega >= 0.0);
@@ -148,8 +154,8 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
       return ok;
     }
     case F_LRSR: {  // :475-494
-      double xi = x + hpp_sin(phi);
-      double eta = y - 1.0 - hpp_cos(phi);
+      double xi = x + sp;
+      double eta = y - 1.0 - cp;
       double rho, theta;
       rs_R(-eta, xi, rho, theta);
       if (rho >= 2.0) {
@@ -164,8 +170,8 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
       return false;
     }
     case F_LRSL: {  // :496-516
-      double xi = x - hpp_sin(phi);
-      double eta = y - 1.0 + hpp_cos(phi);
+      double xi = x - sp;
+      double eta = y - 1.0 + cp;
       double rho, theta;
       rs_R(xi, eta, rho, theta);
       if (rho >= 2.0) {
@@ -181,8 +187,8 @@ static __device__ __noinline__ bool rs_family(int fam, double x, double y, doubl
       return false;
     }
     default: {  // F_LRSLR :626-650
-      double xi = x + hpp_sin(phi);
-      double eta = y - 1.0 - hpp_cos(phi);
+      double xi = x + sp;
+      double eta = y - 1.0 - cp;
       double rho, theta;
       rs_R(xi, eta, rho, theta);
       if (rho >= 2.0) {
@@ -224,7 +230,9 @@ __device__ __forceinline__ void rs_eval_formula(int idx, double x, double y, dou
   const double sg = (var & 1) ? -1.0 : 1.0;                // timeflip variants negate every length
   const bool swapLR = (var & 2) != 0;                      // reflect variants swap L and R
   double t = 0, u = 0, v = 0;
-  const bool ok = rs_family(fam, ax, ay, ap, t, u, v);
+  double sp = 0.0, cp = 1.0;
+  if (fam != F_SLS) hpp_sincos(ap, &sp, &cp);
+  const bool ok = rs_family(fam, ax, ay, ap, sp, cp, t, u, v);
   S.flag[idx] = ok;
   if (!ok) return;
   const double hp = -0.5 * RS_PI;
