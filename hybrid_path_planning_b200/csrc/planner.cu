@@ -742,7 +742,7 @@ struct pipe_smem {
   heap_cache hcache;                   // heap warp: the ancestors of an expansion's pushes (gheap_push_batch)
   // controller -> heap warp: command c (parity c & 1) = "push these keys, then pop"; heap warp -> controller: the root
   // the pop left behind
-  int hm_m[2], hm_first[2];
+  int hm_m[2], hm_first[2], hm_top[2];  // (hm_top: the node the controller took for this pop -- checked by the heap warp)
   double hm_keys[2][HPP_MAX_COMMANDS];
   double hm_root_key;
   int hm_root_idx;                     // -1: the heap is empty
@@ -779,6 +779,7 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
                                                             unsigned long long *__restrict__ cursor, int iter_budget,
                                                             const int *__restrict__ qi_list, const int *__restrict__ n_list,
                                                             int *__restrict__ deferred, int *__restrict__ n_deferred,
+                                                            int check_order,
                                                             unsigned long long *__restrict__ prof) {
   constexpr int THREADS = NW * 32;
 #ifdef HPP_PLAN_PROF
@@ -884,6 +885,9 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
           const double fk = lane < m ? sm.hm_keys[par][lane] : 0.0;
           gheap_push_batch(hkey, hidx, n, sm.hcache, fk, m >= 32 ? 0xffffffffu : ((1u << m) - 1u), sm.hm_first[par]);
         }
+        // The node the controller went on with must be the one std::pop_heap takes now; the host turns a mismatch into
+        // an error (HPP_PLAN_CHECK=0 skips the check; measured cost: none, the heap warp has slack).
+        if (check_order && lane == 0 && hidx[0] != sm.hm_top[par]) atomicAdd(cursor + 2, 1ull);
         gheap_pop_warp(hkey, hidx, n);
         if (lane == 0) {
           sm.hm_root_idx = n > 0 ? hidx[0] : -1;
@@ -1036,6 +1040,7 @@ __global__ void __launch_bounds__(NW * 32, MIN_CTAS) plan_pipe_kernel(plan_const
       if (lane == 0) {
         sm.hm_m[par] = pend_m;
         sm.hm_first[par] = pend_first;
+        sm.hm_top[par] = top_idx;
       }
       pipe_heap_post(2);
       par ^= 1;
@@ -1442,7 +1447,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   }
   const auto t1 = t_now();
   char *d_io = nullptr;
-  const size_t io_bytes = n * 48 + n * 16 + n * sizeof(hpp_plan) + n_maps * sizeof(plan_map_desc) + traj_cap * 40 + 96;
+  const size_t io_bytes = n * 48 + n * 16 + n * sizeof(hpp_plan) + n_maps * sizeof(plan_map_desc) + traj_cap * 40 + 128;
   hpp_status st = hpp_scratch(c, 0, io_bytes, (void **)&d_io);
   if (st != HPP_OK) {
     c->plan_free_bytes = 0;  // the cached figure was stale: ask again next time
@@ -1452,7 +1457,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   int *d_qids = (int *)(d_goals + 3 * n), *d_fq = d_qids + n, *d_mq = d_fq + n;
   hpp_plan *d_plans = (hpp_plan *)(d_mq + n + (n & 1));
   unsigned long long *d_cursor = (unsigned long long *)(d_plans + n);
-  plan_map_desc *d_descs = (plan_map_desc *)(d_cursor + 2);
+  plan_map_desc *d_descs = (plan_map_desc *)(d_cursor + 4);  // cursor: trajectory rows, query counter, open-list check
   int *d_defer = (int *)(d_descs + n_maps), *d_ndefer = d_defer + n;  // queries set aside for the second pass
   double *d_traj = (double *)(d_ndefer + 2 + (n & 1));
   std::vector<plan_map_desc> descs(n_maps);
@@ -1467,7 +1472,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   cudaMemcpyAsync(d_qids, order.data(), n * 4, cudaMemcpyHostToDevice, c->stream);
   cudaMemcpyAsync(d_mq, mq.data(), n * 4, cudaMemcpyHostToDevice, c->stream);
   cudaMemcpyAsync(d_descs, descs.data(), n_maps * sizeof(plan_map_desc), cudaMemcpyHostToDevice, c->stream);
-  cudaMemsetAsync(d_cursor, 0, 16, c->stream);
+  cudaMemsetAsync(d_cursor, 0, 32, c->stream);
   unsigned long long *d_prof = nullptr;
 #ifdef HPP_PLAN_PROF
   if (hpp_scratch(c, 5, 128, (void **)&d_prof) == HPP_OK) cudaMemsetAsync(d_prof, 0, 128, c->stream);
@@ -1629,12 +1634,14 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
                             &d_cursor, &d_prof};
           cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, plan_smem_bytes, c->stream);
         } else {
+          static const int check_env = getenv("HPP_PLAN_CHECK") ? atoi(getenv("HPP_PLAN_CHECK")) : 1;
+          int a_check = check_env;
           int a_budget = two_pass ? pass_budget : PLAN_ITER_CAP + 1;
           const int *a_list = nullptr, *a_nlist = nullptr;
           if (two_pass) cudaMemsetAsync(d_ndefer, 0, 4, c->stream);
           void *params[] = {&pc,       &a_descs, &a_mq,   &a_starts, &a_goals, &a_qids,  &a_nq,     &a_fq,    &a_fields,
                             &d_nodes,  &d_keys,  &d_idx,  &d_table,  &d_plans, &d_traj,  &a_cap,    &d_cursor, &a_budget,
-                            &a_list,   &a_nlist, &d_defer, &d_ndefer, &d_prof};
+                            &a_list,   &a_nlist, &d_defer, &d_ndefer, &a_check, &d_prof};
           cudaLaunchKernel(kern, dim3(grid), dim3(plan_warps * 32), params, plan_smem_bytes, c->stream);
           if (two_pass) {  // the queries set aside, one CTA per SM (the count stays on the device)
             c->launches++;
@@ -1680,9 +1687,14 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
   if (st == HPP_OK) {
     unsigned long long used = 0;
     cudaMemcpyAsync(plans, d_plans, n * sizeof(hpp_plan), cudaMemcpyDeviceToHost, c->stream);
-    cudaMemcpyAsync(c->h_flags + 48, d_cursor, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(c->h_flags + 48, d_cursor, 24, cudaMemcpyDeviceToHost, c->stream);
     e = cudaStreamSynchronize(c->stream);
     memcpy(&used, c->h_flags + 48, 8);
+    unsigned long long order_bad = 0;
+    memcpy(&order_bad, c->h_flags + 52, 8);
+    if (e == cudaSuccess && order_bad)  // never seen; a wrong answer must not pass silently
+      HPP_FAIL(c, HPP_ERR_CUDA, "plan_batch: internal check failed -- the open list's top differed from the node the "
+               "search went on with in %llu pops", order_bad);
     const size_t rows = used < traj_cap ? (size_t)used : traj_cap;
     if (e == cudaSuccess && rows) {
       cudaMemcpyAsync(traj, d_traj, rows * 40, cudaMemcpyDeviceToHost, c->stream);

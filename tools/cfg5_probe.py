@@ -9,6 +9,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hybrid_path_planning_b200 as hpp  # noqa: E402
 from bench import cfg5_jobs, RES  # noqa: E402
 
+if os.environ.get("PROBE_TORCH"):  # what bench.py has around the same call: torch's CUDA state and a large allocation
+    import torch
+    _big = torch.empty(int(os.environ["PROBE_TORCH"]) << 30, dtype=torch.uint8, device="cuda")
+    _big.fill_(1)
+    torch.cuda.synchronize()
 ctx = hpp.Context(0)
 maps = {}
 
