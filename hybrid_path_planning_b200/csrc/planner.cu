@@ -8,6 +8,9 @@
 //                     warps; each worker evaluates one node's whole shot (46 closed forms, ordered de-duplication,
 //                     footprint checks of every candidate path, cost order when one is free); results are retired in
 //                     pop order, so the first success ends the query exactly where the sequential loop would have.
+//                     The open list itself is kept by the last warp of the CTA: it replays "the pushes of the previous
+//                     expansion, then this pop" while the controller expands, and hands back the root the pop left
+//                     behind, from which (and from the new keys) the controller knows its next node.
 //   plan_kernel       Dubins planner, phase by phase: the shot is a single path (warp 0) and the expansion's SAT checks
 //                     (one warp per state) run beside it.
 // Per query the CTA keeps, in its own slice of global memory,
