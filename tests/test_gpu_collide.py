@@ -158,3 +158,52 @@ def test_collide_improved_matches_oracle(ctx):
     plain = O.collide_circles(om, poses)
     assert (want != plain).any() and (want == 0).any() and (want == 1).any()
     m.close()
+
+
+@pytest.mark.parametrize("W,H,res,case", [(301, 203, 0.2, "blocks"), (90, 80, 0.2, "border"), (300, 7, 0.2, "narrow"),
+                                          (160, 120, 1.0, "coarse")])
+def test_collide_filter_path_edge_cases(ctx, W, H, res, case):
+    """Batches of >= 16 384 poses take the float32 filter + exact list kernels (collide.cuh, circles_filter_u8): the verdicts
+    must be the oracle's on poses the filter may not decide itself -- circles straddling the border, poses outside the
+    map, headings beyond its range-reduction limit (|h| > 16), non-finite poses, a map too narrow for its border rule --
+    as on ordinary ones."""
+    import hybrid_path_planning_b200 as hpp
+    from oracle import pyorc as O
+    rng = np.random.default_rng(W + H)
+    if case == "border":
+        occ = np.zeros((H, W), np.int8)
+        occ[H // 2, W // 2] = 100
+    else:
+        occ = block_map(W, H, 0.06, 3, seed=W)
+    m = hpp.Map(ctx, occ, res)
+    om = O.Map(occ, res)
+    n = 40000
+    ex, ey = W * om.res / 2, H * om.res / 2
+    poses = np.empty((n, 3))
+    poses[:, 0] = rng.uniform(-ex - 3.0, ex + 3.0, n)          # a band of 3 m around the map is outside
+    poses[:, 1] = rng.uniform(-ey - 3.0, ey + 3.0, n)
+    poses[:, 2] = rng.uniform(-np.pi, np.pi, n)
+    k = n // 4                                                  # a quarter hugs the four borders
+    side = rng.integers(0, 4, k)
+    d = rng.uniform(-1.5, 1.5, k)
+    t = rng.uniform(-1, 1, k)
+    poses[:k, 0] = np.where(side == 0, -ex + d, np.where(side == 1, ex + d, t * ex))
+    poses[:k, 1] = np.where(side == 2, -ey + d, np.where(side == 3, ey + d, t * ey))
+    poses[k:k + 2000, 2] = rng.uniform(-40.0, 40.0, 2000)       # headings the filter hands to the exact path
+    poses[k + 2000:k + 2100, 2] = rng.choice([16.0, -16.0, 15.999999, 16.000001, np.pi, -np.pi], 100)
+    finite = np.ones(n, bool)
+    bad = rng.choice(np.arange(k + 2100, n), 60, replace=False)
+    poses[bad[:20], 0] = np.nan
+    poses[bad[20:30], 1] = np.inf
+    poses[bad[30:40], 0] = -np.inf
+    poses[bad[40:50], 2] = np.nan
+    poses[bad[50:60], 2] = np.inf
+    finite[bad] = False
+    got = m.collide_circles(poses)
+    want = O.collide_circles(om, poses[finite])
+    assert np.array_equal(got[finite], want), f"{(got[finite] != want).sum()} verdicts differ ({case})"
+    assert case == "narrow" or 0.05 < want.mean() < 0.999   # (a 1.4 m wide map holds no free pose of a 1.9 m wide car)
+    # non-finite poses: the same verdict from the filter path as from the one-pass exact kernel (small batches)
+    small = m.collide_circles(poses[bad])
+    assert np.array_equal(got[bad], small)
+    m.close()

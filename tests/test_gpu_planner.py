@@ -4,12 +4,15 @@ run() -- which itself is bit-identical to the compiled reference (tests/test_ora
 Discrete outcomes (success/failure, iteration count, termination by shot, number of states, cell ids) must be
 identical; continuous ones within 1e-9 (CUDA vs glibc trigonometry), path cost within 1e-9 relative (north_star asks
 for 1e-4).  Every returned path must be collision-free under the oracle's own collision check."""
+import os
+
 import numpy as np
 import pytest
 
 from tests.common import block_map, parking_map, random_poses
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _free_pairs(om, n, seed, variant):
@@ -155,3 +158,43 @@ def test_plan_batch_other_planner_parameters(ctx, variant, path_length, step):
             np.testing.assert_allclose(tr[:, :3], w["traj"][:, :3], rtol=0, atol=1e-9)
     assert same >= 16 and solved >= 5
     m.close()
+
+
+def test_two_pass_batch_equals_one_pass(tmp_path):
+    """Batches of more than 32 queries per SM are planned in two passes (a query that passes HPP_PLAN_BUDGET iterations is set
+    aside and run again, from its start, in the second pass): same plans and trajectories as one pass, also with a budget
+    so small that most queries take the detour.  The variables are read once per process, hence the child processes."""
+    import json
+    import subprocess
+    import sys
+    script = tmp_path / "two_pass.py"
+    script.write_text('''
+import sys, json, hashlib
+sys.path.insert(0, %r)
+import numpy as np
+import hybrid_path_planning_b200 as hpp
+from tests.common import parking_map, random_poses
+occ = parking_map(256, seed=4)
+ctx = hpp.Context(0)
+m = hpp.Map(ctx, occ, 0.2)
+cand = random_poses(60000, 256, 256, margin=3.0, seed=21)
+free = cand[m.collide_circles(cand) == 0]
+n = 5000                                   # > 32 x 148 queries: the two-pass shape
+starts, goals = free[:n], free[n:2 * n]
+plans, traj = m.plan_batch(hpp.VARIANT_RS, starts, goals, traj_cap=1 << 21)
+h = hashlib.sha1()
+for p in plans:                            # trajectories in query order (their offsets depend on the finishing order)
+    o = int(p["traj_offset"])
+    h.update(traj[o:o + int(p["n_states"])].tobytes())
+print(json.dumps({"n": n, "solved": int((plans["n_states"] > 1).sum()), "iters": int(plans["iterations"].sum()),
+                  "max_iters": int(plans["iterations"].max()), "via": int(plans["via_shot"].sum()),
+                  "cost": float(plans["cost"].sum()), "states": int(plans["n_states"].sum()), "traj": h.hexdigest()}))
+''' % ROOT)
+    out = {}
+    for budget in ("0", "64", "2"):
+        env = dict(os.environ, HPP_PLAN_BUDGET=budget)
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[budget] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["0"]["solved"] > 4000 and out["0"]["max_iters"] > 64
+    assert out["64"] == out["0"] and out["2"] == out["0"], out
