@@ -1173,7 +1173,10 @@ hpp_status run_batch(hpp_map *m, int variant, const int32_t *goal_xy, size_t n_f
   a.n_tiles = n_tiles;
   a.n_fields = (int)n_fields;
   // window width: wide windows = fewer rounds (latency of a lone field), narrow = fewer re-evaluations (throughput)
-  a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 768.0 : (n_fields < 64 ? 128.0 : 64.0)) : 2.0 * C::T);
+  // Re-measured on the final kernel (tools/heur_big_sweep.sh, tools/heur_small_sweep.sh): 148 fields of 4096^2, one CTA per
+  // field: 117.4 (48) / 113.9 (64) / 112.1 (96) / 111.4 (128) / 113.1 (160) / 118.6 (256) / 141.7 ms (768); 2 048 fields of
+  // 256^2: parking map 11.4 (64) / 10.7 (128) / 10.3 (256), cluttered map 12.1 / 12.0 / 13.0 ms.
+  a.delta = env_double("HPP_HEUR_DELTA", NB == 1 ? (n_fields < 8 ? 768.0 : 128.0) : 2.0 * C::T);
   a.delta_in = env_double("HPP_HEUR_DELTA_IN", 32.0);
   a.lpt = (int)env_double("HPP_HEUR_LPT", 1);
   // the fields as one (W, H, n_fields) fp64 tensor for the TMA: a tile with its halo is one 38 x 34 box.  Needs 16-byte

@@ -9,13 +9,17 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hybrid_path_planning_b200 as hpp  # noqa: E402
-from tests.common import cfg3_map  # noqa: E402
+from tests.common import cfg3_map, parking_map  # noqa: E402
 
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nf = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 variant = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 occ, goal = cfg3_map(side, seed=1)
+if os.environ.get("PROBE_MAP") == "parking":   # the cfg5 map class
+    occ = parking_map(side, seed=0)
+    fr = np.argwhere(occ == 0)
+    goal = (int(fr[len(fr) // 2][1]), int(fr[len(fr) // 2][0]))
 ctx = hpp.Context(0)
 m = hpp.Map(ctx, occ, 0.2)
 rng = np.random.default_rng(0)
