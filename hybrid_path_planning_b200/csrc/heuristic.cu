@@ -598,8 +598,10 @@ __device__ __forceinline__ unsigned long long warp_visit_tile(const heur_args &a
 // shared memory) gives +6 % throughput when every field has its own CTA -- RS only, the Dubins tiles also hold the
 // class bytes and do not fit 20 times.
 
+// (the 4-warp CTAs are meant to sit five to an SM: without the second launch bound the compiler took 200 registers and the
+// driver a small shared-memory carve-out, and ncu showed TWO resident CTAs = 8 warps per SM, issue slots 27 % busy)
 template <int VARIANT, int WT_WARPS>
-__global__ void __launch_bounds__(WT_WARPS * 32, 1) heur_warp_kernel(const __grid_constant__ heur_args a) {
+__global__ void __launch_bounds__(WT_WARPS * 32, WT_WARPS == 4 ? 5 : 1) heur_warp_kernel(const __grid_constant__ heur_args a) {
   using C = tile_cfg<1>;
   constexpr int S = C::S, ROWS = C::ROWS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1080,6 +1082,8 @@ hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
                : (many ? (const void *)heur_warp_kernel<VARIANT, (VARIANT == HPP_VARIANT_RS ? 20 : 16)>
                        : (const void *)heur_warp_kernel<VARIANT, 16>);
   HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // all of the SM's shared memory: five 4-warp CTAs (or one 20-warp CTA) need 207 KB of it
+  HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
   HPP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) HPP_FAIL(c, HPP_ERR_CUDA, "heuristic kernel does not fit on an SM (%zu B shared)", smem);
