@@ -1065,14 +1065,17 @@ double env_double(const char *name, double dflt) {
 template <int NB, int VARIANT>
 hpp_status launch_persist(hpp_ctx *c, heur_args &a, int ctas_per_field_hint) {
   using C = tile_cfg<NB>;
-  // warp-tile kernel: 20 warps per CTA when every field gets its own CTA (throughput), else 16 (latency).  Small maps
-  // (a wave front of a few tiles: most of a big CTA's warps would idle) with many fields get 4-warp CTAs, five per SM,
-  // so that five fields share an SM instead of one.
+  // warp-tile kernel: 20 warps per CTA when every field gets its own CTA (throughput), else 16 (latency).  Batches of at
+  // least two fields per SM on maps up to 2048^2 get 4-warp CTAs, five per SM, so that five fields share an SM instead
+  // of one: the round of a 4-warp CTA waits for the slowest of 4 tiles, not of 20, and a small map's wave front (a few
+  // tiles) leaves most of a big CTA's warps idle.
   const bool many = NB == 1 && VARIANT == HPP_VARIANT_RS && ctas_per_field_hint <= 1 && a.n_fields >= c->sm_count / 2;
   const int warps_env = (int)env_double("HPP_HEUR_WARPS", 0);
   const bool small = NB == 1 && ctas_per_field_hint <= 1 &&
-                     (warps_env ? warps_env == 4 : (a.n_fields >= 4 * c->sm_count && a.n_tiles <= 256));
-  // (up to 512^2 cells; measured: 128^2 2.3x, 256^2 1.5x, 512^2 1.06x, 1024^2 0.88x)
+                     (warps_env ? warps_env == 4 : (a.n_fields >= 2 * c->sm_count && a.n_tiles <= 4096));
+  // (measured against the 20-warp CTAs with five resident 4-warp CTAs per SM: 2 048 fields of 256^2 6.5 vs 14.7 ms;
+  // 400 x 512^2 7.6 vs 9.1; 300 x 1024^2 21.1 vs 25.5; 600 x 1024^2 33.3 vs 43.0; 600 x 2048^2 131.6 vs 145.8;
+  // 600 x 4096^2 534 vs 540 ms -- the same, so the big maps keep the 20-warp CTAs; 148 x 4096^2: 139 vs 112)
   const int WT_WARPS = small ? 4 : (many ? 20 : 16);
   const int threads = NB == 1 ? WT_WARPS * 32 : C::THREADS;
   size_t smem;
