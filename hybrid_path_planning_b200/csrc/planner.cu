@@ -1547,7 +1547,7 @@ static hpp_status plan_batch_impl(hpp_map *const *maps, size_t n_maps, const uin
       if (plan_smem_bytes > 48 * 1024)
         HPP_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem_bytes));
     }
-    // cached per kernel shape (the RS slots hold the pipelined kernel's two builds; HPP_PLAN_PIPE is read once)
+    // cached per kernel shape (the RS slots hold the pipelined kernel's two builds; HPP_PLAN_PIPE_NW is read once)
     const int occ_slot = pipe ? (plan_warps == 9 ? 0 : 1)
                               : variant * 2 + (plan_warps == PLAN_WARPS_LONE ? 1 : 0);
     int occ_blocks = c->plan_occ_blocks[occ_slot];
