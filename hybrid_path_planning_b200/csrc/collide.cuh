@@ -162,8 +162,9 @@ __device__ __forceinline__ int circle_hits_u8(const hpp_geom &g, const uint8_t *
 //  * The layer is an exact Euclidean distance transform times the resolution, so neighbouring taps differ by at most
 //    res (1 + 2^-19) -- clamped at 255 or not -- and |F(p') - F(p)| <= res (1 + 2^-19) (|du| + |dv|) for a position
 //    error (du, dv) in cells.
-//  * The float32 position is off by at most E = 2^-23 D + C (e_sc + 2^-21) cells per axis: D = max(W, H) + 4 bounds the
-//    index coordinate (its cast and the final subtraction round by half an ulp each), C = max_k (|cx_k| + |cy_k|) / res
+//  * The float32 position is off by at most E = 2^-22 D + C (e_sc + 2^-21) cells per axis: D = max(W, H) + 4 bounds the
+//    index coordinate (its cast and the two fused multiply-adds that add the circle offset round by half an ulp at that
+//    magnitude each: 3 * 2^-24 D <= 2^-22 D), C = max_k (|cx_k| + |cy_k|) / res
 //    is the circle offset in cells, e_sc = 4e-6 bounds sine and cosine: heading cast (|h| <= 16: 9.6e-7), two-constant
 //    range reduction (2.4e-7), clamp to the documented __sinf/__cosf range (5e-7), and their error there (2^-21.41).
 //  * The float32 interpolation itself works in cells on sqrt.approx(d2) (relative error 2^-23; the layer holds
@@ -171,7 +172,7 @@ __device__ __forceinline__ int circle_hits_u8(const hpp_geom &g, const uint8_t *
 // So |res * value32 - value_ref| <= M = 2 res (1 + 2^-19) E + 48 * 2^-24 V + 2^-23 r, and the host passes
 // r_lo = (r - 1.5 M) / res rounded down and r_hi = (r + 1.5 M) / res rounded up: value32 < r_lo means the reference saw
 // value < r, value32 > r_hi means it did not.  A collision on ANY circle is the reference's verdict, so one certain hit decides the pose; a
-// free verdict needs all four circles certainly free.  On the cfg4 map 0.4 % of the poses come back undecided.
+// free verdict needs all four circles certainly free.  On the cfg4 map 0.03-0.06 % of the poses come back undecided.
 struct filt_consts {
   double x0, y0;      // centre of cell (0,0): pos + (0.5 len - 0.5 res)
   double rcp_res;
@@ -339,7 +340,7 @@ static inline filt_margin hpp_filt_margin(const hpp_map *m) {
     if (ck > fm.C) fm.C = ck;
   }
   const double D = (double)(g.W > g.H ? g.W : g.H) + 4.0;
-  fm.E = ldexp(D, -23) + fm.C * (4e-6 + ldexp(1.0, -21));
+  fm.E = ldexp(D, -22) + fm.C * (4e-6 + ldexp(1.0, -21));
   fm.A = 2.0 * g.res * (1.0 + ldexp(1.0, -19)) * fm.E + ldexp(fabs(m->car.cr), -23);
   return fm;
 }
