@@ -252,7 +252,7 @@ __device__ __forceinline__ int circles_filter_f32(const hpp_geom &g, const circ_
   __sincosf(hr, &s, &c);
   const float ax = (float)((cc.fx0 - x) * g.rcp_res), ay = (float)((cc.fy0 - y) * g.rcp_res);
   float fu[4], fv[4];
-  int base[4];
+  long base[4];  // (a 65 534^2 layer has more than 2^31 cells)
   bool inside = true;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -263,7 +263,7 @@ __device__ __forceinline__ int circles_filter_f32(const hpp_geom &g, const circ_
     inside = inside && (unsigned)(il - 2) <= (unsigned)(g.W - 6) && (unsigned)(jl - 2) <= (unsigned)(g.H - 6);
     fu[k] = u - (tu - 12582912.f);
     fv[k] = v - (tv - 12582912.f);
-    base[k] = jl * g.W + il;
+    base[k] = (long)jl * g.W + il;
   }
   if (!inside) return 2;
   float f[4][4];
